@@ -1,0 +1,130 @@
+/*
+ * b200seg -- C ABI of the B200-native (sm_100a) Lovasz-Softmax + confusion-matrix mIoU hot path.
+ *
+ * This header is the drop-in boundary.  Each entry point names the reference interface it replaces
+ * (paths relative to RViMLab/MICCAI2021_Cataract_semantic_segmentation).  The reference has no FFI of
+ * its own (it is pure PyTorch); INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer except `bytes`/`info` outputs is a DEVICE pointer owned by the caller
+ *     (on the PyTorch side: tensors from the caching allocator, workspace included);
+ *   - every call is asynchronous on `stream` (pass torch.cuda.current_stream().cuda_stream);
+ *     no internal allocation, no host synchronisation, no device switch;
+ *   - return value: 0 = ok, <0 = invalid argument (B200SEG_E_*), >0 = cudaError_t of a failed launch;
+ *     b200seg_last_error() returns a thread-local message for the last non-zero return;
+ *   - logits / prediction: fp32, contiguous NCHW, `plane` = H*W elements per (n, c) plane;
+ *   - labels: contiguous [N, H, W] of dtype `label_dtype`; values are compared after saturation to int32;
+ *   - limits: 1 <= n_classes <= 32, n_images*plane < 2^30, n_images*plane*n_classes < 2^31.
+ */
+#ifndef B200SEG_H_
+#define B200SEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEG_VERSION 1
+
+/* label dtypes */
+#define B200SEG_LABEL_U8 0
+#define B200SEG_LABEL_I32 1
+#define B200SEG_LABEL_I64 2
+
+/* "no such label" for filter_label / drop_label */
+#define B200SEG_NO_LABEL INT64_MIN
+
+/* negative return codes */
+#define B200SEG_E_INVALID (-1)   /* bad argument (null pointer, size out of range, unknown dtype) */
+#define B200SEG_E_WORKSPACE (-2) /* workspace too small or misaligned */
+
+/* bits of the device-side status word (`status`, int32, OR-ed into by kernels; caller zeroes it) */
+#define B200SEG_STATUS_LABEL_OOB 1 /* a label outside [0, C) other than drop_label reached the confusion matrix
+                                       (the reference's one_hot raises RuntimeError there) */
+#define B200SEG_STATUS_SPIN_TIMEOUT 2 /* internal chained-scan watchdog fired (results invalid; a bug) */
+
+int b200seg_version(void);
+const char* b200seg_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Lovasz-Softmax  --  replaces LovaszSoftmax.forward + its autograd backward
+ *   reference: losses/LovaszSoftmax.py:19-32 (forward), :34-61 (lovasz_softmax_flat),
+ *              :63-80 (flatten_probabilities), :83-95 (lovasz_grad), :102-120 (mean)
+ *
+ *   per_image     LovaszSoftmax.py:14,27-29   0 = one loss over the whole batch, 1 = mean of per-image losses
+ *   filter_label  LovaszSoftmax.py:15,74-80   `classes_to_ignore`: pixels with this label are removed;
+ *                                             B200SEG_NO_LABEL = keep every pixel
+ *   keep_absent   LovaszSoftmax.py:53         0 = 'present' (skip classes without foreground),
+ *                                             1 = 'all' / explicit list (absent classes contribute max p_c)
+ *   class_mask    LovaszSoftmax.py:46         bit c set = class c is summed ('all'/'present': all C bits)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Bytes of caller-provided scratch for one forward(+backward) call; sized for the worst case in which every
+ * (pixel, class) pair is a sort candidate.  The same workspace must be handed, untouched, to backward. */
+int b200seg_lovasz_workspace_bytes(int32_t n_images, int32_t n_classes, int64_t plane, int32_t per_image,
+                                   size_t* bytes);
+
+/* loss_out[0] (device, fp32) <- Lovasz-Softmax loss.
+ * If cm != NULL the confusion matrix of (argmax_c logits, labels) is accumulated into cm[C*C] (int64,
+ * cm[pred*C+gt]) in the same pass over the logits (fused metrics; see b200seg_confmat_accumulate for
+ * drop_label / status semantics).  `status` may be NULL only if cm is NULL.
+ * need_grad = 0 skips the work only backward needs (validation under torch.no_grad()). */
+int b200seg_lovasz_forward(const float* logits, const void* labels, int32_t label_dtype,
+                           int32_t n_images, int32_t n_classes, int64_t plane,
+                           int32_t per_image, int64_t filter_label, int32_t keep_absent, uint32_t class_mask,
+                           int32_t need_grad, void* workspace, size_t workspace_bytes,
+                           float* loss_out, int64_t* cm, int64_t cm_drop_label, int32_t* status, void* stream);
+
+/* dlogits[N,C,H,W] <- grad_out[0] * d loss / d logits, using the state forward left in `workspace`.
+ * Same logits / labels / shape / mode arguments as the forward call.  grad_out is a DEVICE scalar. */
+int b200seg_lovasz_backward(const float* logits, const void* labels, int32_t label_dtype,
+                            int32_t n_images, int32_t n_classes, int64_t plane,
+                            int32_t per_image, int64_t filter_label, int32_t keep_absent, uint32_t class_mask,
+                            const void* workspace, size_t workspace_bytes,
+                            const float* grad_out, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Confusion matrix  --  replaces t_get_confusion_matrix
+ *   reference: utils/torch_utils.py:221-241 (torch), utils/metrics.py:5-25 (numpy twin)
+ *
+ * cm[pred*C + gt] += #{pixels: argmax_c prediction == pred, label == gt}, int64, accumulated in place
+ * (the reference's `existing_matrix` argument).  argmax takes the first maximum; NaN counts as maximum.
+ * drop_label: pixels with this label are skipped (the ignore column the reference slices off for
+ * C in {17, 25}); any other label outside [0, C) sets B200SEG_STATUS_LABEL_OOB in *status and is skipped.
+ * ------------------------------------------------------------------------------------------------ */
+int b200seg_confmat_accumulate(const float* prediction, const void* labels, int32_t label_dtype,
+                               int32_t n_images, int32_t n_classes, int64_t plane,
+                               int64_t drop_label, int64_t* cm, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * IoU / accuracy summary on the device  --  replaces the C x C arithmetic of
+ *   t_get_mean_iou / t_get_miou (utils/torch_utils.py:274-332) and t_get_pixel_accuracy (:259-271)
+ *
+ * iou_out[C] <- diag / (colsum + rowsum - diag) in fp32 with 0/0 -> 0 (:321-327);
+ * summary_out[0] = mean IoU over the classes whose bit is set in miou_mask, [1] = PA, [2] = PAC,
+ * [3 + k] = mean IoU over set k of `category_masks[n_sets]` (anatomies / instruments / rare ...).
+ * Sums are formed in int64 and converted once, so they equal the reference's fp32 sums whenever those are
+ * exact (every partial sum < 2^24).
+ * ------------------------------------------------------------------------------------------------ */
+int b200seg_metrics_from_confmat(const int64_t* cm, int32_t n_classes, uint32_t miou_mask,
+                                 const uint32_t* category_masks /* host pointer */, int32_t n_sets,
+                                 float* iou_out, float* summary_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Test hook: the segmented stable radix sort used inside b200seg_lovasz_forward, exposed so tests can
+ * compare it bit for bit with a stable CPU sort.  Segment s occupies [s*capacity, s*capacity + counts[s])
+ * of keys_in/vals_in (uint32); keys are sorted ascending on their low `key_bits[s]` bits (1..30), ties keep
+ * input order.  Output lands in keys_out/vals_out with the same segment layout.  The four arrays must not
+ * overlap; keys_in/vals_in are clobbered.  `scratch` from b200seg_sort_scratch_bytes.
+ * ------------------------------------------------------------------------------------------------ */
+int b200seg_sort_scratch_bytes(int32_t n_segments, int64_t capacity, size_t* bytes);
+int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                          const uint32_t* counts, const uint32_t* key_bits, int32_t n_segments, int64_t capacity,
+                          void* scratch, size_t scratch_bytes, int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H_ */

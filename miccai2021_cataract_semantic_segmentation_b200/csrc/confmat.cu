@@ -1,0 +1,207 @@
+// Confusion-matrix accumulation with fused argmax, and the C x C IoU / accuracy summary, for sm_100a.
+// Replaces utils/torch_utils.py:221-241 (t_get_confusion_matrix: transpose copy + argmax + two int64 one-hots +
+// fp32 GEMM) and the arithmetic of :259-332 (t_get_pixel_accuracy, t_get_miou) of the reference.
+//
+// One streaming pass over the logits (4*C + label bytes per pixel, the roofline of this path): every thread takes
+// four consecutive pixels with 128-bit loads per class plane, keeps the running first-maximum, and adds
+// (pred*C + label) to a shared-memory histogram private to the CTA.  Adds are warp-aggregated with match.any so
+// blocky real label maps (whole warps hitting one bin) cost one shared atomic per distinct bin, not 32 serialised
+// ones.  CTAs are persistent (a few per SM) and flush non-zero bins to the int64 matrix once at the end.
+#include "b200seg.h"
+#include "common.cuh"
+
+#define CM_TPB 256
+
+struct ConfmatParams {
+    const float* pred;
+    const void* labels;
+    int N, C;
+    long long HW;
+    int has_drop, drop;
+    unsigned long long* cm;
+    int* status;
+};
+
+__device__ __forceinline__ void cm_add(u32* s_cm, u32 bin) {
+    const u32 m = __match_any_sync(FULL_MASK, bin);
+    if (bin != 0xFFFFFFFFu && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(s_cm + bin, (u32)__popc(m));
+}
+__device__ __forceinline__ u32 cm_bin(const ConfmatParams& p, int lab, int arg, int C, u32& oob) {
+    if (p.has_drop && lab == p.drop) return 0xFFFFFFFFu;
+    if ((unsigned)lab >= (unsigned)C) { oob = 1; return 0xFFFFFFFFu; }
+    return (u32)(arg * C + lab);
+}
+
+template <int CT, typename LT>
+__global__ void __launch_bounds__(CM_TPB) confmat_kernel_v4(ConfmatParams p) {
+    __shared__ u32 s_cm[B200SEG_MAX_CLASSES * B200SEG_MAX_CLASSES];
+    const int tid = threadIdx.x;
+    constexpr int TILE_PX = CM_TPB * 4;
+    const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
+    const long long ntiles = tpi * p.N;
+    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+    for (int i = tid; i < CT * CT; i += CM_TPB) s_cm[i] = 0;
+    __syncthreads();
+    u32 oob = 0;
+    for (long long t = t0; t < t1; ++t) {
+        const int n = (int)(t / tpi);
+        const long long q0 = (t - (long long)n * tpi) * TILE_PX + tid * 4;
+        u32 bin[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (q0 < p.HW) {
+            const float* lp = p.pred + (size_t)n * CT * p.HW + q0;
+            float4 v[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) v[c] = ld_stream4(lp + (size_t)c * p.HW);
+            int lab[4];
+            load_labels4<LT>(p.labels, (size_t)n * p.HW + q0, lab);
+            float best[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+            int arg[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 1; c < CT; ++c) {
+                argmax_step(v[c].x, c, best[0], arg[0]);
+                argmax_step(v[c].y, c, best[1], arg[1]);
+                argmax_step(v[c].z, c, best[2], arg[2]);
+                argmax_step(v[c].w, c, best[3], arg[3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bin[j] = cm_bin(p, lab[j], arg[j], CT, oob);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cm_add(s_cm, bin[j]);
+    }
+    __syncthreads();
+    for (int i = tid; i < CT * CT; i += CM_TPB)
+        if (s_cm[i]) atomicAdd(p.cm + i, (unsigned long long)s_cm[i]);
+    if (oob) atomicOr(p.status, STATUS_LABEL_OOB);
+}
+
+template <typename LT>
+__global__ void __launch_bounds__(CM_TPB) confmat_kernel_generic(ConfmatParams p) {
+    __shared__ u32 s_cm[B200SEG_MAX_CLASSES * B200SEG_MAX_CLASSES];
+    const int tid = threadIdx.x;
+    const int C = p.C;
+    constexpr int TILE_PX = CM_TPB;
+    const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
+    const long long ntiles = tpi * p.N;
+    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+    for (int i = tid; i < C * C; i += CM_TPB) s_cm[i] = 0;
+    __syncthreads();
+    u32 oob = 0;
+    for (long long t = t0; t < t1; ++t) {
+        const int n = (int)(t / tpi);
+        const long long q = (t - (long long)n * tpi) * TILE_PX + tid;
+        u32 bin = 0xFFFFFFFFu;
+        if (q < p.HW) {
+            const float* lp = p.pred + (size_t)n * C * p.HW + q;
+            float best = __ldg(lp);
+            int arg = 0;
+            for (int c = 1; c < C; ++c) argmax_step(__ldg(lp + (size_t)c * p.HW), c, best, arg);
+            bin = cm_bin(p, load_label<LT>(p.labels, (size_t)n * p.HW + q), arg, C, oob);
+        }
+        cm_add(s_cm, bin);
+    }
+    __syncthreads();
+    for (int i = tid; i < C * C; i += CM_TPB)
+        if (s_cm[i]) atomicAdd(p.cm + i, (unsigned long long)s_cm[i]);
+    if (oob) atomicOr(p.status, STATUS_LABEL_OOB);
+}
+
+#define DISPATCH_LABEL(dtype, ...)                                               \
+    switch (dtype) {                                                             \
+        case B200SEG_LABEL_U8: { typedef uint8_t LT; __VA_ARGS__; } break;        \
+        case B200SEG_LABEL_I32: { typedef int32_t LT; __VA_ARGS__; } break;       \
+        case B200SEG_LABEL_I64: { typedef int64_t LT; __VA_ARGS__; } break;       \
+        default: b200seg_set_error("unknown label dtype %d", dtype); return B200SEG_E_INVALID; \
+    }
+
+extern "C" int b200seg_confmat_accumulate(const float* prediction, const void* labels, int32_t label_dtype,
+                                          int32_t n, int32_t c, int64_t hw, int64_t drop_label, int64_t* cm,
+                                          int32_t* status, void* stream) {
+    if (n < 0 || hw < 0 || c < 1 || c > B200SEG_MAX_CLASSES || (long double)n * hw >= (long double)(1u << 30)) {
+        b200seg_set_error("invalid shape: n_images=%d n_classes=%d plane=%lld", n, c, (long long)hw);
+        return B200SEG_E_INVALID;
+    }
+    if (!prediction || !labels || !cm || !status) { b200seg_set_error("null pointer argument"); return B200SEG_E_INVALID; }
+    if ((long long)n * hw == 0) return 0;
+    ConfmatParams p;
+    p.pred = prediction; p.labels = labels; p.N = n; p.C = c; p.HW = hw;
+    p.has_drop = (drop_label != B200SEG_NO_LABEL && drop_label >= INT_MIN && drop_label <= INT_MAX) ? 1 : 0;
+    p.drop = p.has_drop ? (int)drop_label : 0;
+    p.cm = (unsigned long long*)cm; p.status = status;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = b200seg_sm_count();
+    bool v4 = hw % 4 == 0 && ((uintptr_t)prediction & 15) == 0;
+    v4 = v4 && (label_dtype == B200SEG_LABEL_U8 ? ((uintptr_t)labels & 3) == 0 : ((uintptr_t)labels & 15) == 0);
+    if (v4 && (c == 8 || c == 17 || c == 25)) {
+        const long long tiles = (long long)n * ((hw + CM_TPB * 4 - 1) / (CM_TPB * 4));
+        const int grid = (int)(tiles < (long long)sms * 4 ? tiles : (long long)sms * 4);
+        DISPATCH_LABEL(label_dtype, {
+            if (c == 8) confmat_kernel_v4<8, LT><<<grid, CM_TPB, 0, st>>>(p);
+            else if (c == 17) confmat_kernel_v4<17, LT><<<grid, CM_TPB, 0, st>>>(p);
+            else confmat_kernel_v4<25, LT><<<grid, CM_TPB, 0, st>>>(p);
+        });
+    } else {
+        const long long tiles = (long long)n * ((hw + CM_TPB - 1) / CM_TPB);
+        const int grid = (int)(tiles < (long long)sms * 8 ? tiles : (long long)sms * 8);
+        DISPATCH_LABEL(label_dtype, confmat_kernel_generic<LT><<<grid, CM_TPB, 0, st>>>(p));
+    }
+    LAUNCH_CHECK("confmat_kernel");
+    return 0;
+}
+
+// ---- IoU / accuracy summary -----------------------------------------------------------------------------------
+#define MAX_SETS 8
+struct MetricSets { u32 mask[MAX_SETS]; int n; };
+
+__global__ void metrics_kernel(const long long* __restrict__ cm, int C, u32 miou_mask, MetricSets sets,
+                               float* __restrict__ iou_out, float* __restrict__ summary) {
+    __shared__ float s_iou[B200SEG_MAX_CLASSES], s_pac[B200SEG_MAX_CLASSES];
+    __shared__ long long s_diag[B200SEG_MAX_CLASSES], s_row[B200SEG_MAX_CLASSES];
+    const int c = threadIdx.x;
+    if (c < C) {
+        long long row = 0, col = 0;                 // row: prediction totals (sum over dim 1); col: ground-truth totals
+        for (int k = 0; k < C; ++k) { row += cm[c * C + k]; col += cm[k * C + c]; }
+        const long long d = cm[c * C + c];
+        // utils/torch_utils.py:322-327: diag / (sum(dim=0) + sum(dim=1) - diag), NaN -> 0
+        const float den = __fsub_rn(__fadd_rn((float)col, (float)row), (float)d);
+        float iou = __fdiv_rn((float)d, den);
+        if (iou != iou) iou = 0.f;
+        s_iou[c] = iou;
+        iou_out[c] = iou;
+        // utils/torch_utils.py:266-270: correct / max(prediction row sum, 1)
+        s_pac[c] = __fdiv_rn((float)d, row == 0 ? 1.0f : (float)row);
+        s_diag[c] = d; s_row[c] = row;
+    }
+    __syncthreads();
+    if (c == 0) {
+        float acc = 0.f; int cnt = 0;
+        for (int k = 0; k < C; ++k) if ((miou_mask >> k) & 1u) { acc += s_iou[k]; ++cnt; }
+        summary[0] = cnt ? acc / (float)cnt : 0.f;
+        long long dsum = 0, all = 0;
+        float pac = 0.f;
+        for (int k = 0; k < C; ++k) { dsum += s_diag[k]; all += s_row[k]; pac += s_pac[k]; }
+        summary[1] = __fdiv_rn((float)dsum, (float)all);
+        summary[2] = pac / (float)C;
+        for (int s = 0; s < sets.n; ++s) {
+            float a2 = 0.f; int n2 = 0;
+            for (int k = 0; k < C; ++k) if ((sets.mask[s] >> k) & 1u) { a2 += s_iou[k]; ++n2; }
+            summary[3 + s] = n2 ? a2 / (float)n2 : 0.f;
+        }
+    }
+}
+
+extern "C" int b200seg_metrics_from_confmat(const int64_t* cm, int32_t c, uint32_t miou_mask,
+                                            const uint32_t* category_masks, int32_t n_sets, float* iou_out,
+                                            float* summary_out, void* stream) {
+    if (!cm || !iou_out || !summary_out || c < 1 || c > B200SEG_MAX_CLASSES || n_sets < 0 || n_sets > MAX_SETS ||
+        (n_sets > 0 && !category_masks)) {
+        b200seg_set_error("invalid argument to b200seg_metrics_from_confmat");
+        return B200SEG_E_INVALID;
+    }
+    MetricSets sets;
+    sets.n = n_sets;
+    for (int i = 0; i < MAX_SETS; ++i) sets.mask[i] = i < n_sets ? category_masks[i] : 0;
+    metrics_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const long long*)cm, c, miou_mask, sets, iou_out, summary_out);
+    LAUNCH_CHECK("metrics_kernel");
+    return 0;
+}

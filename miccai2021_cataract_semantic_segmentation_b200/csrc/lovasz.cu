@@ -1,0 +1,958 @@
+// Lovasz-Softmax forward + backward for sm_100a.  Replaces losses/LovaszSoftmax.py:19-95 of the reference.
+//
+// Pipeline (all on one stream, no host sync, no allocation):
+//   K1 stats      read logits once: per-pixel softmax max/sum (kept, 8 B/px), per-segment foreground count and
+//                 max key (= min foreground error -> sort threshold), optional fused argmax + confusion matrix
+//   K1c absent    (keep_absent only) max_i p_c(i) for considered classes without foreground
+//   K1b finalize  thresholds, log-thresholds, key widths, class weights 1/n_present(/n_images)
+//   K2 emit       re-read logits: every (pixel, class) with error >= threshold becomes a candidate
+//                 (key = 0x3F800000 - bits(error), value = pixel<<1 | fg), written in pixel order per segment
+//                 (smem bitmask ranks + chained scan across tiles) so a stable sort gives canonical tie order
+//   K3..K4 sort   segmented stable LSD radix sort (sort.cuh)
+//   K5 jaccard    scan of fg flags in sorted order -> Jaccard gradient, loss partials, per-candidate g
+//   K5b loss      mean over present classes (sequential fp32, class order) and over images
+//   K6 backward   re-read logits: dz_k = go * p_k (g_k - sum_j g_j p_j), sparse g gathered per pixel
+//
+// Exactness notes: candidates are a superset of every element with non-zero Jaccard gradient (SURVEY.md §7.3,
+// zero-tail), so pruning changes nothing; p_c is computed by the same inlined fp32 sequence in every pass.
+#include "b200seg.h"
+#include "common.cuh"
+#include "sort.cuh"
+
+#define STATS_TPB 128
+#define EMIT_TPB 256
+#define BWD_TPB 128
+#define JAC_TPB SORT_TPB
+
+enum { TICKET_EMIT = 0, TICKET_JAC = 1, CTRL_STATUS = 8 };
+
+struct LovaszParams {
+    const float* logits;
+    const void* labels;
+    int N, C;
+    long long HW, P, cap;
+    int per_image, has_filter, filter, keep_absent, need_grad;
+    u32 class_mask;
+    int groups, n_seg;
+    // workspace
+    u32* ctrl;
+    u32 *seg_fg, *seg_maxkey, *seg_maxp, *seg_count, *grp_valid, *seg_bits;
+    double* seg_loss;
+    float *seg_thr, *seg_logthr, *seg_w;
+    float *pix_m, *pix_s, *gown, *gbg;
+    u64* emit_state;
+    u32 *keysA, *valsA, *keysB, *valsB;
+    // fused confusion matrix
+    unsigned long long* cm;
+    int has_drop, drop;
+    int* status;
+    float* loss_out;
+};
+
+struct LovaszLayout {
+    size_t ctrl, seg_fg, seg_maxkey, seg_maxp, seg_count, grp_valid, seg_loss, zero_end;
+    size_t seg_thr, seg_logthr, seg_w, seg_bits, emit_state, emit_state_bytes;
+    size_t pix_m, pix_s, gown, keysA, valsA, keysB, valsB, sort_scratch, total;
+    SortScratch sort;
+};
+
+static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
+    LovaszLayout L;
+    const long long P = (long long)N * HW;
+    const int groups = per_image ? N : 1;
+    const size_t S = (size_t)groups * C;
+    const size_t CP = (size_t)C * P;
+    size_t o = 0;
+    L.ctrl = o;       o = align_up(o + 256, 256);
+    L.seg_fg = o;     o = align_up(o + 4 * S, 256);
+    L.seg_maxkey = o; o = align_up(o + 4 * S, 256);
+    L.seg_maxp = o;   o = align_up(o + 4 * S, 256);
+    L.seg_count = o;  o = align_up(o + 4 * S, 256);
+    L.grp_valid = o;  o = align_up(o + 4 * (size_t)groups, 256);
+    L.seg_loss = o;   o = align_up(o + 8 * S, 256);
+    L.zero_end = o;
+    L.seg_thr = o;    o = align_up(o + 4 * S, 256);
+    L.seg_logthr = o; o = align_up(o + 4 * S, 256);
+    L.seg_w = o;      o = align_up(o + 4 * S, 256);
+    L.seg_bits = o;   o = align_up(o + 4 * S, 256);
+    const size_t tiles_max = (size_t)N * (size_t)((HW + EMIT_TPB - 1) / EMIT_TPB);      // VEC=1 tiling is the finest
+    L.emit_state = o; L.emit_state_bytes = 8 * tiles_max * C; o = align_up(o + L.emit_state_bytes, 256);
+    L.pix_m = o;      o = align_up(o + 4 * (size_t)P, 256);
+    L.pix_s = o;      o = align_up(o + 4 * (size_t)P, 256);
+    L.gown = o;       o = align_up(o + 4 * (size_t)P, 256);
+    L.keysA = o;      o = align_up(o + 4 * CP, 256);
+    L.valsA = o;      o = align_up(o + 4 * CP, 256);
+    L.keysB = o;      o = align_up(o + 4 * CP, 256);
+    L.valsB = o;      o = align_up(o + 4 * CP, 256);
+    L.sort = sort_scratch_layout((int)S, (long long)CP);
+    L.sort_scratch = o; o = align_up(o + L.sort.total, 256);
+    L.total = o;
+    return L;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// candidate predicate pieces (shared by K2 and K6 so both passes select exactly the same (pixel, class) pairs)
+// --------------------------------------------------------------------------------------------------------------
+// Conservative log-domain pre-test: a true candidate (p >= thr) always satisfies z >= theta + log(thr).
+__device__ __forceinline__ float pre_theta(float m, float s) {
+    return m + __logf(s) - (1e-3f + 1e-6f * fabsf(m));
+}
+// exact test; err = |fg - p|
+__device__ __forceinline__ bool exact_accept(float z, float m, float s, bool fg, float thr, float& err, float& pr) {
+    pr = sm_prob(z, m, s);
+    if (fg) { err = __fsub_rn(1.0f, pr); return true; }
+    err = pr;
+    return pr >= thr;
+}
+#define THR_INACTIVE 2.0f
+__device__ __forceinline__ bool thr_active(float thr) { return thr <= 1.5f; }
+
+// --------------------------------------------------------------------------------------------------------------
+// K1: stats (+ fused confusion matrix)
+// --------------------------------------------------------------------------------------------------------------
+struct StatsSmem {
+    u32 fg[B200SEG_MAX_CLASSES];
+    u32 key[B200SEG_MAX_CLASSES];
+    u32 valid;
+    u32 oob;
+    u32 cm[B200SEG_MAX_CLASSES * B200SEG_MAX_CLASSES];
+};
+
+__device__ __forceinline__ void stats_flush_group(const LovaszParams& p, StatsSmem& sm, int g) {
+    __syncthreads();
+    const int tid = threadIdx.x;
+    if (tid < p.C) {
+        const size_t seg = (size_t)g * p.C + tid;
+        if (sm.fg[tid]) { atomicAdd(p.seg_fg + seg, sm.fg[tid]); atomicMax(p.seg_maxkey + seg, sm.key[tid]); }
+        sm.fg[tid] = 0; sm.key[tid] = 0;
+    }
+    if (tid == 0) { if (sm.valid) atomicAdd(p.grp_valid + g, sm.valid); sm.valid = 0; }
+    __syncthreads();
+}
+__device__ __forceinline__ void stats_flush_cm(const LovaszParams& p, StatsSmem& sm) {
+    __syncthreads();
+    if (p.cm) {
+        for (int i = threadIdx.x; i < p.C * p.C; i += blockDim.x)
+            if (sm.cm[i]) atomicAdd(p.cm + i, (unsigned long long)sm.cm[i]);
+        if (threadIdx.x == 0 && sm.oob) atomicOr(p.status, STATUS_LABEL_OOB);
+    }
+}
+__device__ __forceinline__ void stats_pixel_tail(const LovaszParams& p, StatsSmem& sm, int lab, float e_lab, float s,
+                                                 int arg, int C, u32& nvalid) {
+    const bool filtered = p.has_filter && lab == p.filter;
+    if (!filtered) {
+        ++nvalid;
+        if ((unsigned)lab < (unsigned)C) {
+            const float pr = __fdiv_rn(e_lab, s);
+            const u32 key = err_key(__fsub_rn(1.0f, pr));
+            atomicAdd(&sm.fg[lab], 1u);
+            atomicMax(&sm.key[lab], key);
+        }
+    }
+    if (p.cm) {
+        if (!(p.has_drop && lab == p.drop)) {
+            if ((unsigned)lab < (unsigned)C) atomicAdd(&sm.cm[arg * C + lab], 1u);
+            else sm.oob = 1;
+        }
+    }
+}
+
+template <int CT, typename LT>
+__global__ void __launch_bounds__(STATS_TPB) stats_kernel_v4(LovaszParams p) {
+    __shared__ StatsSmem sm;
+    const int tid = threadIdx.x;
+    constexpr int TILE_PX = STATS_TPB * 4;
+    const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
+    const long long ntiles = tpi * p.N;
+    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+    for (int i = tid; i < (int)(sizeof(StatsSmem) / 4); i += STATS_TPB) ((u32*)&sm)[i] = 0;
+    __syncthreads();
+    int cur_g = -1;
+    u32 nvalid = 0;
+    for (long long t = t0; t < t1; ++t) {
+        const int n = (int)(t / tpi);
+        const long long q0 = (t - (long long)n * tpi) * TILE_PX + tid * 4;
+        const int g = p.per_image ? n : 0;
+        if (g != cur_g) {
+            if (cur_g >= 0) { if (nvalid) atomicAdd(&sm.valid, nvalid); nvalid = 0; stats_flush_group(p, sm, cur_g); }
+            cur_g = g;
+        }
+        if (q0 >= p.HW) continue;
+        const float* lp = p.logits + (size_t)n * CT * p.HW + q0;
+        float z[CT][4];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float4 v = ld_stream4(lp + (size_t)c * p.HW);
+            z[c][0] = v.x; z[c][1] = v.y; z[c][2] = v.z; z[c][3] = v.w;
+        }
+        int lab[4];
+        const size_t px = (size_t)n * p.HW + q0;
+        load_labels4<LT>(p.labels, px, lab);
+        float mo[4], so[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float m = z[0][j], best = z[0][j];
+            int arg = 0;
+#pragma unroll
+            for (int c = 1; c < CT; ++c) { m = fmaxf(m, z[c][j]); argmax_step(z[c][j], c, best, arg); }
+            float s = 0.f, e_lab = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const float e = sm_exp(z[c][j], m);
+                s = __fadd_rn(s, e);
+                e_lab = (c == lab[j]) ? e : e_lab;
+            }
+            mo[j] = m; so[j] = s;
+            stats_pixel_tail(p, sm, lab[j], e_lab, s, arg, CT, nvalid);
+        }
+        *(float4*)(p.pix_m + px) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+        *(float4*)(p.pix_s + px) = make_float4(so[0], so[1], so[2], so[3]);
+    }
+    if (cur_g >= 0) { if (nvalid) atomicAdd(&sm.valid, nvalid); stats_flush_group(p, sm, cur_g); }
+    stats_flush_cm(p, sm);
+}
+
+// generic: any C <= 32, any plane size / alignment; one pixel per thread, logits re-read from L1/L2
+template <typename LT>
+__global__ void __launch_bounds__(STATS_TPB) stats_kernel_generic(LovaszParams p) {
+    __shared__ StatsSmem sm;
+    const int tid = threadIdx.x;
+    const int C = p.C;
+    constexpr int TILE_PX = STATS_TPB;
+    const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
+    const long long ntiles = tpi * p.N;
+    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+    for (int i = tid; i < (int)(sizeof(StatsSmem) / 4); i += STATS_TPB) ((u32*)&sm)[i] = 0;
+    __syncthreads();
+    int cur_g = -1;
+    u32 nvalid = 0;
+    for (long long t = t0; t < t1; ++t) {
+        const int n = (int)(t / tpi);
+        const long long q = (t - (long long)n * tpi) * TILE_PX + tid;
+        const int g = p.per_image ? n : 0;
+        if (g != cur_g) {
+            if (cur_g >= 0) { if (nvalid) atomicAdd(&sm.valid, nvalid); nvalid = 0; stats_flush_group(p, sm, cur_g); }
+            cur_g = g;
+        }
+        if (q >= p.HW) continue;
+        const float* lp = p.logits + (size_t)n * C * p.HW + q;
+        const size_t px = (size_t)n * p.HW + q;
+        const int lab = load_label<LT>(p.labels, px);
+        float m = __ldg(lp), best = m;
+        int arg = 0;
+        for (int c = 1; c < C; ++c) { const float v = __ldg(lp + (size_t)c * p.HW); m = fmaxf(m, v); argmax_step(v, c, best, arg); }
+        float s = 0.f, e_lab = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float e = sm_exp(__ldg(lp + (size_t)c * p.HW), m);
+            s = __fadd_rn(s, e);
+            e_lab = (c == lab) ? e : e_lab;
+        }
+        p.pix_m[px] = m; p.pix_s[px] = s;
+        stats_pixel_tail(p, sm, lab, e_lab, s, arg, C, nvalid);
+    }
+    if (cur_g >= 0) { if (nvalid) atomicAdd(&sm.valid, nvalid); stats_flush_group(p, sm, cur_g); }
+    stats_flush_cm(p, sm);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K1c: max p_c over the valid pixels of a group, for considered classes without foreground (keep_absent mode)
+//      reference: the loss term of an absent class degenerates to max_i p_c(i) (LovaszSoftmax.py:52-60 with fg == 0)
+// --------------------------------------------------------------------------------------------------------------
+template <typename LT>
+__global__ void __launch_bounds__(256) absent_max_kernel(LovaszParams p) {
+    __shared__ u32 s_max;
+    const int seg = blockIdx.y;
+    const int c = seg % p.C, g = seg / p.C;
+    if (!((p.class_mask >> c) & 1u) || p.seg_fg[seg] > 0 || p.grp_valid[g] == 0) return;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    u32 best = 0;
+    const long long begin = (long long)g * p.cap, end = begin + p.cap;
+    for (long long px = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; px < end;
+         px += (long long)gridDim.x * blockDim.x) {
+        const int lab = load_label<LT>(p.labels, (size_t)px);
+        if (p.has_filter && lab == p.filter) continue;
+        const long long n = px / p.HW, q = px - n * p.HW;
+        const float z = __ldg(p.logits + ((size_t)n * p.C + c) * p.HW + q);
+        const float pr = sm_prob(z, p.pix_m[px], p.pix_s[px]);
+        best = max(best, __float_as_uint(pr));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL_MASK, best, o));
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(&s_max, best);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max) atomicMax(p.seg_maxp + seg, s_max);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K1b: per-group finalisation of the segment table
+// --------------------------------------------------------------------------------------------------------------
+__global__ void finalize_stats_kernel(LovaszParams p) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.groups) return;
+    int nkept = 0;
+    const bool any_valid = p.grp_valid[g] > 0;
+    for (int c = 0; c < p.C; ++c) {
+        const size_t seg = (size_t)g * p.C + c;
+        const u32 fg = p.seg_fg[seg];
+        const bool active = ((p.class_mask >> c) & 1u) && any_valid && (fg > 0 || p.keep_absent);
+        float thr = THR_INACTIVE, logthr = __int_as_float(0x7f800000);
+        u32 bits = 1;
+        if (active) {
+            const u32 thr_bits = fg > 0 ? (ONE_BITS - p.seg_maxkey[seg]) : p.seg_maxp[seg];
+            thr = __uint_as_float(thr_bits);
+            logthr = thr > 0.f ? logf(thr) : __int_as_float(0xff800000);
+            const u32 maxkey = ONE_BITS - thr_bits;
+            bits = maxkey ? (32 - __clz(maxkey)) : 1;
+            ++nkept;
+        }
+        p.seg_thr[seg] = thr;
+        p.seg_logthr[seg] = logthr;
+        p.seg_bits[seg] = bits;
+    }
+    // d(mean)/d(term): the reference's mean() divides only when it averaged more than one value
+    float w = 1.0f;
+    if (p.groups > 1) w = w / (float)p.groups;
+    if (nkept > 1) w = w / (float)nkept;
+    for (int c = 0; c < p.C; ++c) {
+        const size_t seg = (size_t)g * p.C + c;
+        p.seg_w[seg] = thr_active(p.seg_thr[seg]) ? w : 0.f;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K2: candidate emission in pixel order
+// --------------------------------------------------------------------------------------------------------------
+template <int VEC, typename LT>
+__global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
+    constexpr int TILE_PX = EMIT_TPB * VEC;
+    constexpr int WORDS = TILE_PX / 32;
+    constexpr int NWARPS = EMIT_TPB / 32;
+    __shared__ u32 s_mask[B200SEG_MAX_CLASSES][WORDS];
+    __shared__ u32 s_wpre[B200SEG_MAX_CLASSES][WORDS];
+    __shared__ u32 s_tot[B200SEG_MAX_CLASSES];
+    __shared__ u64 s_base[B200SEG_MAX_CLASSES];
+    __shared__ float s_thr[B200SEG_MAX_CLASSES], s_logthr[B200SEG_MAX_CLASSES];
+    __shared__ u32 s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.C;
+    const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
+    const long long ntiles = tpi * p.N;
+    int cur_g = -1;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(p.ctrl + TICKET_EMIT, 1u);
+        __syncthreads();
+        const long long t = s_ticket;
+        if (t >= ntiles) break;
+        const int n = (int)(t / tpi);
+        const long long ti = t - (long long)n * tpi;
+        const int g = p.per_image ? n : 0;
+        if (g != cur_g) {
+            if (tid < C) { s_thr[tid] = p.seg_thr[(size_t)g * C + tid]; s_logthr[tid] = p.seg_logthr[(size_t)g * C + tid]; }
+            cur_g = g;
+        }
+        for (int i = tid; i < B200SEG_MAX_CLASSES * WORDS; i += EMIT_TPB) (&s_mask[0][0])[i] = 0;
+        __syncthreads();
+
+        const long long q0 = ti * TILE_PX + (long long)tid * VEC;
+        const bool inb = q0 < p.HW;
+        const size_t px0 = (size_t)n * p.HW + q0;
+        const float* lp = p.logits + (size_t)n * C * p.HW + q0;
+        float m[VEC], s[VEC];
+        int lab[VEC];
+        u32 acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0;
+        if (inb) {
+            if constexpr (VEC == 4) {
+                const float4 mv = *(const float4*)(p.pix_m + px0), sv = *(const float4*)(p.pix_s + px0);
+                m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+                s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
+                load_labels4<LT>(p.labels, px0, lab);
+            } else {
+                m[0] = p.pix_m[px0]; s[0] = p.pix_s[px0]; lab[0] = load_label<LT>(p.labels, px0);
+            }
+            float theta[VEC];
+            u32 pre[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { theta[j] = pre_theta(m[j], s[j]); pre[j] = 0; }
+#pragma unroll 5
+            for (int c = 0; c < C; ++c) {
+                const float lt = s_logthr[c];
+                float v[VEC];
+                if constexpr (VEC == 4) {
+                    const float4 x = __ldg((const float4*)(lp + (size_t)c * p.HW));
+                    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                } else {
+                    v[0] = __ldg(lp + (size_t)c * p.HW);
+                }
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) pre[j] |= (v[j] >= theta[j] + lt) ? (1u << c) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                if (p.has_filter && lab[j] == p.filter) pre[j] = 0;
+                else if ((unsigned)lab[j] < (unsigned)C && thr_active(s_thr[lab[j]])) pre[j] |= 1u << lab[j];
+                u32 mm = pre[j];
+                while (mm) {
+                    const int c = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    float err, pr;
+                    if (exact_accept(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j], c == lab[j], s_thr[c], err, pr))
+                        acc[j] |= 1u << c;
+                }
+            }
+            u32 uni = 0;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) uni |= acc[j];
+            const int bit0 = tid * VEC;
+            while (uni) {
+                const int c = __ffs(uni) - 1;
+                uni &= uni - 1;
+                u32 nib = 0;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) nib |= ((acc[j] >> c) & 1u) << j;
+                atomicOr(&s_mask[c][bit0 >> 5], nib << (bit0 & 31));
+            }
+        }
+        __syncthreads();
+
+        // exclusive popcount prefix over the words of every class
+        for (int c = warp; c < C; c += NWARPS) {
+            const u32 cnt = lane < WORDS ? __popc(s_mask[c][lane]) : 0;
+            u32 v = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
+            if (lane < WORDS) s_wpre[c][lane] = v - cnt;
+            if (lane == 31) s_tot[c] = v;
+        }
+        __syncthreads();
+
+        // chained scan across tiles: one chain per class (per image in per-image mode)
+        const long long pos = p.per_image ? ti : t;
+        const long long chain_len = p.per_image ? tpi : ntiles;
+        u64* chain0 = p.emit_state + (size_t)(p.per_image ? (long long)n * tpi : 0) * C;
+        if (pos > 0 && lane == 0)
+            for (int c = warp; c < C; c += NWARPS) st_relaxed(chain0 + (size_t)pos * C + c, lb_pack64(LB_AGG, s_tot[c]));
+        for (int c = warp; c < C; c += NWARPS) {
+            const u64 excl = pos > 0 ? lb_lookback64(chain0 + c, pos, (size_t)C, p.status) : 0;
+            if (lane == 0) {
+                const u64 incl = excl + s_tot[c];
+                st_relaxed(chain0 + (size_t)pos * C + c, lb_pack64(LB_INCL, incl));
+                s_base[c] = excl;
+                if (pos == chain_len - 1) p.seg_count[(size_t)g * C + c] = (u32)incl;
+            }
+        }
+        __syncthreads();
+
+        if (inb) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                u32 mm = acc[j];
+                const int bit = tid * VEC + j;
+                while (mm) {
+                    const int c = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    float err, pr;
+                    const bool fg = c == lab[j];
+                    exact_accept(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j], fg, s_thr[c], err, pr);
+                    const u32 rank = s_wpre[c][bit >> 5] + __popc(s_mask[c][bit >> 5] & ((1u << (bit & 31)) - 1u));
+                    const size_t slot = ((size_t)g * C + c) * (size_t)p.cap + (size_t)s_base[c] + rank;
+                    p.keysA[slot] = err_key(err);
+                    p.valsA[slot] = ((u32)(px0 + j) << 1) | (fg ? 1u : 0u);
+                }
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K5: Jaccard gradient over the sorted candidates      reference: lovasz_grad, losses/LovaszSoftmax.py:83-95
+// --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(JAC_TPB) jaccard_kernel(LovaszParams p, SortArgs a) {
+    __shared__ u32 s_wfg[SORT_WARPS];
+    __shared__ double s_red[SORT_WARPS];
+    __shared__ u32 s_ticket;
+    __shared__ u64 s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 le_mask = lane == 31 ? FULL_MASK : ((2u << lane) - 1u);
+    const u32 total_tiles = a.tile_start[a.n_seg];
+    const u32* keys = a.keys[1];
+    const u32* vals = a.vals[1];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(p.ctrl + TICKET_JAC, 1u);
+        __syncthreads();
+        const u32 t = s_ticket;
+        if (t >= total_tiles) break;
+        const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
+        const u32 tis = t - a.tile_start[seg];
+        const u32 off = tis * SORT_TILE;
+        const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
+        const size_t base = (size_t)seg * a.cap + off;
+        const int c = seg % p.C;
+        const float gts = (float)p.seg_fg[seg];
+        const float w = p.seg_w[seg];
+
+        u32 key[SORT_KPT], val[SORT_KPT];
+        unsigned short floc[SORT_KPT];
+        const u32 wbase = warp * (32 * SORT_KPT) + lane;
+        u32 run = 0;
+#pragma unroll
+        for (int k = 0; k < SORT_KPT; ++k) {
+            const u32 idx = wbase + k * 32;
+            const bool valid = idx < n;
+            key[k] = valid ? keys[base + idx] : 0;
+            val[k] = valid ? vals[base + idx] : 0;
+            const u32 b = __ballot_sync(FULL_MASK, valid && (val[k] & 1u));
+            floc[k] = (unsigned short)(run + __popc(b & le_mask));
+            run += __popc(b);
+        }
+        if (lane == 0) s_wfg[warp] = run;
+        __syncthreads();
+        u32 wexcl = 0, ttot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < SORT_WARPS; ++w2) { const u32 x = s_wfg[w2]; if (w2 < warp) wexcl += x; ttot += x; }
+        if (warp == 0) {
+            u64* chain = a.lb_chain + (t - tis);
+            if (tis > 0 && lane == 0) st_relaxed(chain + tis, lb_pack64(LB_AGG, ttot));
+            const u64 excl = tis > 0 ? lb_lookback64(chain, tis, 1, p.status) : 0;
+            if (lane == 0) { st_relaxed(chain + tis, lb_pack64(LB_INCL, excl + ttot)); s_excl = excl; }
+        }
+        __syncthreads();
+        const u32 fbase = (u32)s_excl + wexcl;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < SORT_KPT; ++k) {
+            const u32 idx = wbase + k * 32;
+            if (idx < n) {
+                const u32 i = off + idx;                  // position in the segment's sorted order
+                const u32 fgi = val[k] & 1u;
+                const u32 F = fbase + floc[k];            // foreground among positions 0..i
+                const u32 B = i + 1 - F;                  // background among positions 0..i
+                const float J = 1.0f - __fdiv_rn(gts - (float)F, gts + (float)B);
+                float grad = J;
+                if (i > 0) {
+                    const float Jp = 1.0f - __fdiv_rn(gts - (float)(F - fgi), gts + (float)(B - (1u - fgi)));
+                    grad = __fsub_rn(J, Jp);
+                }
+                const float err = key_err(key[k]);
+                acc += (double)err * (double)grad;
+                if (p.need_grad) {
+                    // d|fg - p|/dp = -sgn(fg - p): fg -> -1, bg -> +1, exactly 0 when the error is 0
+                    const float gv = err > 0.f ? (fgi ? -grad : grad) * w : 0.f;
+                    const u32 px = val[k] >> 1;
+                    if (fgi) p.gown[px] = gv;
+                    else {
+                        const u32 ni = px / (u32)p.HW;
+                        const u32 q = px - ni * (u32)p.HW;
+                        p.gbg[((size_t)ni * p.C + c) * (size_t)p.HW + q] = gv;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < SORT_WARPS; ++w2) tot += s_red[w2];
+            atomicAdd(p.seg_loss + seg, tot);
+        }
+    }
+}
+
+// K5b: loss = mean over groups of (mean over kept classes)      reference: mean(), losses/LovaszSoftmax.py:102-120
+__global__ void loss_finalize_kernel(LovaszParams p) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float total = 0.f;
+    for (int g = 0; g < p.groups; ++g) {
+        float acc = 0.f;
+        int n = 0;
+        for (int c = 0; c < p.C; ++c) {
+            const size_t seg = (size_t)g * p.C + c;
+            if (!thr_active(p.seg_thr[seg])) continue;
+            const float l = (float)p.seg_loss[seg];
+            acc = n ? acc + l : l;
+            ++n;
+        }
+        if (n > 1) acc = acc / (float)n;
+        total = g ? total + acc : acc;
+    }
+    if (p.groups > 1) total = total / (float)p.groups;
+    *p.loss_out = total;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K6: backward      reference: autograd of LovaszSoftmax.forward
+// --------------------------------------------------------------------------------------------------------------
+template <int CT, typename LT>
+__global__ void __launch_bounds__(BWD_TPB) backward_kernel_v4(LovaszParams p, const float* __restrict__ go,
+                                                              float* __restrict__ dlogits) {
+    __shared__ float s_thr[B200SEG_MAX_CLASSES], s_logthr[B200SEG_MAX_CLASSES];
+    const int tid = threadIdx.x;
+    constexpr int TILE_PX = BWD_TPB * 4;
+    const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
+    const long long ntiles = tpi * p.N;
+    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+    const float gsc = __ldg(go);
+    int cur_g = -1;
+    for (long long t = t0; t < t1; ++t) {
+        const int n = (int)(t / tpi);
+        const long long q0 = (t - (long long)n * tpi) * TILE_PX + tid * 4;
+        const int g = p.per_image ? n : 0;
+        if (g != cur_g) {
+            __syncthreads();
+            if (tid < CT) { s_thr[tid] = p.seg_thr[(size_t)g * CT + tid]; s_logthr[tid] = p.seg_logthr[(size_t)g * CT + tid]; }
+            __syncthreads();
+            cur_g = g;
+        }
+        if (q0 >= p.HW) continue;
+        const size_t off = (size_t)n * CT * p.HW + q0;
+        const float* lp = p.logits + off;
+        const float* gb = p.gbg + off;
+        float* dp = dlogits + off;
+        const size_t px = (size_t)n * p.HW + q0;
+        float z[CT][4];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float4 v = ld_stream4(lp + (size_t)c * p.HW);
+            z[c][0] = v.x; z[c][1] = v.y; z[c][2] = v.z; z[c][3] = v.w;
+        }
+        int lab[4];
+        load_labels4<LT>(p.labels, px, lab);
+        const float4 mv = *(const float4*)(p.pix_m + px), sv = *(const float4*)(p.pix_s + px);
+        const float4 gv = *(const float4*)(p.gown + px);
+        const float m[4] = {mv.x, mv.y, mv.z, mv.w}, s[4] = {sv.x, sv.y, sv.z, sv.w}, go4[4] = {gv.x, gv.y, gv.z, gv.w};
+        // sweep 1 (branch-free, unrolled): conservative candidate bits
+        float theta[4];
+        u32 pre[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { theta[j] = pre_theta(m[j], s[j]); pre[j] = 0; }
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float lt = s_logthr[c];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pre[j] |= (z[c][j] >= theta[j] + lt) ? (1u << c) : 0u;
+        }
+        // exact stage on the (few) flagged classes: same predicate as emit_kernel, logits re-read from L1/L2
+        float dot[4], gl[4], nd[4];
+        u32 fix[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool filt = p.has_filter && lab[j] == p.filter;
+            const bool own = !filt && (unsigned)lab[j] < (unsigned)CT && thr_active(s_thr[lab[j] & 31]);
+            const u32 ownbit = (unsigned)lab[j] < (unsigned)CT ? (1u << lab[j]) : 0u;
+            gl[j] = own ? go4[j] : 0.f;
+            float d = 0.f;
+            u32 cm = 0;
+            u32 mm = filt ? 0u : (pre[j] & ~ownbit);
+            while (mm) {
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const float pr = sm_prob(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j]);
+                if (pr >= s_thr[c]) { cm |= 1u << c; d += gb[(size_t)c * p.HW + j] * pr; }
+            }
+            if (own) { d += gl[j] * sm_prob(__ldg(lp + (size_t)lab[j] * p.HW + j), m[j], s[j]); cm |= ownbit; }
+            dot[j] = d; fix[j] = cm;
+            nd[j] = filt ? 0.f : -gsc * d * __fdiv_rn(1.0f, s[j]);
+        }
+        // sweep 2 (branch-free, unrolled): every class gets -go * p_k * dot with the fast exponential ...
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = nd[j] * __expf(z[c][j] - m[j]);
+            st_stream4(dp + (size_t)c * p.HW, make_float4(o[0], o[1], o[2], o[3]));
+        }
+        // ... then the candidate classes are overwritten with the exact go * p_k * (g_k - dot)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            u32 mm = fix[j];
+            while (mm) {
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const float pk = sm_prob(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j]);
+                const float gk = (c == lab[j]) ? gl[j] : gb[(size_t)c * p.HW + j];
+                dp[(size_t)c * p.HW + j] = gsc * pk * (gk - dot[j]);
+            }
+        }
+    }
+}
+
+template <typename LT>
+__global__ void __launch_bounds__(BWD_TPB) backward_kernel_generic(LovaszParams p, const float* __restrict__ go,
+                                                                   float* __restrict__ dlogits) {
+    __shared__ float s_thr[B200SEG_MAX_CLASSES], s_logthr[B200SEG_MAX_CLASSES];
+    const int tid = threadIdx.x;
+    const int C = p.C;
+    constexpr int TILE_PX = BWD_TPB;
+    const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
+    const long long ntiles = tpi * p.N;
+    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+    const float gsc = __ldg(go);
+    int cur_g = -1;
+    for (long long t = t0; t < t1; ++t) {
+        const int n = (int)(t / tpi);
+        const long long q = (t - (long long)n * tpi) * TILE_PX + tid;
+        const int g = p.per_image ? n : 0;
+        if (g != cur_g) {
+            __syncthreads();
+            if (tid < C) { s_thr[tid] = p.seg_thr[(size_t)g * C + tid]; s_logthr[tid] = p.seg_logthr[(size_t)g * C + tid]; }
+            __syncthreads();
+            cur_g = g;
+        }
+        if (q >= p.HW) continue;
+        const size_t off = (size_t)n * C * p.HW + q;
+        const float* lp = p.logits + off;
+        const float* gb = p.gbg + off;
+        float* dp = dlogits + off;
+        const size_t px = (size_t)n * p.HW + q;
+        const int lab = load_label<LT>(p.labels, px);
+        const float m = p.pix_m[px], s = p.pix_s[px];
+        const bool filt = p.has_filter && lab == p.filter;
+        const bool own = !filt && (unsigned)lab < (unsigned)C && thr_active(s_thr[lab & 31]);
+        const float gl = own ? p.gown[px] : 0.f;
+        const float theta = pre_theta(m, s);
+        float d = 0.f;
+        u32 cm = 0;
+        for (int c = 0; c < C; ++c) {
+            const float v = __ldg(lp + (size_t)c * p.HW);
+            if (c == lab) { if (own) d += gl * sm_prob(v, m, s); }
+            else if (!filt && v >= theta + s_logthr[c]) {
+                const float pr = sm_prob(v, m, s);
+                if (pr >= s_thr[c]) { cm |= 1u << c; d += gb[(size_t)c * p.HW] * pr; }
+            }
+        }
+        for (int c = 0; c < C; ++c) {
+            const float v = __ldg(lp + (size_t)c * p.HW);
+            float gk = (c == lab) ? gl : 0.f;
+            if ((cm >> c) & 1u) gk = gb[(size_t)c * p.HW];
+            const float pk = sm_prob(v, m, s);
+            dp[(size_t)c * p.HW] = filt ? 0.f : gsc * pk * (gk - d);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------------------
+static int check_shape(int32_t n, int32_t c, int64_t hw) {
+    if (n < 0 || hw < 0 || c < 1 || c > B200SEG_MAX_CLASSES) {
+        b200seg_set_error("invalid shape: n_images=%d n_classes=%d plane=%lld (need 1 <= n_classes <= %d)", n, c,
+                          (long long)hw, B200SEG_MAX_CLASSES);
+        return B200SEG_E_INVALID;
+    }
+    const long double P = (long double)n * (long double)hw;
+    if (P >= (long double)(1u << 30) || P * c >= (long double)(1ull << 31)) {
+        b200seg_set_error("shape too large: n_images*plane must be < 2^30 and n_images*plane*n_classes < 2^31");
+        return B200SEG_E_INVALID;
+    }
+    return 0;
+}
+
+static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const float* logits, const void* labels,
+                        int32_t n, int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
+                        int32_t keep_absent, uint32_t class_mask) {
+    p.logits = logits; p.labels = labels;
+    p.N = n; p.C = c; p.HW = hw; p.P = (long long)n * hw;
+    p.per_image = per_image ? 1 : 0;
+    p.groups = per_image ? n : 1;
+    p.n_seg = p.groups * c;
+    p.cap = per_image ? hw : p.P;
+    p.has_filter = (filter_label != B200SEG_NO_LABEL && filter_label >= INT_MIN && filter_label <= INT_MAX) ? 1 : 0;
+    p.filter = p.has_filter ? (int)filter_label : 0;
+    p.keep_absent = keep_absent ? 1 : 0;
+    p.class_mask = c == 32 ? class_mask : (class_mask & ((1u << c) - 1u));
+    p.ctrl = (u32*)(ws + L.ctrl);
+    p.seg_fg = (u32*)(ws + L.seg_fg); p.seg_maxkey = (u32*)(ws + L.seg_maxkey); p.seg_maxp = (u32*)(ws + L.seg_maxp);
+    p.seg_count = (u32*)(ws + L.seg_count); p.grp_valid = (u32*)(ws + L.grp_valid); p.seg_bits = (u32*)(ws + L.seg_bits);
+    p.seg_loss = (double*)(ws + L.seg_loss);
+    p.seg_thr = (float*)(ws + L.seg_thr); p.seg_logthr = (float*)(ws + L.seg_logthr); p.seg_w = (float*)(ws + L.seg_w);
+    p.pix_m = (float*)(ws + L.pix_m); p.pix_s = (float*)(ws + L.pix_s); p.gown = (float*)(ws + L.gown);
+    p.emit_state = (u64*)(ws + L.emit_state);
+    p.keysA = (u32*)(ws + L.keysA); p.valsA = (u32*)(ws + L.valsA);
+    p.keysB = (u32*)(ws + L.keysB); p.valsB = (u32*)(ws + L.valsB);
+    p.gbg = (float*)(ws + L.keysA);      // free again once the sort result sits in buffer B
+    p.cm = nullptr; p.has_drop = 0; p.drop = 0;
+    p.status = (int*)(p.ctrl + CTRL_STATUS);
+    p.loss_out = nullptr; p.need_grad = 1;
+    return true;
+}
+
+static bool aligned16(const void* ptr) { return ((uintptr_t)ptr & 15) == 0; }
+static bool vec4_ok(const float* logits, const void* labels, int label_dtype, int64_t hw) {
+    if (hw % 4 != 0 || !aligned16(logits)) return false;
+    if (label_dtype == B200SEG_LABEL_U8) return ((uintptr_t)labels & 3) == 0;
+    return aligned16(labels);
+}
+
+#define DISPATCH_LABEL(dtype, ...)                                               \
+    switch (dtype) {                                                             \
+        case B200SEG_LABEL_U8: { typedef uint8_t LT; __VA_ARGS__; } break;        \
+        case B200SEG_LABEL_I32: { typedef int32_t LT; __VA_ARGS__; } break;       \
+        case B200SEG_LABEL_I64: { typedef int64_t LT; __VA_ARGS__; } break;       \
+        default: b200seg_set_error("unknown label dtype %d", dtype); return B200SEG_E_INVALID; \
+    }
+
+extern "C" int b200seg_lovasz_workspace_bytes(int32_t n, int32_t c, int64_t hw, int32_t per_image, size_t* bytes) {
+    if (!bytes) { b200seg_set_error("bytes is NULL"); return B200SEG_E_INVALID; }
+    if (int rc = check_shape(n, c, hw)) return rc;
+    *bytes = lovasz_layout(n, c, hw, per_image).total;
+    return 0;
+}
+
+extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
+                                      int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
+                                      int32_t keep_absent, uint32_t class_mask, int32_t need_grad, void* workspace,
+                                      size_t workspace_bytes, float* loss_out, int64_t* cm, int64_t cm_drop_label,
+                                      int32_t* status, void* stream) {
+    if (int rc = check_shape(n, c, hw)) return rc;
+    if (!logits || !labels || !workspace || !loss_out || (cm && !status)) {
+        b200seg_set_error("null pointer argument");
+        return B200SEG_E_INVALID;
+    }
+    const LovaszLayout L = lovasz_layout(n, c, hw, per_image);
+    if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
+        b200seg_set_error("workspace too small or not 256-byte aligned: have %zu, need %zu", workspace_bytes, L.total);
+        return B200SEG_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    LovaszParams p;
+    fill_params(p, L, ws, logits, labels, n, c, hw, per_image, filter_label, keep_absent, class_mask);
+    p.loss_out = loss_out;
+    p.need_grad = need_grad ? 1 : 0;
+    p.cm = (unsigned long long*)cm;
+    p.has_drop = (cm_drop_label != B200SEG_NO_LABEL && cm_drop_label >= INT_MIN && cm_drop_label <= INT_MAX) ? 1 : 0;
+    p.drop = p.has_drop ? (int)cm_drop_label : 0;
+    if (status) p.status = status;
+
+    CUDA_TRY(cudaMemsetAsync(ws + L.ctrl, 0, L.zero_end - L.ctrl, st));
+    if (p.P == 0) { CUDA_TRY(cudaMemsetAsync(loss_out, 0, sizeof(float), st)); return 0; }
+    const int sms = b200seg_sm_count();
+    const bool v4 = vec4_ok(logits, labels, label_dtype, hw);
+
+    // K1
+    if (v4 && (c == 8 || c == 17 || c == 25)) {
+        const int grid = sms * 3;
+        DISPATCH_LABEL(label_dtype, {
+            if (c == 8) stats_kernel_v4<8, LT><<<grid, STATS_TPB, 0, st>>>(p);
+            else if (c == 17) stats_kernel_v4<17, LT><<<grid, STATS_TPB, 0, st>>>(p);
+            else stats_kernel_v4<25, LT><<<grid, STATS_TPB, 0, st>>>(p);
+        });
+    } else {
+        DISPATCH_LABEL(label_dtype, stats_kernel_generic<LT><<<sms * 8, STATS_TPB, 0, st>>>(p));
+    }
+    LAUNCH_CHECK("stats_kernel");
+    if (p.keep_absent) {
+        DISPATCH_LABEL(label_dtype, absent_max_kernel<LT><<<dim3(32, p.n_seg), 256, 0, st>>>(p));
+        LAUNCH_CHECK("absent_max_kernel");
+    }
+    finalize_stats_kernel<<<(p.groups + 127) / 128, 128, 0, st>>>(p);
+    LAUNCH_CHECK("finalize_stats_kernel");
+
+    // K2
+    {
+        const int vec = v4 ? 4 : 1;
+        const size_t tiles = (size_t)n * (size_t)((hw + EMIT_TPB * vec - 1) / (EMIT_TPB * vec));
+        CUDA_TRY(cudaMemsetAsync(ws + L.emit_state, 0, 8 * tiles * c, st));
+        const int grid = (int)(tiles < (size_t)sms * 8 ? tiles : (size_t)sms * 8);
+        if (v4) { DISPATCH_LABEL(label_dtype, emit_kernel<4, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
+        else { DISPATCH_LABEL(label_dtype, emit_kernel<1, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
+        LAUNCH_CHECK("emit_kernel");
+    }
+
+    // sort
+    SortArgs a;
+    char* ss = ws + L.sort_scratch;
+    a.keys[0] = p.keysA; a.vals[0] = p.valsA; a.keys[1] = p.keysB; a.vals[1] = p.valsB;
+    a.seg_count = p.seg_count; a.seg_bits = p.seg_bits; a.n_seg = p.n_seg; a.cap = p.cap;
+    a.tile_start = (u32*)(ss + L.sort.tile_start); a.ghist = (u32*)(ss + L.sort.ghist);
+    a.lb[0] = (u32*)(ss + L.sort.lb0); a.lb[1] = (u32*)(ss + L.sort.lb1);
+    a.lb_chain = (u64*)(ss + L.sort.lb_chain); a.tickets = (u32*)(ss + L.sort.tickets);
+    a.status = p.status;
+    if (int rc = sort_enqueue(a, L.sort, ss, st)) return rc;
+
+    // K5
+    jaccard_kernel<<<sms * 4, JAC_TPB, 0, st>>>(p, a);
+    LAUNCH_CHECK("jaccard_kernel");
+    loss_finalize_kernel<<<1, 32, 0, st>>>(p);
+    LAUNCH_CHECK("loss_finalize_kernel");
+    return 0;
+}
+
+extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
+                                       int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
+                                       int32_t keep_absent, uint32_t class_mask, const void* workspace,
+                                       size_t workspace_bytes, const float* grad_out, float* dlogits, void* stream) {
+    if (int rc = check_shape(n, c, hw)) return rc;
+    if (!logits || !labels || !workspace || !grad_out || !dlogits) {
+        b200seg_set_error("null pointer argument");
+        return B200SEG_E_INVALID;
+    }
+    const LovaszLayout L = lovasz_layout(n, c, hw, per_image);
+    if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
+        b200seg_set_error("workspace too small or not 256-byte aligned: have %zu, need %zu", workspace_bytes, L.total);
+        return B200SEG_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    LovaszParams p;
+    fill_params(p, L, (char*)const_cast<void*>(workspace), logits, labels, n, c, hw, per_image, filter_label,
+                keep_absent, class_mask);
+    if (p.P == 0) return 0;
+    const int sms = b200seg_sm_count();
+    const bool v4 = vec4_ok(logits, labels, label_dtype, hw) && aligned16(dlogits);
+    if (v4 && (c == 8 || c == 17 || c == 25)) {
+        const int grid = sms * 3 * 4;
+        DISPATCH_LABEL(label_dtype, {
+            if (c == 8) backward_kernel_v4<8, LT><<<grid, BWD_TPB, 0, st>>>(p, grad_out, dlogits);
+            else if (c == 17) backward_kernel_v4<17, LT><<<grid, BWD_TPB, 0, st>>>(p, grad_out, dlogits);
+            else backward_kernel_v4<25, LT><<<grid, BWD_TPB, 0, st>>>(p, grad_out, dlogits);
+        });
+    } else {
+        DISPATCH_LABEL(label_dtype, backward_kernel_generic<LT><<<sms * 16, BWD_TPB, 0, st>>>(p, grad_out, dlogits));
+    }
+    LAUNCH_CHECK("backward_kernel");
+    return 0;
+}
+
+// ---- test hook: the segmented sort on its own -------------------------------------------------------------------
+extern "C" int b200seg_sort_scratch_bytes(int32_t n_segments, int64_t capacity, size_t* bytes) {
+    if (!bytes || n_segments < 1 || capacity < 0 || (long double)n_segments * capacity >= (long double)(1ull << 31)) {
+        b200seg_set_error("invalid sort shape");
+        return B200SEG_E_INVALID;
+    }
+    *bytes = sort_scratch_layout(n_segments, (long long)n_segments * capacity).total;
+    return 0;
+}
+
+extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                                     const uint32_t* counts, const uint32_t* key_bits, int32_t n_segments,
+                                     int64_t capacity, void* scratch, size_t scratch_bytes, int32_t* status,
+                                     void* stream) {
+    size_t need = 0;
+    if (int rc = b200seg_sort_scratch_bytes(n_segments, capacity, &need)) return rc;
+    if (!keys_in || !vals_in || !keys_out || !vals_out || !counts || !key_bits || !scratch || !status) {
+        b200seg_set_error("null pointer argument");
+        return B200SEG_E_INVALID;
+    }
+    if (scratch_bytes < need || ((uintptr_t)scratch & 255)) {
+        b200seg_set_error("sort scratch too small or misaligned: have %zu, need %zu", scratch_bytes, need);
+        return B200SEG_E_WORKSPACE;
+    }
+    const SortScratch L = sort_scratch_layout(n_segments, (long long)n_segments * capacity);
+    char* ss = (char*)scratch;
+    SortArgs a;
+    a.keys[0] = keys_in; a.vals[0] = vals_in; a.keys[1] = keys_out; a.vals[1] = vals_out;
+    a.seg_count = counts; a.seg_bits = key_bits; a.n_seg = n_segments; a.cap = capacity;
+    a.tile_start = (u32*)(ss + L.tile_start); a.ghist = (u32*)(ss + L.ghist);
+    a.lb[0] = (u32*)(ss + L.lb0); a.lb[1] = (u32*)(ss + L.lb1);
+    a.lb_chain = (u64*)(ss + L.lb_chain); a.tickets = (u32*)(ss + L.tickets);
+    a.status = status;
+    return sort_enqueue(a, L, ss, (cudaStream_t)stream);
+}

@@ -1,0 +1,138 @@
+"""Drop-in ``LovaszSoftmax`` (reference: losses/LovaszSoftmax.py:8-32) backed by the sm_100a kernels.
+
+Same constructor (a config dict read with the reference's four keys), same ``forward(prediction, target)``,
+differentiable w.r.t. ``prediction``; an ``nn.Module`` without parameters or buffers, so checkpoints are unchanged.
+"""
+from __future__ import annotations
+
+import sys
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import _native
+from .class_info import CLASS_INFO
+
+_PRESENT = sys.intern("present")
+
+
+def _resolve_classes(classes_to_consider, n_classes: int):
+    """-> (keep_absent, class_mask).  LovaszSoftmax.py:46,53: 'present' skips classes without foreground; 'all'
+    and explicit lists do not.  The reference tests ``is 'present'`` (identity): the default literal passes, an
+    equal string built at run time (e.g. read from JSON) does not and silently behaves like 'all'.  Reproduced."""
+    full = (1 << n_classes) - 1
+    if isinstance(classes_to_consider, str):
+        if classes_to_consider is _PRESENT:
+            return 0, full
+        if classes_to_consider == "present":
+            warnings.warn("classes_to_consider == 'present' but is not the interned literal (e.g. it came from a JSON "
+                          "file): the reference's `is 'present'` test fails for it and absent classes are NOT skipped; "
+                          "reproducing that. Pass sys.intern('present') or omit the key to skip absent classes.",
+                          stacklevel=3)
+            return 1, full
+        if classes_to_consider == "all":
+            return 1, full
+        raise ValueError("classes_to_consider must be 'present', 'all' or a list of class indices")
+    mask = 0
+    for c in classes_to_consider:
+        c = int(c)
+        if c == n_classes:          # LovaszSoftmax.py:48-49 drops index C for experiments 2/3; out of range otherwise
+            continue
+        if not 0 <= c < n_classes:
+            raise IndexError(f"class index {c} out of range for {n_classes} classes")
+        mask |= 1 << c
+    return 1, mask
+
+
+class _LovaszFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, per_image, filter_label, keep_absent, class_mask, cm, cm_drop, status):
+        lib = _native.load()
+        n, c, h, w = logits.shape
+        hw = h * w
+        need_grad = bool(ctx.needs_input_grad[0])
+        nbytes = _native._sz(0)
+        _native.check(lib.b200seg_lovasz_workspace_bytes(n, c, hw, int(per_image), nbytes), "workspace query")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        _native.check(lib.b200seg_lovasz_forward(
+            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, hw, int(per_image),
+            filter_label, keep_absent, class_mask, int(need_grad), ws.data_ptr(), ws.numel(), loss.data_ptr(),
+            cm.data_ptr() if cm is not None else None, cm_drop,
+            status.data_ptr() if status is not None else None, _native.stream_ptr(logits.device)),
+            "b200seg_lovasz_forward")
+        if need_grad:
+            ctx.save_for_backward(logits, target, ws)
+            ctx.opts = (int(per_image), filter_label, keep_absent, class_mask)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, target, ws = ctx.saved_tensors
+        per_image, filter_label, keep_absent, class_mask = ctx.opts
+        lib = _native.load()
+        n, c, h, w = logits.shape
+        go = grad_out.detach().to(torch.float32).contiguous()
+        dlogits = torch.empty_like(logits)
+        _native.check(lib.b200seg_lovasz_backward(
+            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, per_image, filter_label,
+            keep_absent, class_mask, ws.data_ptr(), ws.numel(), go.data_ptr(), dlogits.data_ptr(),
+            _native.stream_ptr(logits.device)), "b200seg_lovasz_backward")
+        return dlogits, None, None, None, None, None, None, None, None
+
+
+def lovasz_softmax(prediction: torch.Tensor, target: torch.Tensor, per_image: bool = False,
+                   classes_to_ignore=None, keep_absent: int = 0, class_mask: int | None = None,
+                   confusion: torch.Tensor | None = None, confusion_drop_label: int | None = None,
+                   status: torch.Tensor | None = None) -> torch.Tensor:
+    """Functional form.  ``confusion`` (int64 [C, C], accumulated in place) fuses the confusion matrix of
+    (argmax(prediction), target) into the same pass over the logits; ``status`` (int32 [1]) then receives the
+    out-of-range-label flag."""
+    if prediction.dim() != 4:
+        raise ValueError("prediction must be [N, C, H, W]")
+    _native.require_cuda(prediction, target)
+    n, c, h, w = prediction.shape
+    if tuple(target.shape) != (n, h, w):
+        raise ValueError(f"target shape {tuple(target.shape)} does not match prediction {tuple(prediction.shape)}")
+    logits = prediction if prediction.dtype == torch.float32 else prediction.float()
+    logits = logits.contiguous()
+    target = _native.as_label_tensor(target)
+    if class_mask is None:
+        class_mask = (1 << c) - 1
+    filt = _native.NO_LABEL if classes_to_ignore is None else int(classes_to_ignore)
+    drop = _native.NO_LABEL if confusion_drop_label is None else int(confusion_drop_label)
+    if confusion is not None:
+        if confusion.dtype != torch.int64 or tuple(confusion.shape) != (c, c) or not confusion.is_contiguous():
+            raise ValueError("confusion must be a contiguous int64 [C, C] tensor")
+        if status is None:
+            raise ValueError("status (int32 [1]) is required with confusion")
+    return _LovaszFunction.apply(logits, target, bool(per_image), filt, int(keep_absent), int(class_mask),
+                                 confusion, drop, status)
+
+
+class LovaszSoftmax(nn.Module):
+    """Multi-class Lovasz-Softmax loss; reference losses/LovaszSoftmax.py:8-32.
+
+    config keys (LovaszSoftmax.py:12-16): ``experiment`` (required, 1/2/3), ``per_image`` (False),
+    ``classes_to_ignore`` (None; a single label value whose pixels are removed), ``classes_to_consider``
+    ('present' | 'all' | list of class indices).
+
+    Differences from the reference, all supersets: returns a 0-dim zero tensor where the reference returns the
+    python int 0 or an empty tensor (no class kept / every pixel filtered); handles the single-valid-pixel case
+    the reference crashes on (LovaszSoftmax.py:78).  Ties in the per-class sort are broken by ascending pixel
+    index (torch.sort(stable=True)), the canonical order.
+    """
+
+    def __init__(self, config):
+        super().__init__()
+        self.eps = torch.as_tensor(1e-10)
+        self.experiment = config['experiment']
+        self.num_classes = len(CLASS_INFO[self.experiment][1])
+        self.per_image = False if 'per_image' not in config else config['per_image']
+        self.classes_to_ignore = None if 'classes_to_ignore' not in config else config['classes_to_ignore']
+        self.classes_to_consider = _PRESENT if 'classes_to_consider' not in config else config['classes_to_consider']
+
+    def forward(self, prediction: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        keep_absent, mask = _resolve_classes(self.classes_to_consider, prediction.shape[1])
+        return lovasz_softmax(prediction, target, self.per_image, self.classes_to_ignore, keep_absent, mask)

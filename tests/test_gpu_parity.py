@@ -1,0 +1,369 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): the CUDA path, through the C ABI, against the oracle
+and against the golden vectors the reference produced.  Nothing here reads /root/reference.
+
+Tolerances (BASELINE.json north_star): confusion matrix / counts bit-exact; loss |l - l_ref| / |l_ref| <= 1e-5;
+gradient max|g - g_ref| / max|g_ref| <= 1e-5 against the stable-sort reference.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import (confmat_case_ids, confmat_entry, golden, grad_err, lovasz_case_ids, lovasz_entry, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def b200():
+    assert torch.cuda.is_available()
+    import miccai2021_cataract_semantic_segmentation_b200 as pkg
+    from miccai2021_cataract_semantic_segmentation_b200 import _native
+    _native.load()          # hard failure if the CUDA library is missing: no fallback exists
+    return pkg
+
+
+def _cfg(entry):
+    return dict(entry["config"])
+
+
+def _run_lovasz(b200, x, y, cfg, label_dtype=torch.int64):
+    xd = torch.from_numpy(x).cuda().requires_grad_(True)
+    yd = torch.from_numpy(y).cuda().to(label_dtype)
+    loss = b200.LovaszSoftmax(cfg)(xd, yd)
+    loss.backward()
+    return float(loss.item()), xd.grad.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors produced by the reference itself
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", lovasz_case_ids())
+def test_lovasz_matches_reference_golden(b200, name):
+    g = golden()
+    e = lovasz_entry(name)
+    x, y = g.inputs(e)
+    cfg = _cfg(e)
+    if e.get("present_only") is False:
+        cfg["classes_to_consider"] = "".join(["pre", "sent"])     # run-time string: not the interned literal
+    loss, grad = _run_lovasz(b200, x, y, cfg)
+    assert rel_err(loss, g.get("lovasz", name, "loss")) <= LOSS_RTOL
+    assert grad_err(grad, g.get("lovasz", name, "grad")) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("name", confmat_case_ids())
+def test_confmat_matches_reference_golden(b200, name):
+    g = golden()
+    e = confmat_entry(name)
+    x, y = g.inputs(e)
+    tdt = getattr(torch, e["target_dtype"])
+    existing = torch.from_numpy(g.get("confmat", name, "existing")).cuda() if e["has_existing"] else None
+    cm = b200.t_get_confusion_matrix(torch.from_numpy(x).cuda(), torch.from_numpy(y).to(tdt).cuda(), existing,
+                                     e["no_ignore_class"])
+    ref = g.get("confmat", name, "cm")
+    assert cm.dtype == torch.int64
+    assert np.array_equal(cm.cpu().numpy(), ref.astype(np.int64))          # bit-exact counts
+    cm32 = cm.to(torch.int32)
+    pa, pac = b200.t_get_pixel_accuracy(cm32)
+    assert np.array_equal(np.array([pa.item(), pac.item()], np.float32), g.get("confmat", name, "pixel_accuracy"))
+    if not e["metrics"]:
+        return
+    exp = e["experiment"]
+    assert np.float32(b200.t_get_mean_iou(cm32, exp).item()) == g.get("confmat", name, "miou")
+    four = b200.t_get_mean_iou(cm32, exp, True, rare=True)
+    assert np.array_equal(np.array([v.item() for v in four], np.float32), g.get("confmat", name, "miou_categories_rare"))
+    vecs = b200.t_get_mean_iou(cm32, exp, True, calculate_mean=False, rare=True)
+    for tag, v in zip(("all", "instruments", "anatomies", "rare"), vecs):
+        assert np.array_equal(v.cpu().numpy(), g.get("confmat", name, f"iou_vec_{tag}"))
+    assert np.array_equal(b200.t_normalise_confusion_matrix(cm32, "row").cpu().numpy(), g.get("confmat", name, "norm_row"))
+    assert np.array_equal(b200.t_normalise_confusion_matrix(cm32, "col").cpu().numpy(), g.get("confmat", name, "norm_col"))
+    sc = np.array([float(b200.t_get_single_class_iou(cm32, exp, k)) for k in range(x.shape[1])], np.float32)
+    assert np.array_equal(sc, g.get("confmat", name, "single_class_iou"))
+    # device-side summary kernel: same formulas, one launch
+    iou, summary = b200.metrics_summary(cm, exp)
+    assert np.allclose(iou.cpu().numpy(), g.get("confmat", name, "iou_vec_all"), rtol=0, atol=0)
+    ref4 = g.get("confmat", name, "miou_categories_rare")
+    got4 = summary.cpu().numpy()[[0, 3, 4, 5]]
+    assert np.allclose(got4, ref4, rtol=2e-7, atol=0)
+    assert np.allclose(summary.cpu().numpy()[1:3], g.get("confmat", name, "pixel_accuracy"), rtol=2e-7, atol=0)
+    if g.has("confmat", name, "np_cm"):
+        ncm = b200.get_confusion_matrix(x, y)
+        assert ncm.dtype == np.int32 and np.array_equal(ncm, g.get("confmat", name, "np_cm"))
+        assert np.allclose(np.array(b200.get_mean_iou(ncm, 1, categories=True)),
+                           g.get("confmat", name, "np_miou_categories"), rtol=0, atol=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# seeded inputs against the oracle at sizes it finishes in seconds
+# ---------------------------------------------------------------------------------------------------------------
+def _d1(n, c, h, w, seed, with_ignore):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((n, c, h, w), generator=g)
+    y = torch.randint(0, c + 1 if with_ignore else c, (n, h, w), generator=g)
+    return x, y
+
+
+def _blocky(n, c, h, w, seed, with_ignore):
+    """trained-like: blocky label map, confident logits with 10 % flips (D2 of SURVEY.md §8d, synthetic masks)"""
+    g = torch.Generator().manual_seed(seed)
+    coarse = torch.randint(0, c + 1 if with_ignore else c, (n, (h + 15) // 16, (w + 15) // 16), generator=g)
+    coarse[coarse >= c // 2 + 2] = 0 if not with_ignore else c                 # several classes absent
+    y = coarse.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :h, :w].contiguous()
+    noisy = y.clone()
+    flips = torch.rand((n, h, w), generator=g) < 0.10
+    noisy[flips] = torch.randint(0, c, (int(flips.sum()),), generator=g)
+    onehot = torch.nn.functional.one_hot(noisy.clamp(max=c - 1), c).permute(0, 3, 1, 2).float()
+    return 6.0 * onehot + torch.randn((n, c, h, w), generator=g), y
+
+
+CASES = [
+    # name, builder, (n, c, h, w), experiment, extra config
+    ("d1_c8_flat", _d1, (2, 8, 135, 240), 1, {}),
+    ("d1_c17_per_image", _d1, (3, 17, 135, 240), 2, {"per_image": True}),
+    ("d1_c25_flat", _d1, (2, 25, 135, 240), 3, {}),
+    ("d1_c25_flat_ignore", _d1, (2, 25, 108, 192), 3, {"classes_to_ignore": 25}),
+    ("d1_c25_all", _d1, (1, 25, 54, 96), 3, {"classes_to_consider": "all"}),
+    ("d1_c25_odd_plane", _d1, (2, 25, 61, 97), 3, {}),                          # H*W % 4 != 0 -> generic kernels
+    ("d1_c5_generic", _d1, (2, 5, 64, 96), 1, {}),                              # C without a templated kernel
+    ("d2_c25_flat", _blocky, (2, 25, 128, 240), 3, {}),
+    ("d2_c17_per_image_ignore", _blocky, (2, 17, 128, 240), 2, {"per_image": True, "classes_to_ignore": 17}),
+    ("d2_c25_list", _blocky, (2, 25, 96, 160), 3, {"classes_to_consider": [0, 1, 2, 7, 20, 24]}),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("label_dtype", [torch.int64, torch.int32, torch.uint8], ids=["i64", "i32", "u8"])
+def test_lovasz_and_confmat_match_oracle(b200, case, label_dtype):
+    from oracle import port
+    name, builder, (n, c, h, w), exp, extra = case
+    if label_dtype != torch.int64 and not name.startswith(("d1_c25_flat", "d2_c17")):
+        pytest.skip("label dtype sweep runs on two representative cases")
+    x, y = builder(n, c, h, w, seed=1234 + n * c, with_ignore=exp != 1)
+    kw = dict(per_image=extra.get("per_image", False), classes_to_ignore=extra.get("classes_to_ignore"),
+              classes_to_consider=extra.get("classes_to_consider", "present"))
+    ref_loss, ref_grad = port.lovasz_softmax_with_grad(x, y, exp, **kw)
+    cfg = {"experiment": exp, **extra}
+    loss, grad = _run_lovasz(b200, x.numpy(), y.numpy(), cfg, label_dtype)
+    assert rel_err(loss, float(ref_loss)) <= LOSS_RTOL
+    assert grad_err(grad, ref_grad.numpy()) <= GRAD_RTOL
+    # elementwise gate of SURVEY.md §8(d)
+    gmax = float(ref_grad.abs().max())
+    assert np.allclose(grad, ref_grad.numpy(), rtol=1e-5, atol=1e-5 * gmax)
+    # confusion matrix on the same inputs: standalone kernel and fused into the loss forward, both bit-exact
+    if c in (8, 17, 25):
+        ref_cm = port.confusion_matrix(x, y.int()).to(torch.int64)
+        cm = b200.t_get_confusion_matrix(x.cuda(), y.cuda().to(label_dtype))
+        assert torch.equal(cm.cpu(), ref_cm)
+        meter = b200.SegmentationMeter(exp, c)
+        fused = b200.LovaszSoftmaxWithMetrics(cfg, meter)
+        xd = x.cuda().requires_grad_(True)
+        l2 = fused(xd, y.cuda().to(label_dtype))
+        l2.backward()
+        assert float(l2.item()) == loss
+        assert np.array_equal(xd.grad.cpu().numpy(), grad)
+        assert torch.equal(meter.cm.cpu(), ref_cm)
+        meter.check()
+
+
+def test_c_oracle_second_opinion(b200):
+    """the plain-C restatement (closed-form backward) against the CUDA path"""
+    from oracle import cref
+    x, y = _blocky(2, 17, 64, 96, seed=5, with_ignore=True)
+    loss, grad = _run_lovasz(b200, x.numpy(), y.numpy(), {"experiment": 2, "per_image": True})
+    rl, rg = cref.lovasz(x.numpy(), y.numpy(), per_image=True)
+    assert rel_err(loss, rl) <= LOSS_RTOL and grad_err(grad, rg) <= GRAD_RTOL
+    assert np.array_equal(b200.t_get_confusion_matrix(x.cuda(), y.cuda()).cpu().numpy(), cref.confmat(x.numpy(), y.numpy()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the segmented stable radix sort on its own: bit-exact against a stable CPU sort
+# ---------------------------------------------------------------------------------------------------------------
+def _sort_segments(keys, vals, counts, bits, cap):
+    from miccai2021_cataract_semantic_segmentation_b200 import _native
+    lib = _native.load()
+    nseg = len(counts)
+    need = ctypes.c_size_t(0)
+    _native.check(lib.b200seg_sort_scratch_bytes(nseg, cap, need), "scratch")
+    scratch = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+    kin = torch.from_numpy(keys.astype(np.int64)).cuda().to(torch.int32)
+    vin = torch.from_numpy(vals.astype(np.int64)).cuda().to(torch.int32)
+    kout, vout = torch.empty_like(kin), torch.empty_like(vin)
+    cnt = torch.from_numpy(counts.astype(np.int32)).cuda()
+    bts = torch.from_numpy(bits.astype(np.int32)).cuda()
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _native.check(lib.b200seg_sort_segments(kin.data_ptr(), vin.data_ptr(), kout.data_ptr(), vout.data_ptr(),
+                                            cnt.data_ptr(), bts.data_ptr(), nseg, cap, scratch.data_ptr(),
+                                            scratch.numel(), status.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "sort")
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    return kout.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, vout.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_segmented_sort_is_stable_and_exact(b200, seed):
+    rng = np.random.RandomState(seed)
+    cap = 40000
+    counts = np.array([0, 1, 17, 4096, 4097, 40000, 12345, 0, 33000, 2], dtype=np.int64)
+    bits = np.array([1, 5, 3, 30, 25, 24, 10, 7, 2, 30], dtype=np.int64)
+    nseg = len(counts)
+    keys = np.zeros(nseg * cap, dtype=np.int64)
+    vals = np.zeros(nseg * cap, dtype=np.int64)
+    for s in range(nseg):
+        n = counts[s]
+        hi = 1 << bits[s]
+        k = rng.randint(0, hi, size=n)
+        if seed == 1 and n > 100:                       # heavy ties
+            k = rng.randint(0, min(hi, 7), size=n)
+        if seed == 2 and n > 100:                       # clustered keys (what the loss produces)
+            k = np.clip((rng.randn(n) * hi / 64 + hi / 2).astype(np.int64), 0, hi - 1)
+        keys[s * cap:s * cap + n] = k
+        vals[s * cap:s * cap + n] = np.arange(n) * 2 + (rng.rand(n) < 0.3)
+    kout, vout = _sort_segments(keys, vals, counts, bits, cap)
+    for s in range(nseg):
+        n = counts[s]
+        sl = slice(s * cap, s * cap + n)
+        order = np.argsort(keys[sl], kind="stable")
+        assert np.array_equal(kout[sl], keys[sl][order]), f"segment {s}: keys"
+        assert np.array_equal(vout[sl], vals[sl][order]), f"segment {s}: values / tie order"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge cases and error behaviour
+# ---------------------------------------------------------------------------------------------------------------
+def test_label_range_errors(b200):
+    x = torch.zeros(1, 8, 4, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="Class values must be smaller"):
+        b200.t_get_confusion_matrix(x, torch.full((1, 4, 4), 8, device="cuda"))
+    x17 = torch.zeros(1, 17, 4, 4, device="cuda")
+    assert int(b200.t_get_confusion_matrix(x17, torch.full((1, 4, 4), 17, device="cuda")).sum()) == 0
+    with pytest.raises(RuntimeError):
+        b200.t_get_confusion_matrix(x17, torch.full((1, 4, 4), 18, device="cuda"))
+    with pytest.raises(RuntimeError):
+        b200.t_get_confusion_matrix(x17, torch.full((1, 4, 4), 17, device="cuda"), no_ignore_class=False)
+    with pytest.raises(IndexError):
+        b200.get_confusion_matrix(x17.cpu().numpy(), np.full((1, 4, 4), 17))
+
+
+def test_argmax_ties_and_nan(b200):
+    x = torch.zeros(1, 8, 2, 4, device="cuda")
+    x[0, 3, 0, 0] = 1.0
+    x[0, 5, 0, 0] = 1.0                      # tie -> first maximum (3)
+    x[0, 6, 0, 1] = float("nan")             # NaN counts as maximum
+    x[0, 2, 0, 2] = float("nan")
+    x[0, 7, 0, 2] = float("nan")             # first NaN wins (2)
+    y = torch.zeros(1, 2, 4, dtype=torch.int64, device="cuda")
+    cm = b200.t_get_confusion_matrix(x, y)
+    ref = torch.bincount(x.cpu().transpose(1, 0).reshape(8, -1).argmax(0) * 8, minlength=64).view(8, 8)
+    assert torch.equal(cm.cpu(), ref)
+    assert int(cm[3, 0]) == 1 and int(cm[6, 0]) == 1 and int(cm[2, 0]) == 1
+
+
+def test_degenerate_inputs(b200):
+    # every pixel filtered -> zero loss, zero gradient (reference returns an empty tensor / crashes)
+    x = torch.randn(2, 17, 8, 8, device="cuda", requires_grad=True)
+    y = torch.full((2, 8, 8), 17, device="cuda")
+    loss = b200.LovaszSoftmax({"experiment": 2, "classes_to_ignore": 17})(x, y)
+    loss.backward()
+    assert float(loss) == 0.0 and float(x.grad.abs().max()) == 0.0
+    # no class present (all labels == ignore, not filtered) -> reference returns python int 0
+    x2 = torch.randn(1, 17, 8, 8, device="cuda", requires_grad=True)
+    l2 = b200.LovaszSoftmax({"experiment": 2})(x2, torch.full((1, 8, 8), 17, device="cuda"))
+    l2.backward()
+    assert float(l2) == 0.0 and float(x2.grad.abs().max()) == 0.0
+    # exactly one valid pixel (reference crashes in flatten_probabilities): loss = 1 - p_label
+    x3 = torch.randn(1, 17, 4, 4, device="cuda")
+    y3 = torch.full((1, 4, 4), 17, device="cuda")
+    y3[0, 2, 1] = 4
+    l3 = b200.LovaszSoftmax({"experiment": 2, "classes_to_ignore": 17})(x3, y3)
+    p = torch.softmax(x3[0, :, 2, 1], 0)[4]
+    assert abs(float(l3) - float(1 - p)) < 1e-6
+    # empty batch
+    l4 = b200.LovaszSoftmax({"experiment": 1})(torch.zeros(0, 8, 4, 4, device="cuda"),
+                                               torch.zeros(0, 4, 4, dtype=torch.int64, device="cuda"))
+    assert float(l4) == 0.0
+    # callers mutate the returned loss in place and run under anomaly mode (main.py:8, LossWrapper.py:71-73)
+    with torch.autograd.set_detect_anomaly(True):
+        x5 = torch.randn(1, 8, 16, 16, device="cuda", requires_grad=True)
+        l5 = b200.LovaszSoftmax({"experiment": 1})(x5, torch.randint(0, 8, (1, 16, 16), device="cuda"))
+        l5 *= 0.5
+        total = torch.tensor(0.0, device="cuda")
+        total += l5
+        total.backward()
+        assert torch.isfinite(x5.grad).all()
+
+
+def test_no_grad_forward_and_non_contiguous(b200):
+    from oracle import port
+    x, y = _d1(2, 17, 40, 64, seed=3, with_ignore=True)
+    ref = float(port.lovasz_softmax(x, y, 2))
+    with torch.no_grad():
+        l = b200.LovaszSoftmax({"experiment": 2})(x.cuda(), y.cuda())
+    assert rel_err(float(l), ref) <= LOSS_RTOL
+    xt = x.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2).cuda()         # non-contiguous view, same values
+    assert not xt.is_contiguous()
+    l2 = b200.LovaszSoftmax({"experiment": 2})(xt, y.cuda())
+    assert float(l2) == float(l)
+    xs = x.cuda()[1:]                                                          # offset base pointer
+    l3 = b200.LovaszSoftmax({"experiment": 2})(xs, y.cuda()[1:])
+    assert rel_err(float(l3), float(port.lovasz_softmax(x[1:], y[1:], 2))) <= LOSS_RTOL
+
+
+def test_gradient_scales_with_upstream_weight(b200):
+    x, y = _d1(1, 8, 32, 48, seed=9, with_ignore=False)
+    a = x.cuda().requires_grad_(True)
+    b = x.cuda().requires_grad_(True)
+    mod = b200.LovaszSoftmax({"experiment": 1})
+    mod(a, y.cuda()).backward()
+    (0.4 * mod(b, y.cuda())).backward()
+    assert torch.allclose(b.grad, 0.4 * a.grad, rtol=1e-6, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties (the oracle would take minutes here)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c,exp,per_image", [(25, 3, False), (17, 2, True)])
+def test_full_size_properties(b200, c, exp, per_image):
+    n, h, w = 8, 540, 960
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn((n, c, h, w), generator=g, device="cuda")
+    y = torch.randint(0, c + 1, (n, h, w), generator=g, device="cuda")
+    meter = b200.SegmentationMeter(exp, c)
+    mod = b200.LovaszSoftmaxWithMetrics({"experiment": exp, "per_image": per_image}, meter)
+    xr = x.clone().requires_grad_(True)
+    loss = mod(xr, y)
+    loss.backward()
+    meter.check()
+    assert 0.0 < float(loss) <= 1.0
+    assert torch.isfinite(xr.grad).all()
+    # softmax Jacobian property: the logit gradient of every pixel sums to zero over classes
+    assert float(xr.grad.sum(1).abs().max()) <= 1e-4 * float(xr.grad.abs().max())
+    # confusion matrix invariants of utils/metrics.py:17-21 and agreement of fused vs standalone kernels
+    cm = meter.cm
+    assert int(cm.sum()) == int((y < c).sum())
+    pred = x.argmax(1)
+    assert torch.equal(cm.sum(1), torch.bincount(pred[y < c].flatten(), minlength=c))
+    assert torch.equal(cm.sum(0), torch.bincount(y[y < c].flatten(), minlength=c))
+    assert torch.equal(b200.t_get_confusion_matrix(x, y.int()), cm)
+    # checksum of checksums against an independent torch formulation of the same counts
+    ref = torch.bincount((pred * (c + 1) + y).flatten(), minlength=c * (c + 1)).view(c, c + 1)[:, :c]
+    assert torch.equal(cm, ref)
+    # determinism: same inputs, same bits
+    xr2 = x.clone().requires_grad_(True)
+    loss2 = b200.LovaszSoftmax({"experiment": exp, "per_image": per_image})(xr2, y)
+    loss2.backward()
+    assert float(loss2) == float(loss) and torch.equal(xr2.grad, xr.grad)
+    # per-image loss of a batch is the mean of single-image losses (flat: images interact, so only per-image)
+    if per_image:
+        singles = [float(b200.LovaszSoftmax({"experiment": exp, "per_image": True})(x[i:i + 1], y[i:i + 1]))
+                   for i in range(n)]
+        assert abs(np.mean(singles) - float(loss)) <= 1e-6
+    # one image of the batch against the oracle's loss (forward only, ~10 s of CPU)
+    from oracle import port
+    ref1 = float(port.lovasz_softmax(x[:1].cpu(), y[:1].cpu(), exp, per_image=per_image))
+    got1 = float(b200.LovaszSoftmax({"experiment": exp, "per_image": per_image})(x[:1], y[:1]))
+    assert rel_err(got1, ref1) <= LOSS_RTOL

@@ -1,0 +1,152 @@
+"""CPU-side tests: the C ABI library loads and exports every declared symbol, and the host logic above it."""
+import ctypes
+import os
+import re
+import sys
+import types
+import warnings
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    from miccai2021_cataract_semantic_segmentation_b200 import _native, build
+    build.build()            # nvcc cross-compiles sm_100a without a GPU
+    return _native
+
+
+def test_library_exports_every_declared_symbol(native):
+    header = open(os.path.join(ROOT, "include", "b200seg.h")).read()
+    declared = set(re.findall(r"\b(b200seg_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(native.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200seg.h but not exported"
+    assert declared == set(native.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert native.load().b200seg_version() == 1
+
+
+def test_argument_validation_without_gpu(native):
+    lib = native.load()
+    n = ctypes.c_size_t(0)
+    assert lib.b200seg_lovasz_workspace_bytes(8, 25, 540 * 960, 0, n) == 0
+    p, c = 8 * 540 * 960, 25
+    assert n.value >= 4 * 4 * c * p + 3 * 4 * p            # four candidate arrays + per-pixel state
+    assert lib.b200seg_lovasz_workspace_bytes(8, 33, 64, 0, n) == -1
+    assert b"n_classes" in lib.b200seg_last_error()
+    assert lib.b200seg_lovasz_workspace_bytes(4096, 25, 540 * 960, 0, n) == -1      # > 2^30 pixels in one call
+    assert lib.b200seg_lovasz_forward(None, None, 2, 1, 8, 16, 0, native.NO_LABEL, 0, 255, 1, None, 0, None, None,
+                                      native.NO_LABEL, None, None) == -1
+
+
+def test_no_cpu_fallback(native):
+    import miccai2021_cataract_semantic_segmentation_b200 as b200
+    x = torch.zeros(1, 8, 4, 4)
+    y = torch.zeros(1, 4, 4, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        b200.LovaszSoftmax({"experiment": 1})(x, y)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        b200.t_get_confusion_matrix(x, y)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "miccai2021_cataract_semantic_segmentation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "oracle/" not in src and "/root/reference" not in src, f
+
+
+def test_config_surface_matches_reference():
+    import miccai2021_cataract_semantic_segmentation_b200 as b200
+    from miccai2021_cataract_semantic_segmentation_b200.lovasz import _resolve_classes
+    m = b200.LovaszSoftmax({"experiment": 3})
+    assert (m.num_classes, m.per_image, m.classes_to_ignore, m.classes_to_consider) == (26, False, None, "present")
+    assert list(m.state_dict().keys()) == [] and list(m.parameters()) == []
+    with pytest.raises(KeyError):
+        b200.LovaszSoftmax({})
+    assert _resolve_classes(m.classes_to_consider, 25) == (0, (1 << 25) - 1)
+    assert _resolve_classes("all", 8) == (1, 255)
+    assert _resolve_classes([0, 3, 17], 17) == (1, 0b1001)            # index C is dropped like LovaszSoftmax.py:48-49
+    with pytest.raises(IndexError):
+        _resolve_classes([0, 30], 17)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert _resolve_classes("".join(["pre", "sent"]), 8) == (1, 255)   # the reference's `is 'present'` quirk
+        assert len(w) == 1
+
+
+def test_class_tables_match_reference_manifest(gold):
+    from miccai2021_cataract_semantic_segmentation_b200 import CLASS_INFO
+    for exp in (1, 2, 3):
+        info = gold.manifest["class_info"][str(exp)]
+        assert list(CLASS_INFO[exp][1].keys()) == info["keys"]
+        assert CLASS_INFO[exp][2] == info["categories"]
+
+
+def test_cpu_side_metric_formulas_match_golden(gold):
+    """t_get_mean_iou & co. are plain torch on the C x C matrix: check them on CPU against the reference's numbers."""
+    import numpy as np
+    import miccai2021_cataract_semantic_segmentation_b200 as b200
+    for e in gold.manifest["confmat"]:
+        if not e["metrics"]:
+            continue
+        name, exp = e["name"], e["experiment"]
+        cm = torch.from_numpy(gold.get("confmat", name, "cm"))
+        assert np.float32(b200.t_get_mean_iou(cm, exp).item()) == gold.get("confmat", name, "miou")
+        four = b200.t_get_mean_iou(cm, exp, True, rare=True)
+        assert np.array_equal(np.array([v.item() for v in four], np.float32),
+                              gold.get("confmat", name, "miou_categories_rare"))
+        pa, pac = b200.t_get_pixel_accuracy(cm)
+        assert np.array_equal(np.array([pa.item(), pac.item()], np.float32), gold.get("confmat", name, "pixel_accuracy"))
+        assert np.array_equal(b200.t_normalise_confusion_matrix(cm, "row").numpy(), gold.get("confmat", name, "norm_row"))
+        sc = np.array([float(b200.t_get_single_class_iou(cm, exp, k)) for k in range(cm.shape[0])], np.float32)
+        assert np.array_equal(sc, gold.get("confmat", name, "single_class_iou"))
+        assert np.array_equal(b200.t_get_mean_iou(cm, exp, single_class=3).numpy().reshape(-1)[:1],
+                              gold.get("confmat", name, "single_class_iou")[3:4])
+    out = b200.IoU(torch.from_numpy(gold.arrays["softiou/x"]), torch.from_numpy(gold.arrays["softiou/t"]))
+    assert np.array_equal(out.numpy(), gold.arrays["softiou/out"])
+
+
+def test_install_rebinds_names_bound_at_import_time():
+    """managers / compositor losses bind the names at import; install() patches their globals."""
+    import miccai2021_cataract_semantic_segmentation_b200 as b200
+
+    class OldLoss:            # stands in for the reference class
+        pass
+
+    def old_cm(*a, **k):
+        return "old"
+
+    fake = {}
+    for name in ("losses", "losses.LovaszSoftmax", "losses.LossWrapper", "managers", "managers.OCRNet_Manager", "utils",
+                 "utils.torch_utils"):
+        fake[name] = types.ModuleType(name)
+    for name in ("losses", "losses.LovaszSoftmax", "losses.LossWrapper", "managers.OCRNet_Manager"):
+        fake[name].LovaszSoftmax = OldLoss
+    for name in ("utils", "utils.torch_utils", "managers.OCRNet_Manager"):
+        fake[name].t_get_confusion_matrix = old_cm
+    saved = {k: sys.modules.get(k) for k in fake}
+    sys.modules.update(fake)
+    try:
+        rep = b200.install()
+        assert fake["losses"].LovaszSoftmax is b200.LovaszSoftmax
+        assert fake["losses.LossWrapper"].LovaszSoftmax is b200.LovaszSoftmax        # globals()[name] lookup site
+        assert fake["managers.OCRNet_Manager"].LovaszSoftmax is b200.LovaszSoftmax
+        assert fake["managers.OCRNet_Manager"].t_get_confusion_matrix is b200.t_get_confusion_matrix
+        assert fake["utils"].t_get_confusion_matrix is b200.t_get_confusion_matrix
+        assert fake["losses.LovaszSoftmax"].LovaszSoftmax is OldLoss                 # defining modules untouched
+        assert fake["utils.torch_utils"].t_get_confusion_matrix is old_cm
+        assert "losses.LossWrapper" in rep
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
