@@ -261,15 +261,15 @@ __global__ void __launch_bounds__(STATS_TPB) stats_kernel_generic(LovaszParams p
 template <typename LT>
 __global__ void __launch_bounds__(256) absent_max_kernel(LovaszParams p) {
     __shared__ u32 s_max;
-    const int seg = blockIdx.y;
+    const int seg = blockIdx.x;
     const int c = seg % p.C, g = seg / p.C;
     if (!((p.class_mask >> c) & 1u) || p.seg_fg[seg] > 0 || p.grp_valid[g] == 0) return;
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
     u32 best = 0;
     const long long begin = (long long)g * p.cap, end = begin + p.cap;
-    for (long long px = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; px < end;
-         px += (long long)gridDim.x * blockDim.x) {
+    for (long long px = begin + (long long)blockIdx.y * blockDim.x + threadIdx.x; px < end;
+         px += (long long)gridDim.y * blockDim.x) {
         const int lab = load_label<LT>(p.labels, (size_t)px);
         if (p.has_filter && lab == p.filter) continue;
         const long long n = px / p.HW, q = px - n * p.HW;
@@ -850,7 +850,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     }
     LAUNCH_CHECK("stats_kernel");
     if (p.keep_absent) {
-        DISPATCH_LABEL(label_dtype, absent_max_kernel<LT><<<dim3(32, p.n_seg), 256, 0, st>>>(p));
+        DISPATCH_LABEL(label_dtype, absent_max_kernel<LT><<<dim3(p.n_seg, 32), 256, 0, st>>>(p));
         LAUNCH_CHECK("absent_max_kernel");
     }
     finalize_stats_kernel<<<(p.groups + 127) / 128, 128, 0, st>>>(p);
