@@ -812,7 +812,12 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
                                       size_t workspace_bytes, float* loss_out, int64_t* cm, int64_t cm_drop_label,
                                       int32_t* status, void* stream) {
     if (int rc = check_shape(n, c, hw)) return rc;
-    if (!logits || !labels || !workspace || !loss_out || (cm && !status)) {
+    if (!loss_out) { b200seg_set_error("loss_out is NULL"); return B200SEG_E_INVALID; }
+    if ((long long)n * hw == 0) {      // empty batch: nothing to read, loss 0
+        CUDA_TRY(cudaMemsetAsync(loss_out, 0, sizeof(float), (cudaStream_t)stream));
+        return 0;
+    }
+    if (!logits || !labels || !workspace || (cm && !status)) {
         b200seg_set_error("null pointer argument");
         return B200SEG_E_INVALID;
     }
@@ -833,7 +838,6 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     if (status) p.status = status;
 
     CUDA_TRY(cudaMemsetAsync(ws + L.ctrl, 0, L.zero_end - L.ctrl, st));
-    if (p.P == 0) { CUDA_TRY(cudaMemsetAsync(loss_out, 0, sizeof(float), st)); return 0; }
     const int sms = b200seg_sm_count();
     const bool v4 = vec4_ok(logits, labels, label_dtype, hw);
 
@@ -891,6 +895,7 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
                                        int32_t keep_absent, uint32_t class_mask, const void* workspace,
                                        size_t workspace_bytes, const float* grad_out, float* dlogits, void* stream) {
     if (int rc = check_shape(n, c, hw)) return rc;
+    if ((long long)n * hw == 0) return 0;
     if (!logits || !labels || !workspace || !grad_out || !dlogits) {
         b200seg_set_error("null pointer argument");
         return B200SEG_E_INVALID;
