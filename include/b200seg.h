@@ -113,6 +113,18 @@ int b200seg_metrics_from_confmat(const int64_t* cm, int32_t n_classes, uint32_t 
                                  float* iou_out, float* summary_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Measurement hook (no reference counterpart): per host thread, hand the library up to B200SEG_N_STAGES
+ * cudaEvent_t handles; while set, b200seg_lovasz_forward / _backward record events[i] on their stream at stage
+ * boundary i, so a caller can time each kernel group with cudaEventElapsedTime without a profiler.
+ *   0 forward entry      1 stats kernel done        2 threshold finalisation done   3 candidate emission done
+ *   4 sort plan+histogram+scan done   5 three sort passes done   6 Jaccard + loss done
+ *   7 backward entry     8 backward kernel done
+ * Pass NULL / 0 to clear.  Entries that are NULL are skipped.
+ * ------------------------------------------------------------------------------------------------ */
+#define B200SEG_N_STAGES 9
+int b200seg_set_stage_events(void* const* events, int32_t n_events);
+
+/* ------------------------------------------------------------------------------------------------
  * Test hook: the segmented stable radix sort used inside b200seg_lovasz_forward, exposed so tests can
  * compare it bit for bit with a stable CPU sort.  Segment s occupies [s*capacity, s*capacity + counts[s])
  * of keys_in/vals_in (uint32); keys are sorted ascending on their low `key_bits[s]` bits (1..30), ties keep

@@ -27,3 +27,21 @@ int b200seg_sm_count() {
 
 extern "C" int b200seg_version(void) { return B200SEG_VERSION; }
 extern "C" const char* b200seg_last_error(void) { return g_err; }
+
+// ---- stage events (measurement hook) -------------------------------------------------------------------------
+static thread_local cudaEvent_t g_stage_events[B200SEG_N_STAGES] = {nullptr};
+static thread_local int g_n_stage_events = 0;
+
+extern "C" int b200seg_set_stage_events(void* const* events, int32_t n_events) {
+    if (n_events < 0 || n_events > B200SEG_N_STAGES || (n_events > 0 && !events)) {
+        b200seg_set_error("b200seg_set_stage_events: need 0 <= n_events <= %d", B200SEG_N_STAGES);
+        return B200SEG_E_INVALID;
+    }
+    g_n_stage_events = n_events;
+    for (int i = 0; i < B200SEG_N_STAGES; ++i) g_stage_events[i] = i < n_events ? (cudaEvent_t)events[i] : nullptr;
+    return 0;
+}
+
+void b200seg_stage(int i, cudaStream_t st) {
+    if (i < g_n_stage_events && g_stage_events[i]) cudaEventRecord(g_stage_events[i], st);
+}

@@ -840,6 +840,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     CUDA_TRY(cudaMemsetAsync(ws + L.ctrl, 0, L.zero_end - L.ctrl, st));
     const int sms = b200seg_sm_count();
     const bool v4 = vec4_ok(logits, labels, label_dtype, hw);
+    b200seg_stage(0, st);
 
     // K1
     if (v4 && (c == 8 || c == 17 || c == 25)) {
@@ -853,12 +854,14 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
         DISPATCH_LABEL(label_dtype, stats_kernel_generic<LT><<<sms * 8, STATS_TPB, 0, st>>>(p));
     }
     LAUNCH_CHECK("stats_kernel");
+    b200seg_stage(1, st);
     if (p.keep_absent) {
         DISPATCH_LABEL(label_dtype, absent_max_kernel<LT><<<dim3(p.n_seg, 32), 256, 0, st>>>(p));
         LAUNCH_CHECK("absent_max_kernel");
     }
     finalize_stats_kernel<<<(p.groups + 127) / 128, 128, 0, st>>>(p);
     LAUNCH_CHECK("finalize_stats_kernel");
+    b200seg_stage(2, st);
 
     // K2
     {
@@ -870,6 +873,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
         else { DISPATCH_LABEL(label_dtype, emit_kernel<1, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
         LAUNCH_CHECK("emit_kernel");
     }
+    b200seg_stage(3, st);
 
     // sort
     SortArgs a;
@@ -887,6 +891,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     LAUNCH_CHECK("jaccard_kernel");
     loss_finalize_kernel<<<1, 32, 0, st>>>(p);
     LAUNCH_CHECK("loss_finalize_kernel");
+    b200seg_stage(6, st);
     return 0;
 }
 
@@ -912,6 +917,7 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
     if (p.P == 0) return 0;
     const int sms = b200seg_sm_count();
     const bool v4 = vec4_ok(logits, labels, label_dtype, hw) && aligned16(dlogits);
+    b200seg_stage(7, st);
     if (v4 && (c == 8 || c == 17 || c == 25)) {
         const int grid = sms * 3 * 4;
         DISPATCH_LABEL(label_dtype, {
@@ -923,6 +929,7 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
         DISPATCH_LABEL(label_dtype, backward_kernel_generic<LT><<<sms * 16, BWD_TPB, 0, st>>>(p, grad_out, dlogits));
     }
     LAUNCH_CHECK("backward_kernel");
+    b200seg_stage(8, st);
     return 0;
 }
 

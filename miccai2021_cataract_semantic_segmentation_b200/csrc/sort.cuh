@@ -290,9 +290,11 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, void* sc
     LAUNCH_CHECK("sort_hist_kernel");
     sort_scan_kernel<<<dim3(a.n_seg, SORT_PASSES), SORT_MAX_BINS, 0, st>>>(a);
     LAUNCH_CHECK("sort_scan_kernel");
+    b200seg_stage(4, st);
     for (int p = 0; p < SORT_PASSES; ++p) {
         sort_pass_kernel<<<sms * 4, SORT_TPB, 0, st>>>(a, p);
         LAUNCH_CHECK("sort_pass_kernel");
     }
+    b200seg_stage(5, st);
     return 0;
 }
