@@ -113,7 +113,7 @@ int b200seg_metrics_from_confmat(const int64_t* cm, int32_t n_classes, uint32_t 
                                  float* iou_out, float* summary_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Measurement hook (no reference counterpart): per host thread, hand the library up to B200SEG_N_STAGES
+ * Measurement hook (no reference counterpart): process-wide, hand the library up to B200SEG_N_STAGES
  * cudaEvent_t handles; while set, b200seg_lovasz_forward / _backward record events[i] on their stream at stage
  * boundary i, so a caller can time each kernel group with cudaEventElapsedTime without a profiler.
  *   0 forward entry      1 stats kernel done        2 threshold finalisation done   3 candidate emission done

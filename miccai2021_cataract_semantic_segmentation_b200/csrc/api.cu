@@ -29,8 +29,9 @@ extern "C" int b200seg_version(void) { return B200SEG_VERSION; }
 extern "C" const char* b200seg_last_error(void) { return g_err; }
 
 // ---- stage events (measurement hook) -------------------------------------------------------------------------
-static thread_local cudaEvent_t g_stage_events[B200SEG_N_STAGES] = {nullptr};
-static thread_local int g_n_stage_events = 0;
+// process-wide on purpose: PyTorch runs backward on its own autograd thread
+static cudaEvent_t g_stage_events[B200SEG_N_STAGES] = {nullptr};
+static volatile int g_n_stage_events = 0;
 
 extern "C" int b200seg_set_stage_events(void* const* events, int32_t n_events) {
     if (n_events < 0 || n_events > B200SEG_N_STAGES || (n_events > 0 && !events)) {

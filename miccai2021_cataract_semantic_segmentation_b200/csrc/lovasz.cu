@@ -24,7 +24,7 @@
 #define BWD_TPB 128
 #define JAC_TPB SORT_TPB
 
-enum { TICKET_EMIT = 0, TICKET_JAC = 1, CTRL_STATUS = 8 };
+enum { CTRL_STATUS = 8 };
 
 struct LovaszParams {
     const float* logits;
@@ -40,7 +40,9 @@ struct LovaszParams {
     double* seg_loss;
     float *seg_thr, *seg_logthr, *seg_w;
     float *pix_m, *pix_s, *gown, *gbg;
-    u64* emit_state;
+    u32 *run_cnt, *run_prefix;          // [groups*n_runs][C] candidate counts per emission chunk; [n_seg][n_runs+1]
+    int n_runs, tiles_per_chunk;        // emission chunks per group, emission tiles per chunk
+    long long run_stride, src_cap;      // slots per chunk, holey segment stride (= n_runs * run_stride)
     u32 *keysA, *valsA, *keysB, *valsB;
     // fused confusion matrix
     unsigned long long* cm;
@@ -51,10 +53,28 @@ struct LovaszParams {
 
 struct LovaszLayout {
     size_t ctrl, seg_fg, seg_maxkey, seg_maxp, seg_count, grp_valid, seg_loss, zero_end;
-    size_t seg_thr, seg_logthr, seg_w, seg_bits, emit_state, emit_state_bytes;
+    size_t seg_thr, seg_logthr, seg_w, seg_bits, run_cnt, run_prefix;
     size_t pix_m, pix_s, gown, keysA, valsA, keysB, valsB, sort_scratch, total;
     SortScratch sort;
 };
+
+// Emission geometry for one pixel-vector width: tiles of EMIT_TPB*vec pixels never straddle images; a chunk is
+// `tpc` consecutive tiles of one group and owns run_stride = tpc * tile_px candidate slots per class.
+struct EmitGeom { long long tile_px, tpi, tpg, tpc, n_runs, run_stride, src_cap; };
+static EmitGeom emit_geom(int N, long long HW, int per_image, int vec) {
+    EmitGeom G;
+    G.tile_px = (long long)EMIT_TPB * vec;
+    G.tpi = (HW + G.tile_px - 1) / G.tile_px;
+    G.tpg = per_image ? G.tpi : G.tpi * N;
+    const long long total_tiles = G.tpi * N;
+    G.tpc = (total_tiles + 1023) / 1024;                 // ~1000 chunks in flight over the whole batch
+    if (G.tpc < 1) G.tpc = 1;
+    G.n_runs = (G.tpg + G.tpc - 1) / G.tpc;
+    if (G.n_runs < 1) G.n_runs = 1;
+    G.run_stride = G.tpc * G.tile_px;
+    G.src_cap = G.n_runs * G.run_stride;
+    return G;
+}
 
 static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     LovaszLayout L;
@@ -62,6 +82,9 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     const int groups = per_image ? N : 1;
     const size_t S = (size_t)groups * C;
     const size_t CP = (size_t)C * P;
+    const EmitGeom G4 = emit_geom(N, HW, per_image, 4), G1 = emit_geom(N, HW, per_image, 1);
+    const size_t holey = S * (size_t)(G4.src_cap > G1.src_cap ? G4.src_cap : G1.src_cap);   // >= CP
+    const size_t runs = (size_t)groups * (size_t)(G4.n_runs > G1.n_runs ? G4.n_runs : G1.n_runs);
     size_t o = 0;
     L.ctrl = o;       o = align_up(o + 256, 256);
     L.seg_fg = o;     o = align_up(o + 4 * S, 256);
@@ -75,13 +98,13 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     L.seg_logthr = o; o = align_up(o + 4 * S, 256);
     L.seg_w = o;      o = align_up(o + 4 * S, 256);
     L.seg_bits = o;   o = align_up(o + 4 * S, 256);
-    const size_t tiles_max = (size_t)N * (size_t)((HW + EMIT_TPB - 1) / EMIT_TPB);      // VEC=1 tiling is the finest
-    L.emit_state = o; L.emit_state_bytes = 8 * tiles_max * C; o = align_up(o + L.emit_state_bytes, 256);
+    L.run_cnt = o;    o = align_up(o + 4 * runs * C, 256);
+    L.run_prefix = o; o = align_up(o + 4 * (runs + (size_t)groups) * C, 256);
     L.pix_m = o;      o = align_up(o + 4 * (size_t)P, 256);
     L.pix_s = o;      o = align_up(o + 4 * (size_t)P, 256);
     L.gown = o;       o = align_up(o + 4 * (size_t)P, 256);
-    L.keysA = o;      o = align_up(o + 4 * CP, 256);
-    L.valsA = o;      o = align_up(o + 4 * CP, 256);
+    L.keysA = o;      o = align_up(o + 4 * holey, 256);
+    L.valsA = o;      o = align_up(o + 4 * holey, 256);
     L.keysB = o;      o = align_up(o + 4 * CP, 256);
     L.valsB = o;      o = align_up(o + 4 * CP, 256);
     L.sort = sort_scratch_layout((int)S, (long long)CP);
@@ -321,7 +344,10 @@ __global__ void finalize_stats_kernel(LovaszParams p) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// K2: candidate emission in pixel order
+// K2: candidate emission.  Every chunk (a few consecutive tiles of one group) owns a private slot range per class,
+//     so CTAs never talk to each other: within the chunk candidates are written in pixel order (shared-memory
+//     bitmask ranks + running per-class offsets), chunks are ordered by construction, and the per-chunk counts are
+//     turned into the sort's run prefix by run_scan_kernel.  A stable sort then yields the canonical tie order.
 // --------------------------------------------------------------------------------------------------------------
 template <int VEC, typename LT>
 __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
@@ -331,141 +357,152 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
     __shared__ u32 s_mask[B200SEG_MAX_CLASSES][WORDS];
     __shared__ u32 s_wpre[B200SEG_MAX_CLASSES][WORDS];
     __shared__ u32 s_tot[B200SEG_MAX_CLASSES];
-    __shared__ u64 s_base[B200SEG_MAX_CLASSES];
+    __shared__ u32 s_run[B200SEG_MAX_CLASSES];
     __shared__ float s_thr[B200SEG_MAX_CLASSES], s_logthr[B200SEG_MAX_CLASSES];
-    __shared__ u32 s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = p.C;
     const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
-    const long long ntiles = tpi * p.N;
+    const long long tpg = p.per_image ? tpi : tpi * p.N;
+    const long long total_chunks = (long long)p.groups * p.n_runs;
     int cur_g = -1;
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_ticket = atomicAdd(p.ctrl + TICKET_EMIT, 1u);
-        __syncthreads();
-        const long long t = s_ticket;
-        if (t >= ntiles) break;
-        const int n = (int)(t / tpi);
-        const long long ti = t - (long long)n * tpi;
-        const int g = p.per_image ? n : 0;
+    for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+        const int g = (int)(chunk / p.n_runs);
+        const long long r = chunk - (long long)g * p.n_runs;
+        const long long gt0 = r * p.tiles_per_chunk;
+        const long long gt1 = min(gt0 + (long long)p.tiles_per_chunk, tpg);
+        __syncthreads();                                   // previous chunk fully written out
         if (g != cur_g) {
             if (tid < C) { s_thr[tid] = p.seg_thr[(size_t)g * C + tid]; s_logthr[tid] = p.seg_logthr[(size_t)g * C + tid]; }
             cur_g = g;
         }
+        if (tid < B200SEG_MAX_CLASSES) s_run[tid] = 0;
         for (int i = tid; i < B200SEG_MAX_CLASSES * WORDS; i += EMIT_TPB) (&s_mask[0][0])[i] = 0;
         __syncthreads();
 
-        const long long q0 = ti * TILE_PX + (long long)tid * VEC;
-        const bool inb = q0 < p.HW;
-        const size_t px0 = (size_t)n * p.HW + q0;
-        const float* lp = p.logits + (size_t)n * C * p.HW + q0;
-        float m[VEC], s[VEC];
-        int lab[VEC];
-        u32 acc[VEC];
+        for (long long gt = gt0; gt < gt1; ++gt) {
+            const int n = p.per_image ? g : (int)(gt / tpi);
+            const long long ti = p.per_image ? gt : gt - (long long)n * tpi;
+            const long long q0 = ti * TILE_PX + (long long)tid * VEC;
+            const bool inb = q0 < p.HW;
+            const size_t px0 = (size_t)n * p.HW + q0;
+            const float* lp = p.logits + (size_t)n * C * p.HW + q0;
+            float m[VEC], s[VEC];
+            int lab[VEC];
+            u32 acc[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = 0;
-        if (inb) {
-            if constexpr (VEC == 4) {
-                const float4 mv = *(const float4*)(p.pix_m + px0), sv = *(const float4*)(p.pix_s + px0);
-                m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
-                s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
-                load_labels4<LT>(p.labels, px0, lab);
-            } else {
-                m[0] = p.pix_m[px0]; s[0] = p.pix_s[px0]; lab[0] = load_label<LT>(p.labels, px0);
-            }
-            float theta[VEC];
-            u32 pre[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) { theta[j] = pre_theta(m[j], s[j]); pre[j] = 0; }
-#pragma unroll 5
-            for (int c = 0; c < C; ++c) {
-                const float lt = s_logthr[c];
-                float v[VEC];
+            for (int j = 0; j < VEC; ++j) acc[j] = 0;
+            if (inb) {
                 if constexpr (VEC == 4) {
-                    const float4 x = __ldg((const float4*)(lp + (size_t)c * p.HW));
-                    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                    const float4 mv = *(const float4*)(p.pix_m + px0), sv = *(const float4*)(p.pix_s + px0);
+                    m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+                    s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
+                    load_labels4<LT>(p.labels, px0, lab);
                 } else {
-                    v[0] = __ldg(lp + (size_t)c * p.HW);
+                    m[0] = p.pix_m[px0]; s[0] = p.pix_s[px0]; lab[0] = load_label<LT>(p.labels, px0);
+                }
+                float theta[VEC];
+                u32 pre[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) { theta[j] = pre_theta(m[j], s[j]); pre[j] = 0; }
+#pragma unroll 5
+                for (int c = 0; c < C; ++c) {
+                    const float lt = s_logthr[c];
+                    float v[VEC];
+                    if constexpr (VEC == 4) {
+                        const float4 x = __ldg((const float4*)(lp + (size_t)c * p.HW));
+                        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                    } else {
+                        v[0] = __ldg(lp + (size_t)c * p.HW);
+                    }
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) pre[j] |= (v[j] >= theta[j] + lt) ? (1u << c) : 0u;
                 }
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) pre[j] |= (v[j] >= theta[j] + lt) ? (1u << c) : 0u;
-            }
+                for (int j = 0; j < VEC; ++j) {
+                    if (p.has_filter && lab[j] == p.filter) pre[j] = 0;
+                    else if ((unsigned)lab[j] < (unsigned)C && thr_active(s_thr[lab[j]])) pre[j] |= 1u << lab[j];
+                    u32 mm = pre[j];
+                    while (mm) {
+                        const int c = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        float err, pr;
+                        if (exact_accept(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j], c == lab[j], s_thr[c], err, pr))
+                            acc[j] |= 1u << c;
+                    }
+                }
+                u32 uni = 0;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                if (p.has_filter && lab[j] == p.filter) pre[j] = 0;
-                else if ((unsigned)lab[j] < (unsigned)C && thr_active(s_thr[lab[j]])) pre[j] |= 1u << lab[j];
-                u32 mm = pre[j];
-                while (mm) {
-                    const int c = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    float err, pr;
-                    if (exact_accept(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j], c == lab[j], s_thr[c], err, pr))
-                        acc[j] |= 1u << c;
+                for (int j = 0; j < VEC; ++j) uni |= acc[j];
+                const int bit0 = tid * VEC;
+                while (uni) {
+                    const int c = __ffs(uni) - 1;
+                    uni &= uni - 1;
+                    u32 nib = 0;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) nib |= ((acc[j] >> c) & 1u) << j;
+                    atomicOr(&s_mask[c][bit0 >> 5], nib << (bit0 & 31));
                 }
             }
-            u32 uni = 0;
+            __syncthreads();
+
+            // exclusive popcount prefix over the words of every class
+            for (int c = warp; c < C; c += NWARPS) {
+                const u32 cnt = lane < WORDS ? __popc(s_mask[c][lane]) : 0;
+                u32 v = cnt;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) uni |= acc[j];
-            const int bit0 = tid * VEC;
-            while (uni) {
-                const int c = __ffs(uni) - 1;
-                uni &= uni - 1;
-                u32 nib = 0;
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) nib |= ((acc[j] >> c) & 1u) << j;
-                atomicOr(&s_mask[c][bit0 >> 5], nib << (bit0 & 31));
+                for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
+                if (lane < WORDS) s_wpre[c][lane] = v - cnt;
+                if (lane == 31) s_tot[c] = v;
             }
-        }
-        __syncthreads();
+            __syncthreads();
 
-        // exclusive popcount prefix over the words of every class
-        for (int c = warp; c < C; c += NWARPS) {
-            const u32 cnt = lane < WORDS ? __popc(s_mask[c][lane]) : 0;
-            u32 v = cnt;
+            if (inb) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
-            if (lane < WORDS) s_wpre[c][lane] = v - cnt;
-            if (lane == 31) s_tot[c] = v;
-        }
-        __syncthreads();
-
-        // chained scan across tiles: one chain per class (per image in per-image mode)
-        const long long pos = p.per_image ? ti : t;
-        const long long chain_len = p.per_image ? tpi : ntiles;
-        u64* chain0 = p.emit_state + (size_t)(p.per_image ? (long long)n * tpi : 0) * C;
-        if (pos > 0 && lane == 0)
-            for (int c = warp; c < C; c += NWARPS) st_relaxed(chain0 + (size_t)pos * C + c, lb_pack64(LB_AGG, s_tot[c]));
-        for (int c = warp; c < C; c += NWARPS) {
-            const u64 excl = pos > 0 ? lb_lookback64(chain0 + c, pos, (size_t)C, p.status) : 0;
-            if (lane == 0) {
-                const u64 incl = excl + s_tot[c];
-                st_relaxed(chain0 + (size_t)pos * C + c, lb_pack64(LB_INCL, incl));
-                s_base[c] = excl;
-                if (pos == chain_len - 1) p.seg_count[(size_t)g * C + c] = (u32)incl;
-            }
-        }
-        __syncthreads();
-
-        if (inb) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                u32 mm = acc[j];
-                const int bit = tid * VEC + j;
-                while (mm) {
-                    const int c = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    float err, pr;
-                    const bool fg = c == lab[j];
-                    exact_accept(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j], fg, s_thr[c], err, pr);
-                    const u32 rank = s_wpre[c][bit >> 5] + __popc(s_mask[c][bit >> 5] & ((1u << (bit & 31)) - 1u));
-                    const size_t slot = ((size_t)g * C + c) * (size_t)p.cap + (size_t)s_base[c] + rank;
-                    p.keysA[slot] = err_key(err);
-                    p.valsA[slot] = ((u32)(px0 + j) << 1) | (fg ? 1u : 0u);
+                for (int j = 0; j < VEC; ++j) {
+                    u32 mm = acc[j];
+                    const int bit = tid * VEC + j;
+                    while (mm) {
+                        const int c = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        float err, pr;
+                        const bool fg = c == lab[j];
+                        exact_accept(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j], fg, s_thr[c], err, pr);
+                        const u32 rank = s_run[c] + s_wpre[c][bit >> 5] +
+                                         __popc(s_mask[c][bit >> 5] & ((1u << (bit & 31)) - 1u));
+                        const size_t slot = ((size_t)g * C + c) * (size_t)p.src_cap + (size_t)r * p.run_stride + rank;
+                        p.keysA[slot] = err_key(err);
+                        p.valsA[slot] = ((u32)(px0 + j) << 1) | (fg ? 1u : 0u);
+                    }
                 }
             }
+            __syncthreads();
+            if (tid < C) s_run[tid] += s_tot[tid];
+            for (int i = tid; i < B200SEG_MAX_CLASSES * WORDS; i += EMIT_TPB) (&s_mask[0][0])[i] = 0;
+            __syncthreads();
         }
+        if (tid < C) p.run_cnt[(size_t)chunk * C + tid] = s_run[tid];
     }
+}
+
+// per segment: exclusive prefix of the chunk counts (the sort's run prefix) and the segment's candidate count
+__global__ void __launch_bounds__(256) run_scan_kernel(LovaszParams p) {
+    const int lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seg >= p.n_seg) return;
+    const int g = seg / p.C, c = seg - g * p.C;
+    u32* out = p.run_prefix + (size_t)seg * (p.n_runs + 1);
+    u32 carry = 0;
+    for (int r0 = 0; r0 < p.n_runs; r0 += 32) {
+        const int r = r0 + lane;
+        const u32 x = r < p.n_runs ? p.run_cnt[((size_t)g * p.n_runs + r) * p.C + c] : 0;
+        u32 v = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
+        if (r < p.n_runs) out[r] = carry + v - x;
+        carry += __shfl_sync(FULL_MASK, v, 31);
+    }
+    if (lane == 0) { out[p.n_runs] = carry; p.seg_count[seg] = carry; }
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -474,21 +511,17 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
 __global__ void __launch_bounds__(JAC_TPB) jaccard_kernel(LovaszParams p, SortArgs a) {
     __shared__ u32 s_wfg[SORT_WARPS];
     __shared__ double s_red[SORT_WARPS];
-    __shared__ u32 s_ticket;
-    __shared__ u64 s_excl;
+    __shared__ u32 s_excl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 le_mask = lane == 31 ? FULL_MASK : ((2u << lane) - 1u);
     const u32 total_tiles = a.tile_start[a.n_seg];
     const u32* keys = a.keys[1];
     const u32* vals = a.vals[1];
-    for (;;) {
+    for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         __syncthreads();
-        if (tid == 0) s_ticket = atomicAdd(p.ctrl + TICKET_JAC, 1u);
-        __syncthreads();
-        const u32 t = s_ticket;
-        if (t >= total_tiles) break;
         const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
-        const u32 tis = t - a.tile_start[seg];
+        const u32 tseg0 = a.tile_start[seg];
+        const u32 tis = t - tseg0;
         const u32 off = tis * SORT_TILE;
         const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
         const size_t base = (size_t)seg * a.cap + off;
@@ -515,14 +548,15 @@ __global__ void __launch_bounds__(JAC_TPB) jaccard_kernel(LovaszParams p, SortAr
         u32 wexcl = 0, ttot = 0;
 #pragma unroll
         for (int w2 = 0; w2 < SORT_WARPS; ++w2) { const u32 x = s_wfg[w2]; if (w2 < warp) wexcl += x; ttot += x; }
-        if (warp == 0) {
-            u64* chain = a.lb_chain + (t - tis);
-            if (tis > 0 && lane == 0) st_relaxed(chain + tis, lb_pack64(LB_AGG, ttot));
-            const u64 excl = tis > 0 ? lb_lookback64(chain, tis, 1, p.status) : 0;
-            if (lane == 0) { st_relaxed(chain + tis, lb_pack64(LB_INCL, excl + ttot)); s_excl = excl; }
+        if (warp == 0) {                                   // foreground flags in the tiles before this one (last sort pass)
+            u32 e = 0;
+            for (u32 i = lane; i < tis; i += 32) e += a.tile_fg[tseg0 + i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(FULL_MASK, e, o);
+            if (lane == 0) s_excl = e;
         }
         __syncthreads();
-        const u32 fbase = (u32)s_excl + wexcl;
+        const u32 fbase = s_excl + wexcl;
         double acc = 0.0;
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
@@ -774,7 +808,8 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.seg_loss = (double*)(ws + L.seg_loss);
     p.seg_thr = (float*)(ws + L.seg_thr); p.seg_logthr = (float*)(ws + L.seg_logthr); p.seg_w = (float*)(ws + L.seg_w);
     p.pix_m = (float*)(ws + L.pix_m); p.pix_s = (float*)(ws + L.pix_s); p.gown = (float*)(ws + L.gown);
-    p.emit_state = (u64*)(ws + L.emit_state);
+    p.run_cnt = (u32*)(ws + L.run_cnt); p.run_prefix = (u32*)(ws + L.run_prefix);
+    p.n_runs = 0; p.tiles_per_chunk = 0; p.run_stride = 0; p.src_cap = 0;
     p.keysA = (u32*)(ws + L.keysA); p.valsA = (u32*)(ws + L.valsA);
     p.keysB = (u32*)(ws + L.keysB); p.valsB = (u32*)(ws + L.valsB);
     p.gbg = (float*)(ws + L.keysA);      // free again once the sort result sits in buffer B
@@ -865,26 +900,29 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
 
     // K2
     {
-        const int vec = v4 ? 4 : 1;
-        const size_t tiles = (size_t)n * (size_t)((hw + EMIT_TPB * vec - 1) / (EMIT_TPB * vec));
-        CUDA_TRY(cudaMemsetAsync(ws + L.emit_state, 0, 8 * tiles * c, st));
-        const int grid = (int)(tiles < (size_t)sms * 8 ? tiles : (size_t)sms * 8);
+        const EmitGeom G = emit_geom(n, hw, per_image, v4 ? 4 : 1);
+        p.n_runs = (int)G.n_runs; p.tiles_per_chunk = (int)G.tpc; p.run_stride = G.run_stride; p.src_cap = G.src_cap;
+        const long long chunks = (long long)p.groups * G.n_runs;
+        const int grid = (int)(chunks < (long long)sms * 8 ? chunks : (long long)sms * 8);
         if (v4) { DISPATCH_LABEL(label_dtype, emit_kernel<4, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
         else { DISPATCH_LABEL(label_dtype, emit_kernel<1, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
         LAUNCH_CHECK("emit_kernel");
+        run_scan_kernel<<<(p.n_seg + 7) / 8, 256, 0, st>>>(p);
+        LAUNCH_CHECK("run_scan_kernel");
     }
     b200seg_stage(3, st);
 
-    // sort
+    // sort: holey source in A (gathered through the run prefix), ping-pong B -> A -> B
     SortArgs a;
     char* ss = ws + L.sort_scratch;
     a.keys[0] = p.keysA; a.vals[0] = p.valsA; a.keys[1] = p.keysB; a.vals[1] = p.valsB;
     a.seg_count = p.seg_count; a.seg_bits = p.seg_bits; a.n_seg = p.n_seg; a.cap = p.cap;
-    a.tile_start = (u32*)(ss + L.sort.tile_start); a.ghist = (u32*)(ss + L.sort.ghist);
-    a.lb[0] = (u32*)(ss + L.sort.lb0); a.lb[1] = (u32*)(ss + L.sort.lb1);
-    a.lb_chain = (u64*)(ss + L.sort.lb_chain); a.tickets = (u32*)(ss + L.sort.tickets);
+    a.src_keys = p.keysA; a.src_vals = p.valsA; a.run_prefix = p.run_prefix; a.n_runs = p.n_runs;
+    a.run_stride = p.run_stride; a.src_cap = p.src_cap;
+    a.tile_start = (u32*)(ss + L.sort.tile_start); a.tilehist = (u32*)(ss + L.sort.tilehist);
+    a.bin_base = (u32*)(ss + L.sort.bin_base); a.tile_fg = (u32*)(ss + L.sort.tile_fg);
     a.status = p.status;
-    if (int rc = sort_enqueue(a, L.sort, ss, st)) return rc;
+    if (int rc = sort_enqueue(a, L.sort, st)) return rc;
 
     // K5
     jaccard_kernel<<<sms * 4, JAC_TPB, 0, st>>>(p, a);
@@ -962,9 +1000,9 @@ extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint3
     SortArgs a;
     a.keys[0] = keys_in; a.vals[0] = vals_in; a.keys[1] = keys_out; a.vals[1] = vals_out;
     a.seg_count = counts; a.seg_bits = key_bits; a.n_seg = n_segments; a.cap = capacity;
-    a.tile_start = (u32*)(ss + L.tile_start); a.ghist = (u32*)(ss + L.ghist);
-    a.lb[0] = (u32*)(ss + L.lb0); a.lb[1] = (u32*)(ss + L.lb1);
-    a.lb_chain = (u64*)(ss + L.lb_chain); a.tickets = (u32*)(ss + L.tickets);
+    a.src_keys = nullptr; a.src_vals = nullptr; a.run_prefix = nullptr; a.n_runs = 0; a.run_stride = 0; a.src_cap = 0;
+    a.tile_start = (u32*)(ss + L.tile_start); a.tilehist = (u32*)(ss + L.tilehist);
+    a.bin_base = (u32*)(ss + L.bin_base); a.tile_fg = (u32*)(ss + L.tile_fg);
     a.status = status;
-    return sort_enqueue(a, L, ss, (cudaStream_t)stream);
+    return sort_enqueue(a, L, (cudaStream_t)stream);
 }

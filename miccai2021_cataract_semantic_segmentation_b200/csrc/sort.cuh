@@ -3,11 +3,17 @@
 // Replaces the C sequential full-length torch.sort calls of losses/LovaszSoftmax.py:57 (reference): one
 // segment per class (flat) or per (image, class) (per-image); only candidate elements are present.
 //
-// Layout in HBM: segment s owns [s*cap, s*cap + seg_count[s]) of each array.  Keys carry at most
+// Layout in HBM: segment s owns [s*cap, s*cap + seg_count[s]) of each ping-pong array.  Keys carry at most
 // seg_bits[s] <= 30 significant bits, so exactly three digit passes of w = ceil(bits/3) <= 10 bits are run
-// (A -> B -> A -> B; the result always lands in buffer 1).  Each pass is a single "onesweep"-style kernel:
-// tiles of 4096 elements take a ticket, rank their keys stably (warp match + per-warp counters), publish
-// per-bin tile counts and resolve the bins' global offsets by decoupled look-back within the segment.
+// (src -> B -> A -> B; the result always lands in buffer 1).  Segments have few tiles (tens), all running at the
+// same time, so a chained scan would serialise; each pass is three short kernels instead:
+//   count    per-tile digit histogram (shared-memory atomics)                    -> tilehist[tile][bin]
+//   scan     per segment: column scan over its tiles + exclusive scan over bins  -> tilehist (tile offsets), bin_base
+//   scatter  re-read the tile (L2), stable ranks (warp match + per-warp counters), write to the other buffer
+// The first pass can read a "holey" source: every segment is a concatenation of n_runs runs, run r starting at
+// s*src_cap + r*run_stride with run_prefix[s][r+1]-run_prefix[s][r] elements (what the emission kernel leaves
+// behind without any cross-CTA ordering); elements are gathered by binary search over the run prefix.
+// The last pass also counts foreground flags (value bit 0) per destination tile for the Jaccard scan.
 #pragma once
 #include "common.cuh"
 
@@ -17,6 +23,7 @@
 #define SORT_TILE (SORT_TPB * SORT_KPT)      // 4096 elements
 #define SORT_MAX_BINS 1024
 #define SORT_PASSES 3
+#define SORT_RUN_WINDOW 1024                 // run-prefix entries staged in shared memory per tile
 
 struct SortArgs {
     u32* keys[2];
@@ -24,17 +31,23 @@ struct SortArgs {
     const u32* seg_count;   // [n_seg] elements per segment
     const u32* seg_bits;    // [n_seg] significant key bits (1..30)
     int n_seg;
-    long long cap;          // segment region stride (elements)
-    u32* tile_start;        // [n_seg + 1] exclusive prefix of tiles per segment (written by sort_plan_kernel)
-    u32* ghist;             // [n_seg][3][1024] digit histograms -> exclusive bin bases
-    u32* lb[2];             // [max_tiles][1024] look-back state, ping-pong between passes
-    u64* lb_chain;          // [max_tiles] spare single-chain state (zeroed here, used by the Jaccard kernel)
-    u32* tickets;           // [4]
+    long long cap;          // segment stride of the ping-pong arrays (elements)
+    // holey source of pass 0 (run_prefix == nullptr: pass 0 reads keys[0] / vals[0], compact)
+    const u32* src_keys;
+    const u32* src_vals;
+    const u32* run_prefix;  // [n_seg][n_runs + 1]
+    int n_runs;
+    long long run_stride, src_cap;
+    // scratch
+    u32* tile_start;        // [n_seg + 1] exclusive prefix of tiles per segment
+    u32* tilehist;          // [max_tiles][1024]
+    u32* bin_base;          // [n_seg][1024]
+    u32* tile_fg;           // [max_tiles] foreground flags per tile of the final order (zeroed by sort_plan_kernel)
     int* status;
 };
 
 struct SortScratch {
-    size_t tile_start, ghist, lb0, lb1, lb_chain, tickets, total;
+    size_t tile_start, tilehist, bin_base, tile_fg, total;
     u32 max_tiles;
 };
 
@@ -42,12 +55,10 @@ static inline SortScratch sort_scratch_layout(int n_seg, long long total_capacit
     SortScratch L;
     L.max_tiles = (u32)(total_capacity / SORT_TILE + n_seg + 1);
     size_t o = 0;
-    L.tickets = o;    o = align_up(o + 64, 256);
     L.tile_start = o; o = align_up(o + sizeof(u32) * (size_t)(n_seg + 1), 256);
-    L.ghist = o;      o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_PASSES * SORT_MAX_BINS, 256);
-    L.lb0 = o;        o = align_up(o + sizeof(u32) * (size_t)L.max_tiles * SORT_MAX_BINS, 256);
-    L.lb1 = o;        o = align_up(o + sizeof(u32) * (size_t)L.max_tiles * SORT_MAX_BINS, 256);
-    L.lb_chain = o;   o = align_up(o + sizeof(u64) * (size_t)L.max_tiles, 256);
+    L.bin_base = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_MAX_BINS, 256);
+    L.tile_fg = o;    o = align_up(o + sizeof(u32) * (size_t)L.max_tiles, 256);
+    L.tilehist = o;   o = align_up(o + sizeof(u32) * (size_t)L.max_tiles * SORT_MAX_BINS, 256);
     L.total = o;
     return L;
 }
@@ -67,8 +78,8 @@ __device__ __forceinline__ int sort_find_segment(const u32* tile_start, int n_se
     return lo;
 }
 
-// ---- plan: tiles per segment -> exclusive prefix ------------------------------------------------------------
-__global__ void __launch_bounds__(1024) sort_plan_kernel(SortArgs a) {
+// ---- plan: tiles per segment -> exclusive prefix; clears the per-tile foreground counters -----------------------
+__global__ void __launch_bounds__(1024) sort_plan_kernel(SortArgs a, u32 max_tiles) {
     __shared__ u32 s_warp[32];
     __shared__ u32 s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -96,71 +107,129 @@ __global__ void __launch_bounds__(1024) sort_plan_kernel(SortArgs a) {
         __syncthreads();
     }
     if (tid == 0) a.tile_start[a.n_seg] = s_carry;
+    const u32 total = s_carry;
+    for (u32 i = tid; i < total && i < max_tiles; i += 1024) a.tile_fg[i] = 0;
 }
 
-// ---- upfront digit histograms of all three passes (one read of the keys) -----------------------------------
-__global__ void __launch_bounds__(SORT_TPB) sort_hist_kernel(SortArgs a) {
-    __shared__ u32 s_hist[SORT_PASSES][SORT_MAX_BINS];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const u32 total_tiles = a.tile_start[a.n_seg];
-    const u32 t0 = (u32)(((u64)total_tiles * blockIdx.x) / gridDim.x);
-    const u32 t1 = (u32)(((u64)total_tiles * (blockIdx.x + 1)) / gridDim.x);
-    if (t0 >= t1) return;
-    for (int i = tid; i < SORT_PASSES * SORT_MAX_BINS; i += SORT_TPB) (&s_hist[0][0])[i] = 0;
+// ---- tile addressing (compact or gathered through the run prefix) ------------------------------------------------
+struct TileSrc {
+    const u32* keys;
+    const u32* vals;
+    size_t base;            // compact: element 0 of the tile
+    // gathered:
+    bool gather;
+    const u32* prefix;      // run prefix of this segment (global)
+    u32 r_lo, r_hi;         // runs intersecting the tile: [r_lo, r_hi]
+    u32 voff;               // virtual index of tile element 0 within the segment
+    size_t seg_base;
+    long long run_stride;
+    bool window;            // prefix[r_lo .. r_hi + 1] staged in shared memory
+};
+
+__device__ __forceinline__ u32 upper_run(const u32* prefix, u32 lo, u32 hi, u32 v) {   // largest r in [lo,hi]: prefix[r] <= v
+    while (lo < hi) {
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (prefix[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Block-wide setup; s_win needs SORT_RUN_WINDOW + 1 entries.  Contains __syncthreads().
+__device__ __forceinline__ TileSrc tile_src_setup(const SortArgs& a, int pass, int seg, u32 off, u32 n, u32* s_win,
+                                                  u32* s_pair) {
+    TileSrc T;
+    const bool odd = pass & 1;
+    T.gather = (pass == 0 && a.run_prefix != nullptr);
+    T.prefix = nullptr; T.r_lo = T.r_hi = T.voff = 0; T.seg_base = 0; T.run_stride = 0; T.window = false; T.base = 0;
+    if (!T.gather) {
+        T.keys = odd ? a.keys[1] : a.keys[0];
+        T.vals = odd ? a.vals[1] : a.vals[0];
+        T.base = (size_t)seg * a.cap + off;
+        return T;
+    }
+    T.keys = a.src_keys; T.vals = a.src_vals;
+    T.prefix = a.run_prefix + (size_t)seg * (a.n_runs + 1);
+    T.voff = off;
+    T.seg_base = (size_t)seg * a.src_cap;
+    T.run_stride = a.run_stride;
+    if (threadIdx.x == 0) {
+        s_pair[0] = upper_run(T.prefix, 0, a.n_runs - 1, off);
+        s_pair[1] = upper_run(T.prefix, 0, a.n_runs - 1, off + n - 1);
+    }
     __syncthreads();
-    int seg = sort_find_segment(a.tile_start, a.n_seg, t0);
-    const u32* kin = a.keys[0];
-    for (u32 t = t0; t < t1; ++t) {
-        if (t >= a.tile_start[seg + 1]) {                 // segment change: flush
-            __syncthreads();
-            const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]);
-            for (int i = tid; i < SORT_PASSES * SORT_MAX_BINS; i += SORT_TPB) {
-                const u32 v = (&s_hist[0][0])[i];
-                if ((u32)(i & (SORT_MAX_BINS - 1)) < nbins && v) atomicAdd(a.ghist + (size_t)seg * SORT_PASSES * SORT_MAX_BINS + i, v);
-                (&s_hist[0][0])[i] = 0;
-            }
-            __syncthreads();
-            seg = sort_find_segment(a.tile_start, a.n_seg, t);
-        }
+    T.r_lo = s_pair[0]; T.r_hi = s_pair[1];
+    T.window = (T.r_hi - T.r_lo + 2) <= SORT_RUN_WINDOW + 1;
+    if (T.window)
+        for (u32 i = threadIdx.x; i < T.r_hi - T.r_lo + 2; i += blockDim.x) s_win[i] = T.prefix[T.r_lo + i];
+    __syncthreads();
+    return T;
+}
+
+__device__ __forceinline__ size_t tile_src_index(const TileSrc& T, const u32* s_win, u32 idx) {
+    if (!T.gather) return T.base + idx;
+    const u32 v = T.voff + idx;
+    u32 r, start;
+    if (T.window) {
+        r = upper_run(s_win, 0, T.r_hi - T.r_lo, v);
+        start = s_win[r];
+        r += T.r_lo;
+    } else {
+        r = upper_run(T.prefix, T.r_lo, T.r_hi, v);
+        start = T.prefix[r];
+    }
+    return T.seg_base + (size_t)r * T.run_stride + (v - start);
+}
+
+// ---- count: per-tile digit histogram --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pass) {
+    __shared__ u32 s_hist[SORT_MAX_BINS];
+    __shared__ u32 s_win[SORT_RUN_WINDOW + 1];
+    __shared__ u32 s_pair[2];
+    const int tid = threadIdx.x;
+    const u32 total_tiles = a.tile_start[a.n_seg];
+    for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
         const u32 off = (t - a.tile_start[seg]) * SORT_TILE;
-        const u32 count = a.seg_count[seg];
-        const u32 n = min((u32)SORT_TILE, count - off);
+        const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
         const u32 w = sort_digit_width(a.seg_bits[seg]);
-        const u32 dmask = (1u << w) - 1;
-        const size_t base = (size_t)seg * a.cap + off;
+        const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
+        __syncthreads();                                   // previous iteration done with s_hist / s_win
+        for (u32 b = tid; b < nbins; b += SORT_TPB) s_hist[b] = 0;
+        const TileSrc T = tile_src_setup(a, pass, seg, off, n, s_win, s_pair);
+        __syncthreads();
 #pragma unroll 4
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = k * SORT_TPB + tid;
-            const bool valid = idx < n;
-            const u32 key = valid ? kin[base + idx] : 0;
-#pragma unroll
-            for (int p = 0; p < SORT_PASSES; ++p) {
-                const u32 d = valid ? ((key >> (p * w)) & dmask) : 0xFFFFFFFFu;
-                const u32 m = __match_any_sync(FULL_MASK, d);
-                if (valid && lane == __ffs(m) - 1) atomicAdd(&s_hist[p][d], (u32)__popc(m));
-            }
+            if (idx < n) atomicAdd(&s_hist[(T.keys[tile_src_index(T, s_win, idx)] >> shift) & dmask], 1u);
         }
-        // clear the look-back state the first pass (and the Jaccard chain) will use for this tile
-        uint4* row = (uint4*)(a.lb[0] + (size_t)t * SORT_MAX_BINS);
-        row[tid] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) a.lb_chain[t] = 0;
-    }
-    __syncthreads();
-    const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]);
-    for (int i = tid; i < SORT_PASSES * SORT_MAX_BINS; i += SORT_TPB) {
-        const u32 v = (&s_hist[0][0])[i];
-        if ((u32)(i & (SORT_MAX_BINS - 1)) < nbins && v) atomicAdd(a.ghist + (size_t)seg * SORT_PASSES * SORT_MAX_BINS + i, v);
+        __syncthreads();
+        u32* row = a.tilehist + (size_t)t * SORT_MAX_BINS;
+        for (u32 b = tid; b < nbins; b += SORT_TPB) row[b] = s_hist[b];
     }
 }
 
-// ---- exclusive scan of each (segment, pass) histogram -> bin bases ------------------------------------------
+// ---- scan: one block per segment ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SORT_MAX_BINS) sort_scan_kernel(SortArgs a) {
     __shared__ u32 s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    u32* h = a.ghist + ((size_t)blockIdx.x * SORT_PASSES + blockIdx.y) * SORT_MAX_BINS;
-    if (a.seg_count[blockIdx.x] == 0) return;
-    const u32 x = h[tid];
-    u32 v = x;
+    const int seg = blockIdx.x;
+    const u32 t0 = a.tile_start[seg], t1 = a.tile_start[seg + 1];
+    if (t0 == t1) return;
+    const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]);
+    u32 run = 0;
+    if ((u32)tid < nbins) {
+        u32* col = a.tilehist + (size_t)t0 * SORT_MAX_BINS + tid;
+        u32 t = t0;
+        for (; t + 4 <= t1; t += 4, col += 4 * SORT_MAX_BINS) {          // independent loads, then the running sum
+            const u32 x0 = col[0], x1 = col[SORT_MAX_BINS], x2 = col[2 * SORT_MAX_BINS], x3 = col[3 * SORT_MAX_BINS];
+            col[0] = run; run += x0;
+            col[SORT_MAX_BINS] = run; run += x1;
+            col[2 * SORT_MAX_BINS] = run; run += x2;
+            col[3 * SORT_MAX_BINS] = run; run += x3;
+        }
+        for (; t < t1; ++t, col += SORT_MAX_BINS) { const u32 x = *col; *col = run; run += x; }
+    }
+    u32 v = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
     if (lane == 31) s_warp[warp] = v;
@@ -172,55 +241,51 @@ __global__ void __launch_bounds__(SORT_MAX_BINS) sort_scan_kernel(SortArgs a) {
         s_warp[lane] = wv;
     }
     __syncthreads();
-    h[tid] = v - x + (warp ? s_warp[warp - 1] : 0);
+    if ((u32)tid < nbins) a.bin_base[(size_t)seg * SORT_MAX_BINS + tid] = v - run + (warp ? s_warp[warp - 1] : 0);
 }
 
-// ---- one digit pass -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_TPB) sort_pass_kernel(SortArgs a, int pass) {
+// ---- scatter ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int pass) {
     __shared__ u32 s_cnt[SORT_WARPS][SORT_MAX_BINS + 1];
     __shared__ u32 s_binoff[SORT_MAX_BINS];
-    __shared__ u32 s_ticket;
+    __shared__ u32 s_win[SORT_RUN_WINDOW + 1];
+    __shared__ u32 s_pair[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1;
     const u32 total_tiles = a.tile_start[a.n_seg];
     // (static indexing only: a dynamically indexed kernel-parameter array would be copied to local memory)
     const bool odd = pass & 1;
-    const u32* __restrict__ kin = odd ? a.keys[1] : a.keys[0];
-    const u32* __restrict__ vin = odd ? a.vals[1] : a.vals[0];
     u32* __restrict__ kout = odd ? a.keys[0] : a.keys[1];
     u32* __restrict__ vout = odd ? a.vals[0] : a.vals[1];
-    u32* lbr = odd ? a.lb[1] : a.lb[0];
-    u32* lbn = odd ? a.lb[0] : a.lb[1];
+    const bool last = pass == SORT_PASSES - 1;
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_ticket = atomicAdd(a.tickets + 1 + pass, 1u);
-        __syncthreads();
-        const u32 t = s_ticket;
-        if (t >= total_tiles) break;
+    for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
-        const u32 tis = t - a.tile_start[seg];                 // tile index within its segment
-        const u32 off = tis * SORT_TILE;
+        const u32 tseg0 = a.tile_start[seg];
+        const u32 off = (t - tseg0) * SORT_TILE;
         const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
         const u32 w = sort_digit_width(a.seg_bits[seg]);
-        const u32 nbins = 1u << w;
-        const u32 dmask = nbins - 1;
-        const u32 shift = pass * w;
-        const size_t base = (size_t)seg * a.cap;
-
+        const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
+        const size_t obase = (size_t)seg * a.cap;
+        __syncthreads();
         for (u32 i = tid; i < SORT_WARPS * (SORT_MAX_BINS + 1); i += SORT_TPB) {
             const u32 b = i % (SORT_MAX_BINS + 1);
             if (b <= nbins) (&s_cnt[0][0])[i] = 0;
         }
+        for (u32 b = tid; b < nbins; b += SORT_TPB)
+            s_binoff[b] = a.bin_base[(size_t)seg * SORT_MAX_BINS + b] + a.tilehist[(size_t)t * SORT_MAX_BINS + b];
+        const TileSrc T = tile_src_setup(a, pass, seg, off, n, s_win, s_pair);
         __syncthreads();
 
         u32 key[SORT_KPT];
+        u32 src[SORT_KPT];                                     // source index relative to the source arrays (< 2^31)
         unsigned short rnk[SORT_KPT];
         const u32 wbase = warp * (32 * SORT_KPT) + lane;
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = wbase + k * 32;
-            key[k] = idx < n ? kin[base + off + idx] : 0xFFFFFFFFu;
+            src[k] = idx < n ? (u32)tile_src_index(T, s_win, idx) : 0;
+            key[k] = idx < n ? T.keys[src[k]] : 0xFFFFFFFFu;
         }
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
@@ -235,65 +300,46 @@ __global__ void __launch_bounds__(SORT_TPB) sort_pass_kernel(SortArgs a, int pas
             __syncwarp();
         }
         __syncthreads();
-
-        for (u32 b = tid; b < nbins; b += SORT_TPB) {
+        for (u32 b = tid; b < nbins; b += SORT_TPB) {       // per-warp counts -> exclusive offsets across warps
             u32 run = 0;
 #pragma unroll
             for (int w2 = 0; w2 < SORT_WARPS; ++w2) { const u32 c = s_cnt[w2][b]; s_cnt[w2][b] = run; run += c; }
-            u32* mine = lbr + (size_t)t * SORT_MAX_BINS + b;
-            u32 excl = 0;
-            if (tis == 0) {
-                st_relaxed(mine, lb_pack32(LB_INCL, run));
-            } else {
-                st_relaxed(mine, lb_pack32(LB_AGG, run));
-                long long look = (long long)t - 1;
-                const long long first = (long long)t - tis;
-                while (look >= first) {
-                    const u32 s = lb_wait32(lbr + (size_t)look * SORT_MAX_BINS + b, a.status);
-                    excl += lb_val32(s);
-                    if (lb_flag32(s) != LB_AGG) break;
-                    --look;
-                }
-                st_relaxed(mine, lb_pack32(LB_INCL, excl + run));
-            }
-            s_binoff[b] = a.ghist[((size_t)seg * SORT_PASSES + pass) * SORT_MAX_BINS + b] + excl;
         }
         __syncthreads();
-
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = wbase + k * 32;
-            if (idx < n) {
+            const bool valid = idx < n;
+            u32 pos = 0, val = 0;
+            if (valid) {
                 const u32 d = (key[k] >> shift) & dmask;
-                const u32 pos = s_binoff[d] + s_cnt[warp][d] + rnk[k];
-                kout[base + pos] = key[k];
-                vout[base + pos] = vin[base + off + idx];
+                pos = s_binoff[d] + s_cnt[warp][d] + rnk[k];
+                val = T.vals[src[k]];
+                kout[obase + pos] = key[k];
+                vout[obase + pos] = val;
             }
-        }
-        if (pass + 1 < SORT_PASSES) {
-            uint4* row = (uint4*)(lbn + (size_t)t * SORT_MAX_BINS);
-            row[tid] = make_uint4(0, 0, 0, 0);
+            if (last) {                                       // foreground flags per destination tile (warp-aggregated)
+                const u32 dt = valid && (val & 1u) ? (pos / SORT_TILE) : 0xFFFFFFFFu;
+                const u32 m = __match_any_sync(FULL_MASK, dt);
+                if (dt != 0xFFFFFFFFu && lane == __ffs(m) - 1) atomicAdd(a.tile_fg + tseg0 + dt, (u32)__popc(m));
+            }
         }
     }
 }
 
-// Enqueue plan + histogram + scan + three passes.  keys/vals[0] = input, result in keys/vals[1].
-static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, void* scratch_base, cudaStream_t st) {
-    // tickets + histograms start from zero
-    CUDA_TRY(cudaMemsetAsync((char*)scratch_base + L.tickets, 0, 64, st));
-    CUDA_TRY(cudaMemsetAsync((char*)scratch_base + L.ghist, 0,
-                             sizeof(u32) * (size_t)a.n_seg * SORT_PASSES * SORT_MAX_BINS, st));
-    sort_plan_kernel<<<1, 1024, 0, st>>>(a);
+// Enqueue plan + three (count, scan, scatter) passes.  Result in keys/vals[1].
+static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStream_t st) {
+    sort_plan_kernel<<<1, 1024, 0, st>>>(a, L.max_tiles);
     LAUNCH_CHECK("sort_plan_kernel");
-    const int sms = b200seg_sm_count();
-    sort_hist_kernel<<<sms * 2, SORT_TPB, 0, st>>>(a);
-    LAUNCH_CHECK("sort_hist_kernel");
-    sort_scan_kernel<<<dim3(a.n_seg, SORT_PASSES), SORT_MAX_BINS, 0, st>>>(a);
-    LAUNCH_CHECK("sort_scan_kernel");
     b200seg_stage(4, st);
+    const int sms = b200seg_sm_count();
     for (int p = 0; p < SORT_PASSES; ++p) {
-        sort_pass_kernel<<<sms * 4, SORT_TPB, 0, st>>>(a, p);
-        LAUNCH_CHECK("sort_pass_kernel");
+        sort_count_kernel<<<sms * 4, SORT_TPB, 0, st>>>(a, p);
+        LAUNCH_CHECK("sort_count_kernel");
+        sort_scan_kernel<<<a.n_seg, SORT_MAX_BINS, 0, st>>>(a);
+        LAUNCH_CHECK("sort_scan_kernel");
+        sort_scatter_kernel<<<sms * 4, SORT_TPB, 0, st>>>(a, p);
+        LAUNCH_CHECK("sort_scatter_kernel");
     }
     b200seg_stage(5, st);
     return 0;
