@@ -519,11 +519,11 @@ __global__ void __launch_bounds__(JAC_TPB) jaccard_kernel(LovaszParams p, SortAr
     const u32* vals = a.vals[1];
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         __syncthreads();
-        const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
-        const u32 tseg0 = a.tile_start[seg];
-        const u32 tis = t - tseg0;
-        const u32 off = tis * SORT_TILE;
-        const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
+        const uint4 d4 = a.tile_desc[t];
+        const int seg = (int)d4.x;
+        const u32 off = d4.y, n = d4.z;
+        const u32 tis = off / SORT_TILE;
+        const u32 tseg0 = t - tis;
         const size_t base = (size_t)seg * a.cap + off;
         const int c = seg % p.C;
         const float gts = (float)p.seg_fg[seg];
@@ -920,6 +920,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     a.src_keys = p.keysA; a.src_vals = p.valsA; a.run_prefix = p.run_prefix; a.n_runs = p.n_runs;
     a.run_stride = p.run_stride; a.src_cap = p.src_cap;
     a.tile_start = (u32*)(ss + L.sort.tile_start); a.tilehist = (u32*)(ss + L.sort.tilehist);
+    a.tile_desc = (uint4*)(ss + L.sort.tile_desc);
     a.bin_base = (u32*)(ss + L.sort.bin_base); a.tile_fg = (u32*)(ss + L.sort.tile_fg);
     a.status = p.status;
     if (int rc = sort_enqueue(a, L.sort, st)) return rc;
@@ -1002,6 +1003,7 @@ extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint3
     a.seg_count = counts; a.seg_bits = key_bits; a.n_seg = n_segments; a.cap = capacity;
     a.src_keys = nullptr; a.src_vals = nullptr; a.run_prefix = nullptr; a.n_runs = 0; a.run_stride = 0; a.src_cap = 0;
     a.tile_start = (u32*)(ss + L.tile_start); a.tilehist = (u32*)(ss + L.tilehist);
+    a.tile_desc = (uint4*)(ss + L.tile_desc);
     a.bin_base = (u32*)(ss + L.bin_base); a.tile_fg = (u32*)(ss + L.tile_fg);
     a.status = status;
     return sort_enqueue(a, L, (cudaStream_t)stream);

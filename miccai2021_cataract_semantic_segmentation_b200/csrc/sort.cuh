@@ -40,6 +40,7 @@ struct SortArgs {
     long long run_stride, src_cap;
     // scratch
     u32* tile_start;        // [n_seg + 1] exclusive prefix of tiles per segment
+    uint4* tile_desc;       // [max_tiles] {segment, first element, element count, digit width | first tile << 8 ...}
     u32* tilehist;          // [max_tiles][1024]
     u32* bin_base;          // [n_seg][1024]
     u32* tile_fg;           // [max_tiles] foreground flags per tile of the final order (zeroed by sort_plan_kernel)
@@ -47,7 +48,7 @@ struct SortArgs {
 };
 
 struct SortScratch {
-    size_t tile_start, tilehist, bin_base, tile_fg, total;
+    size_t tile_start, tile_desc, tilehist, bin_base, tile_fg, total;
     u32 max_tiles;
 };
 
@@ -56,6 +57,7 @@ static inline SortScratch sort_scratch_layout(int n_seg, long long total_capacit
     L.max_tiles = (u32)(total_capacity / SORT_TILE + n_seg + 1);
     size_t o = 0;
     L.tile_start = o; o = align_up(o + sizeof(u32) * (size_t)(n_seg + 1), 256);
+    L.tile_desc = o;  o = align_up(o + sizeof(uint4) * (size_t)L.max_tiles, 256);
     L.bin_base = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_MAX_BINS, 256);
     L.tile_fg = o;    o = align_up(o + sizeof(u32) * (size_t)L.max_tiles, 256);
     L.tilehist = o;   o = align_up(o + sizeof(u32) * (size_t)L.max_tiles * SORT_MAX_BINS, 256);
@@ -109,6 +111,18 @@ __global__ void __launch_bounds__(1024) sort_plan_kernel(SortArgs a, u32 max_til
     if (tid == 0) a.tile_start[a.n_seg] = s_carry;
     const u32 total = s_carry;
     for (u32 i = tid; i < total && i < max_tiles; i += 1024) a.tile_fg[i] = 0;
+}
+
+// one thread per tile: {segment, offset of the tile's first element in its segment, element count, digit width}
+// so the per-tile prologue of every later kernel is a single 16-byte load instead of a chain of dependent ones
+__global__ void __launch_bounds__(256) sort_desc_kernel(SortArgs a) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 total = a.tile_start[a.n_seg];
+    if (t >= total) return;
+    const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
+    const u32 off = (t - a.tile_start[seg]) * SORT_TILE;
+    const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
+    a.tile_desc[t] = make_uint4((u32)seg, off, n, sort_digit_width(a.seg_bits[seg]));
 }
 
 // ---- tile addressing (compact or gathered through the run prefix) ------------------------------------------------
@@ -181,27 +195,30 @@ __device__ __forceinline__ size_t tile_src_index(const TileSrc& T, const u32* s_
 }
 
 // ---- count: per-tile digit histogram --------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pass) {
+__global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pass, u32 total_bound) {
     __shared__ u32 s_hist[SORT_MAX_BINS];
     __shared__ u32 s_win[SORT_RUN_WINDOW + 1];
     __shared__ u32 s_pair[2];
     const int tid = threadIdx.x;
-    const u32 total_tiles = a.tile_start[a.n_seg];
+    const u32 total_tiles = min(a.tile_start[a.n_seg], total_bound);
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
-        const u32 off = (t - a.tile_start[seg]) * SORT_TILE;
-        const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
-        const u32 w = sort_digit_width(a.seg_bits[seg]);
+        const uint4 d4 = a.tile_desc[t];
+        const int seg = (int)d4.x;
+        const u32 off = d4.y, n = d4.z, w = d4.w;
         const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
         __syncthreads();                                   // previous iteration done with s_hist / s_win
         for (u32 b = tid; b < nbins; b += SORT_TPB) s_hist[b] = 0;
         const TileSrc T = tile_src_setup(a, pass, seg, off, n, s_win, s_pair);
         __syncthreads();
-#pragma unroll 4
+        u32 key[SORT_KPT];
+#pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = k * SORT_TPB + tid;
-            if (idx < n) atomicAdd(&s_hist[(T.keys[tile_src_index(T, s_win, idx)] >> shift) & dmask], 1u);
+            key[k] = idx < n ? T.keys[tile_src_index(T, s_win, idx)] : 0;
         }
+#pragma unroll
+        for (int k = 0; k < SORT_KPT; ++k)
+            if (k * SORT_TPB + tid < n) atomicAdd(&s_hist[(key[k] >> shift) & dmask], 1u);
         __syncthreads();
         u32* row = a.tilehist + (size_t)t * SORT_MAX_BINS;
         for (u32 b = tid; b < nbins; b += SORT_TPB) row[b] = s_hist[b];
@@ -220,7 +237,14 @@ __global__ void __launch_bounds__(SORT_MAX_BINS) sort_scan_kernel(SortArgs a) {
     if ((u32)tid < nbins) {
         u32* col = a.tilehist + (size_t)t0 * SORT_MAX_BINS + tid;
         u32 t = t0;
-        for (; t + 4 <= t1; t += 4, col += 4 * SORT_MAX_BINS) {          // independent loads, then the running sum
+        for (; t + 16 <= t1; t += 16, col += 16 * SORT_MAX_BINS) {       // 16 independent loads, then the running sum
+            u32 x[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = col[i * SORT_MAX_BINS];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { col[i * SORT_MAX_BINS] = run; run += x[i]; }
+        }
+        for (; t + 4 <= t1; t += 4, col += 4 * SORT_MAX_BINS) {
             const u32 x0 = col[0], x1 = col[SORT_MAX_BINS], x2 = col[2 * SORT_MAX_BINS], x3 = col[3 * SORT_MAX_BINS];
             col[0] = run; run += x0;
             col[SORT_MAX_BINS] = run; run += x1;
@@ -245,14 +269,26 @@ __global__ void __launch_bounds__(SORT_MAX_BINS) sort_scan_kernel(SortArgs a) {
 }
 
 // ---- scatter ----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int pass) {
-    __shared__ u32 s_cnt[SORT_WARPS][SORT_MAX_BINS + 1];
-    __shared__ u32 s_binoff[SORT_MAX_BINS];
-    __shared__ u32 s_win[SORT_RUN_WINDOW + 1];
-    __shared__ u32 s_pair[2];
+// Elements are first placed at their tile-local sorted position in shared memory, then streamed out so that the
+// lanes of a warp write consecutive addresses within each digit bin (a fully scattered 4-byte store costs the LSU
+// one wavefront per lane).
+struct ScatterSmem {
+    unsigned short cnt[SORT_WARPS][SORT_MAX_BINS + 2];   // per-warp digit counters -> exclusive offsets across warps
+    unsigned short binexcl[SORT_MAX_BINS];               // exclusive prefix of the tile's bin totals
+    u32 binoff[SORT_MAX_BINS];                           // global position of local sorted index i in bin d: binoff[d] + i
+    u32 keys[SORT_TILE];
+    u32 vals[SORT_TILE];
+    u32 win[SORT_RUN_WINDOW + 1];
+    u32 warp_sum[SORT_WARPS];
+    u32 pair[2];
+};
+
+__global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1;
-    const u32 total_tiles = a.tile_start[a.n_seg];
+    const u32 total_tiles = min(a.tile_start[a.n_seg], total_bound);
     // (static indexing only: a dynamically indexed kernel-parameter array would be copied to local memory)
     const bool odd = pass & 1;
     u32* __restrict__ kout = odd ? a.keys[0] : a.keys[1];
@@ -260,32 +296,29 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
     const bool last = pass == SORT_PASSES - 1;
 
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
-        const u32 tseg0 = a.tile_start[seg];
-        const u32 off = (t - tseg0) * SORT_TILE;
-        const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
-        const u32 w = sort_digit_width(a.seg_bits[seg]);
+        const uint4 d4 = a.tile_desc[t];
+        const int seg = (int)d4.x;
+        const u32 off = d4.y, n = d4.z, w = d4.w;
+        const u32 tseg0 = t - off / SORT_TILE;
         const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
         const size_t obase = (size_t)seg * a.cap;
         __syncthreads();
-        for (u32 i = tid; i < SORT_WARPS * (SORT_MAX_BINS + 1); i += SORT_TPB) {
-            const u32 b = i % (SORT_MAX_BINS + 1);
-            if (b <= nbins) (&s_cnt[0][0])[i] = 0;
+        {
+            u32* z = reinterpret_cast<u32*>(&S.cnt[0][0]);
+            for (u32 i = tid; i < sizeof(S.cnt) / 4; i += SORT_TPB) z[i] = 0;
         }
-        for (u32 b = tid; b < nbins; b += SORT_TPB)
-            s_binoff[b] = a.bin_base[(size_t)seg * SORT_MAX_BINS + b] + a.tilehist[(size_t)t * SORT_MAX_BINS + b];
-        const TileSrc T = tile_src_setup(a, pass, seg, off, n, s_win, s_pair);
+        const TileSrc T = tile_src_setup(a, pass, seg, off, n, S.win, S.pair);
         __syncthreads();
 
-        u32 key[SORT_KPT];
-        u32 src[SORT_KPT];                                     // source index relative to the source arrays (< 2^31)
+        u32 key[SORT_KPT], val[SORT_KPT];
         unsigned short rnk[SORT_KPT];
         const u32 wbase = warp * (32 * SORT_KPT) + lane;
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = wbase + k * 32;
-            src[k] = idx < n ? (u32)tile_src_index(T, s_win, idx) : 0;
-            key[k] = idx < n ? T.keys[src[k]] : 0xFFFFFFFFu;
+            const u32 src = idx < n ? (u32)tile_src_index(T, S.win, idx) : 0;
+            key[k] = idx < n ? T.keys[src] : 0xFFFFFFFFu;
+            val[k] = idx < n ? T.vals[src] : 0;
         }
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
@@ -294,32 +327,67 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
             const u32 m = __match_any_sync(FULL_MASK, d);
             const int leader = __ffs(m) - 1;
             u32 old = 0;
-            if (lane == leader) { old = s_cnt[warp][d]; s_cnt[warp][d] = old + __popc(m); }
+            if (lane == leader) { old = S.cnt[warp][d]; S.cnt[warp][d] = (unsigned short)(old + __popc(m)); }
             old = __shfl_sync(FULL_MASK, old, leader);
             rnk[k] = (unsigned short)(old + __popc(m & lt_mask));
             __syncwarp();
         }
         __syncthreads();
-        for (u32 b = tid; b < nbins; b += SORT_TPB) {       // per-warp counts -> exclusive offsets across warps
-            u32 run = 0;
+        // thread b owns bins [4b, 4b+4): per-warp counts -> exclusive offsets across warps, bin totals -> block scan
+        u32 tot[4], tsum = 0;
 #pragma unroll
-            for (int w2 = 0; w2 < SORT_WARPS; ++w2) { const u32 c = s_cnt[w2][b]; s_cnt[w2][b] = run; run += c; }
+        for (int j = 0; j < 4; ++j) {
+            const u32 b = 4 * tid + j;
+            u32 run = 0;
+            if (b < nbins) {
+#pragma unroll
+                for (int w2 = 0; w2 < SORT_WARPS; ++w2) { const u32 c = S.cnt[w2][b]; S.cnt[w2][b] = (unsigned short)run; run += c; }
+            }
+            tot[j] = run; tsum += run;
+        }
+        u32 v = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
+        if (lane == 31) S.warp_sum[warp] = v;
+        __syncthreads();
+        u32 excl = v - tsum;
+#pragma unroll
+        for (int w2 = 0; w2 < SORT_WARPS; ++w2) if (w2 < warp) excl += S.warp_sum[w2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const u32 b = 4 * tid + j;
+            if (b < nbins) {
+                S.binexcl[b] = (unsigned short)excl;
+                S.binoff[b] = a.bin_base[(size_t)seg * SORT_MAX_BINS + b] + a.tilehist[(size_t)t * SORT_MAX_BINS + b] - excl;
+            }
+            excl += tot[j];
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = wbase + k * 32;
-            const bool valid = idx < n;
-            u32 pos = 0, val = 0;
-            if (valid) {
+            if (idx < n) {
                 const u32 d = (key[k] >> shift) & dmask;
-                pos = s_binoff[d] + s_cnt[warp][d] + rnk[k];
-                val = T.vals[src[k]];
-                kout[obase + pos] = key[k];
-                vout[obase + pos] = val;
+                const u32 lpos = (u32)S.binexcl[d] + S.cnt[warp][d] + rnk[k];
+                S.keys[lpos] = key[k];
+                S.vals[lpos] = val[k];
+            }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < SORT_KPT; ++k) {
+            const u32 i = k * SORT_TPB + tid;
+            const bool valid = i < n;
+            u32 pos = 0, vv = 0;
+            if (valid) {
+                const u32 kk = S.keys[i];
+                vv = S.vals[i];
+                pos = S.binoff[(kk >> shift) & dmask] + i;
+                kout[obase + pos] = kk;
+                vout[obase + pos] = vv;
             }
             if (last) {                                       // foreground flags per destination tile (warp-aggregated)
-                const u32 dt = valid && (val & 1u) ? (pos / SORT_TILE) : 0xFFFFFFFFu;
+                const u32 dt = valid && (vv & 1u) ? (pos / SORT_TILE) : 0xFFFFFFFFu;
                 const u32 m = __match_any_sync(FULL_MASK, dt);
                 if (dt != 0xFFFFFFFFu && lane == __ffs(m) - 1) atomicAdd(a.tile_fg + tseg0 + dt, (u32)__popc(m));
             }
@@ -327,18 +395,30 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
     }
 }
 
-// Enqueue plan + three (count, scan, scatter) passes.  Result in keys/vals[1].
+// Enqueue plan + descriptors + three (count, scan, scatter) passes.  Result in keys/vals[1].
 static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStream_t st) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {          // opt in to > 48 KB of dynamic shared memory, once per device
+        CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(ScatterSmem)));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     sort_plan_kernel<<<1, 1024, 0, st>>>(a, L.max_tiles);
     LAUNCH_CHECK("sort_plan_kernel");
+    sort_desc_kernel<<<(L.max_tiles + 255) / 256, 256, 0, st>>>(a);
+    LAUNCH_CHECK("sort_desc_kernel");
     b200seg_stage(4, st);
     const int sms = b200seg_sm_count();
+    const u32 cgrid = L.max_tiles < (u32)sms * 8 ? L.max_tiles : (u32)sms * 8;
+    const u32 sgrid = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;
     for (int p = 0; p < SORT_PASSES; ++p) {
-        sort_count_kernel<<<sms * 4, SORT_TPB, 0, st>>>(a, p);
+        sort_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_count_kernel");
         sort_scan_kernel<<<a.n_seg, SORT_MAX_BINS, 0, st>>>(a);
         LAUNCH_CHECK("sort_scan_kernel");
-        sort_scatter_kernel<<<sms * 4, SORT_TPB, 0, st>>>(a, p);
+        sort_scatter_kernel<<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_scatter_kernel");
     }
     b200seg_stage(5, st);
