@@ -4,9 +4,9 @@
 //
 // One streaming pass over the logits (4*C + label bytes per pixel, the roofline of this path): every thread takes
 // four consecutive pixels with 128-bit loads per class plane, keeps the running first-maximum, and adds
-// (pred*C + label) to a shared-memory histogram private to the CTA.  Adds are warp-aggregated with match.any so
-// blocky real label maps (whole warps hitting one bin) cost one shared atomic per distinct bin, not 32 serialised
-// ones.  CTAs are persistent (a few per SM) and flush non-zero bins to the int64 matrix once at the end.
+// (pred*C + label) to a shared-memory histogram private to the CTA (same-bin lanes serialise inside the atomic unit;
+// cheaper than any warp pre-aggregation, see cm_add).  CTAs are persistent (a few per SM) and flush non-zero bins to
+// the int64 matrix once at the end.
 #include "b200seg.h"
 #include "common.cuh"
 
@@ -22,9 +22,10 @@ struct ConfmatParams {
     int* status;
 };
 
+// Plain shared-memory atomics: lanes hitting one bin serialise at ~1 lane/cycle (32 cycles for a fully uniform warp),
+// far cheaper than aggregating with match.any first (MATCH.ANY measured at ~250 cycles per warp instruction here).
 __device__ __forceinline__ void cm_add(u32* s_cm, u32 bin) {
-    const u32 m = __match_any_sync(FULL_MASK, bin);
-    if (bin != 0xFFFFFFFFu && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(s_cm + bin, (u32)__popc(m));
+    if (bin != 0xFFFFFFFFu) atomicAdd(s_cm + bin, 1u);
 }
 __device__ __forceinline__ u32 cm_bin(const ConfmatParams& p, int lab, int arg, int C, u32& oob) {
     if (p.has_drop && lab == p.drop) return 0xFFFFFFFFu;

@@ -493,14 +493,22 @@ __global__ void __launch_bounds__(256) run_scan_kernel(LovaszParams p) {
     const int g = seg / p.C, c = seg - g * p.C;
     u32* out = p.run_prefix + (size_t)seg * (p.n_runs + 1);
     u32 carry = 0;
-    for (int r0 = 0; r0 < p.n_runs; r0 += 32) {
-        const int r = r0 + lane;
-        const u32 x = r < p.n_runs ? p.run_cnt[((size_t)g * p.n_runs + r) * p.C + c] : 0;
-        u32 v = x;
+    for (int base = 0; base < p.n_runs; base += 1024) {                 // 32 independent loads per lane, then the scans
+        u32 x[32];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
-        if (r < p.n_runs) out[r] = carry + v - x;
-        carry += __shfl_sync(FULL_MASK, v, 31);
+        for (int i = 0; i < 32; ++i) {
+            const int r = base + i * 32 + lane;
+            x[i] = r < p.n_runs ? p.run_cnt[((size_t)g * p.n_runs + r) * p.C + c] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int r = base + i * 32 + lane;
+            u32 v = x[i];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
+            if (r < p.n_runs) out[r] = carry + v - x[i];
+            carry += __shfl_sync(FULL_MASK, v, 31);
+        }
     }
     if (lane == 0) { out[p.n_runs] = carry; p.seg_count[seg] = carry; }
 }
@@ -920,7 +928,8 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     a.src_keys = p.keysA; a.src_vals = p.valsA; a.run_prefix = p.run_prefix; a.n_runs = p.n_runs;
     a.run_stride = p.run_stride; a.src_cap = p.src_cap;
     a.tile_start = (u32*)(ss + L.sort.tile_start); a.tilehist = (u32*)(ss + L.sort.tilehist);
-    a.tile_desc = (uint4*)(ss + L.sort.tile_desc);
+    a.tile_desc = (uint4*)(ss + L.sort.tile_desc); a.tile_runs = (uint2*)(ss + L.sort.tile_runs);
+    a.seg_done = (u32*)(ss + L.sort.seg_done);
     a.bin_base = (u32*)(ss + L.sort.bin_base); a.tile_fg = (u32*)(ss + L.sort.tile_fg);
     a.status = p.status;
     if (int rc = sort_enqueue(a, L.sort, st)) return rc;
@@ -1003,7 +1012,8 @@ extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint3
     a.seg_count = counts; a.seg_bits = key_bits; a.n_seg = n_segments; a.cap = capacity;
     a.src_keys = nullptr; a.src_vals = nullptr; a.run_prefix = nullptr; a.n_runs = 0; a.run_stride = 0; a.src_cap = 0;
     a.tile_start = (u32*)(ss + L.tile_start); a.tilehist = (u32*)(ss + L.tilehist);
-    a.tile_desc = (uint4*)(ss + L.tile_desc);
+    a.tile_desc = (uint4*)(ss + L.tile_desc); a.tile_runs = (uint2*)(ss + L.tile_runs);
+    a.seg_done = (u32*)(ss + L.seg_done);
     a.bin_base = (u32*)(ss + L.bin_base); a.tile_fg = (u32*)(ss + L.tile_fg);
     a.status = status;
     return sort_enqueue(a, L, (cudaStream_t)stream);

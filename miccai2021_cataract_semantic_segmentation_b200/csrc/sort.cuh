@@ -6,10 +6,11 @@
 // Layout in HBM: segment s owns [s*cap, s*cap + seg_count[s]) of each ping-pong array.  Keys carry at most
 // seg_bits[s] <= 30 significant bits, so exactly three digit passes of w = ceil(bits/3) <= 10 bits are run
 // (src -> B -> A -> B; the result always lands in buffer 1).  Segments have few tiles (tens), all running at the
-// same time, so a chained scan would serialise; each pass is three short kernels instead:
-//   count    per-tile digit histogram (shared-memory atomics)                    -> tilehist[tile][bin]
-//   scan     per segment: column scan over its tiles + exclusive scan over bins  -> tilehist (tile offsets), bin_base
-//   scatter  re-read the tile (L2), stable ranks (warp match + per-warp counters), write to the other buffer
+// same time, so a chained scan would serialise; each pass is two short kernels instead:
+//   count    per-tile digit histogram (shared-memory atomics) -> tilehist[tile][bin]; the CTA that finishes a segment's
+//            last tile scans it: column scan over its tiles + exclusive scan over bins -> tile offsets, bin_base
+//   scatter  re-read the tile (L2), stable ranks (ballot peer masks + per-warp counters), reorder in shared memory,
+//            write to the other buffer with warp-contiguous stores
 // The first pass can read a "holey" source: every segment is a concatenation of n_runs runs, run r starting at
 // s*src_cap + r*run_stride with run_prefix[s][r+1]-run_prefix[s][r] elements (what the emission kernel leaves
 // behind without any cross-CTA ordering); elements are gathered by binary search over the run prefix.
@@ -40,7 +41,9 @@ struct SortArgs {
     long long run_stride, src_cap;
     // scratch
     u32* tile_start;        // [n_seg + 1] exclusive prefix of tiles per segment
-    uint4* tile_desc;       // [max_tiles] {segment, first element, element count, digit width | first tile << 8 ...}
+    uint4* tile_desc;       // [max_tiles] {segment, first element, element count, digit width}
+    uint2* tile_runs;       // [max_tiles] {first, last} source run intersecting the tile (holey pass-0 source only)
+    u32* seg_done;          // [SORT_PASSES][n_seg] tiles counted so far (last CTA of a segment runs its scan)
     u32* tilehist;          // [max_tiles][1024]
     u32* bin_base;          // [n_seg][1024]
     u32* tile_fg;           // [max_tiles] foreground flags per tile of the final order (zeroed by sort_plan_kernel)
@@ -48,7 +51,7 @@ struct SortArgs {
 };
 
 struct SortScratch {
-    size_t tile_start, tile_desc, tilehist, bin_base, tile_fg, total;
+    size_t tile_start, tile_desc, tile_runs, seg_done, tilehist, bin_base, tile_fg, total;
     u32 max_tiles;
 };
 
@@ -58,6 +61,8 @@ static inline SortScratch sort_scratch_layout(int n_seg, long long total_capacit
     size_t o = 0;
     L.tile_start = o; o = align_up(o + sizeof(u32) * (size_t)(n_seg + 1), 256);
     L.tile_desc = o;  o = align_up(o + sizeof(uint4) * (size_t)L.max_tiles, 256);
+    L.tile_runs = o;  o = align_up(o + sizeof(uint2) * (size_t)L.max_tiles, 256);
+    L.seg_done = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_PASSES, 256);
     L.bin_base = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_MAX_BINS, 256);
     L.tile_fg = o;    o = align_up(o + sizeof(u32) * (size_t)L.max_tiles, 256);
     L.tilehist = o;   o = align_up(o + sizeof(u32) * (size_t)L.max_tiles * SORT_MAX_BINS, 256);
@@ -111,6 +116,15 @@ __global__ void __launch_bounds__(1024) sort_plan_kernel(SortArgs a, u32 max_til
     if (tid == 0) a.tile_start[a.n_seg] = s_carry;
     const u32 total = s_carry;
     for (u32 i = tid; i < total && i < max_tiles; i += 1024) a.tile_fg[i] = 0;
+    for (int i = tid; i < a.n_seg * SORT_PASSES; i += 1024) a.seg_done[i] = 0;
+}
+
+__device__ __forceinline__ u32 upper_run(const u32* prefix, u32 lo, u32 hi, u32 v) {   // largest r in [lo,hi]: prefix[r] <= v
+    while (lo < hi) {
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (prefix[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
 }
 
 // one thread per tile: {segment, offset of the tile's first element in its segment, element count, digit width}
@@ -123,6 +137,10 @@ __global__ void __launch_bounds__(256) sort_desc_kernel(SortArgs a) {
     const u32 off = (t - a.tile_start[seg]) * SORT_TILE;
     const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
     a.tile_desc[t] = make_uint4((u32)seg, off, n, sort_digit_width(a.seg_bits[seg]));
+    if (a.run_prefix) {
+        const u32* prefix = a.run_prefix + (size_t)seg * (a.n_runs + 1);
+        a.tile_runs[t] = make_uint2(upper_run(prefix, 0, a.n_runs - 1, off), upper_run(prefix, 0, a.n_runs - 1, off + n - 1));
+    }
 }
 
 // ---- tile addressing (compact or gathered through the run prefix) ------------------------------------------------
@@ -140,17 +158,8 @@ struct TileSrc {
     bool window;            // prefix[r_lo .. r_hi + 1] staged in shared memory
 };
 
-__device__ __forceinline__ u32 upper_run(const u32* prefix, u32 lo, u32 hi, u32 v) {   // largest r in [lo,hi]: prefix[r] <= v
-    while (lo < hi) {
-        const u32 mid = (lo + hi + 1) >> 1;
-        if (prefix[mid] <= v) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
-// Block-wide setup; s_win needs SORT_RUN_WINDOW + 1 entries.  Contains __syncthreads().
-__device__ __forceinline__ TileSrc tile_src_setup(const SortArgs& a, int pass, int seg, u32 off, u32 n, u32* s_win,
-                                                  u32* s_pair) {
+// Block-wide setup; s_win needs SORT_RUN_WINDOW + 1 entries.  Contains a __syncthreads() when gathering.
+__device__ __forceinline__ TileSrc tile_src_setup(const SortArgs& a, int pass, u32 t, int seg, u32 off, u32* s_win) {
     TileSrc T;
     const bool odd = pass & 1;
     T.gather = (pass == 0 && a.run_prefix != nullptr);
@@ -166,12 +175,8 @@ __device__ __forceinline__ TileSrc tile_src_setup(const SortArgs& a, int pass, i
     T.voff = off;
     T.seg_base = (size_t)seg * a.src_cap;
     T.run_stride = a.run_stride;
-    if (threadIdx.x == 0) {
-        s_pair[0] = upper_run(T.prefix, 0, a.n_runs - 1, off);
-        s_pair[1] = upper_run(T.prefix, 0, a.n_runs - 1, off + n - 1);
-    }
-    __syncthreads();
-    T.r_lo = s_pair[0]; T.r_hi = s_pair[1];
+    const uint2 rr = a.tile_runs[t];
+    T.r_lo = rr.x; T.r_hi = rr.y;
     T.window = (T.r_hi - T.r_lo + 2) <= SORT_RUN_WINDOW + 1;
     if (T.window)
         for (u32 i = threadIdx.x; i < T.r_hi - T.r_lo + 2; i += blockDim.x) s_win[i] = T.prefix[T.r_lo + i];
@@ -194,11 +199,54 @@ __device__ __forceinline__ size_t tile_src_index(const TileSrc& T, const u32* s_
     return T.seg_base + (size_t)r * T.run_stride + (v - start);
 }
 
-// ---- count: per-tile digit histogram --------------------------------------------------------------------------------
+// ---- per-segment scan, run by the CTA that counted the segment's last tile ---------------------------------------------
+// column scan over the segment's tiles (tilehist[tile][bin] -> exclusive offset of the tile within the bin) and
+// exclusive scan over the bin totals (-> bin_base).  256 threads, thread b owns bins [4b, 4b+4).
+__device__ __forceinline__ void segment_scan(const SortArgs& a, int seg, u32 t0, u32 t1, u32 nbins, u32* s_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 tot[4] = {0, 0, 0, 0};
+    if ((u32)(4 * tid) < nbins) {
+        uint4* col = reinterpret_cast<uint4*>(a.tilehist + (size_t)t0 * SORT_MAX_BINS + 4 * tid);
+        constexpr int STRIDE = SORT_MAX_BINS / 4;
+        u32 t = t0;
+        for (; t + 8 <= t1; t += 8, col += 8 * STRIDE) {                 // 8 independent 16-byte loads, then the sums
+            uint4 x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __ldcg(col + i * STRIDE);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                col[i * STRIDE] = make_uint4(tot[0], tot[1], tot[2], tot[3]);
+                tot[0] += x[i].x; tot[1] += x[i].y; tot[2] += x[i].z; tot[3] += x[i].w;
+            }
+        }
+        for (; t < t1; ++t, col += STRIDE) {
+            const uint4 x = __ldcg(col);
+            *col = make_uint4(tot[0], tot[1], tot[2], tot[3]);
+            tot[0] += x.x; tot[1] += x.y; tot[2] += x.z; tot[3] += x.w;
+        }
+    }
+    const u32 tsum = tot[0] + tot[1] + tot[2] + tot[3];
+    u32 v = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    u32 excl = v - tsum;
+#pragma unroll
+    for (int w2 = 0; w2 < SORT_WARPS; ++w2) if (w2 < warp) excl += s_warp[w2];
+    if ((u32)(4 * tid) < nbins) {
+        u32* bb = a.bin_base + (size_t)seg * SORT_MAX_BINS + 4 * tid;
+        *reinterpret_cast<uint4*>(bb) = make_uint4(excl, excl + tot[0], excl + tot[0] + tot[1], excl + tot[0] + tot[1] + tot[2]);
+    }
+    __syncthreads();
+}
+
+// ---- count: per-tile digit histogram (+ the segment's scan once its last tile is in) ---------------------------------
 __global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pass, u32 total_bound) {
-    __shared__ u32 s_hist[SORT_MAX_BINS];
+    __shared__ __align__(16) u32 s_hist[SORT_MAX_BINS];
     __shared__ u32 s_win[SORT_RUN_WINDOW + 1];
-    __shared__ u32 s_pair[2];
+    __shared__ u32 s_warp[SORT_WARPS];
+    __shared__ u32 s_last;
     const int tid = threadIdx.x;
     const u32 total_tiles = min(a.tile_start[a.n_seg], total_bound);
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -207,8 +255,8 @@ __global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pa
         const u32 off = d4.y, n = d4.z, w = d4.w;
         const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
         __syncthreads();                                   // previous iteration done with s_hist / s_win
-        for (u32 b = tid; b < nbins; b += SORT_TPB) s_hist[b] = 0;
-        const TileSrc T = tile_src_setup(a, pass, seg, off, n, s_win, s_pair);
+        for (u32 b = tid; b < SORT_MAX_BINS; b += SORT_TPB) s_hist[b] = 0;
+        const TileSrc T = tile_src_setup(a, pass, t, seg, off, s_win);
         __syncthreads();
         u32 key[SORT_KPT];
 #pragma unroll
@@ -220,58 +268,41 @@ __global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pa
         for (int k = 0; k < SORT_KPT; ++k)
             if (k * SORT_TPB + tid < n) atomicAdd(&s_hist[(key[k] >> shift) & dmask], 1u);
         __syncthreads();
-        u32* row = a.tilehist + (size_t)t * SORT_MAX_BINS;
-        for (u32 b = tid; b < nbins; b += SORT_TPB) row[b] = s_hist[b];
-    }
-}
-
-// ---- scan: one block per segment ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_MAX_BINS) sort_scan_kernel(SortArgs a) {
-    __shared__ u32 s_warp[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int seg = blockIdx.x;
-    const u32 t0 = a.tile_start[seg], t1 = a.tile_start[seg + 1];
-    if (t0 == t1) return;
-    const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]);
-    u32 run = 0;
-    if ((u32)tid < nbins) {
-        u32* col = a.tilehist + (size_t)t0 * SORT_MAX_BINS + tid;
-        u32 t = t0;
-        for (; t + 16 <= t1; t += 16, col += 16 * SORT_MAX_BINS) {       // 16 independent loads, then the running sum
-            u32 x[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = col[i * SORT_MAX_BINS];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { col[i * SORT_MAX_BINS] = run; run += x[i]; }
+        uint4* row = reinterpret_cast<uint4*>(a.tilehist + (size_t)t * SORT_MAX_BINS);
+        if ((u32)(4 * tid) < nbins) __stcg(row + tid, reinterpret_cast<const uint4*>(s_hist)[tid]);
+        // last CTA to finish a tile of this segment scans the segment
+        __threadfence();
+        __syncthreads();
+        const u32 tseg0 = t - off / SORT_TILE;
+        const u32 ntiles_seg = (a.seg_count[seg] + SORT_TILE - 1) / SORT_TILE;
+        if (tid == 0) s_last = (atomicAdd(a.seg_done + (size_t)pass * a.n_seg + seg, 1u) == ntiles_seg - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            segment_scan(a, seg, tseg0, tseg0 + ntiles_seg, nbins, s_warp);
         }
-        for (; t + 4 <= t1; t += 4, col += 4 * SORT_MAX_BINS) {
-            const u32 x0 = col[0], x1 = col[SORT_MAX_BINS], x2 = col[2 * SORT_MAX_BINS], x3 = col[3 * SORT_MAX_BINS];
-            col[0] = run; run += x0;
-            col[SORT_MAX_BINS] = run; run += x1;
-            col[2 * SORT_MAX_BINS] = run; run += x2;
-            col[3 * SORT_MAX_BINS] = run; run += x3;
-        }
-        for (; t < t1; ++t, col += SORT_MAX_BINS) { const u32 x = *col; *col = run; run += x; }
     }
-    u32 v = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
-    if (lane == 31) s_warp[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        u32 wv = s_warp[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, wv, o); if (lane >= o) wv += y; }
-        s_warp[lane] = wv;
-    }
-    __syncthreads();
-    if ((u32)tid < nbins) a.bin_base[(size_t)seg * SORT_MAX_BINS + tid] = v - run + (warp ? s_warp[warp - 1] : 0);
 }
 
 // ---- scatter ----------------------------------------------------------------------------------------------------------------
 // Elements are first placed at their tile-local sorted position in shared memory, then streamed out so that the
 // lanes of a warp write consecutive addresses within each digit bin (a fully scattered 4-byte store costs the LSU
 // one wavefront per lane).
+// lanes holding the same digit (what match.any returns, but built from ballots: MATCH.ANY costs ~250 cycles per warp
+// instruction on this part, a ballot a few)
+__device__ __forceinline__ u32 peer_mask(u32 d, u32 nbits) {
+    u32 peers = FULL_MASK;
+#pragma unroll
+    for (u32 b = 0; b < 11; ++b) {
+        if (b < nbits) {
+            const bool bit = (d >> b) & 1u;
+            const u32 m = __ballot_sync(FULL_MASK, bit);
+            peers &= bit ? m : ~m;
+        }
+    }
+    return peers;
+}
+
 struct ScatterSmem {
     unsigned short cnt[SORT_WARPS][SORT_MAX_BINS + 2];   // per-warp digit counters -> exclusive offsets across warps
     unsigned short binexcl[SORT_MAX_BINS];               // exclusive prefix of the tile's bin totals
@@ -280,7 +311,6 @@ struct ScatterSmem {
     u32 vals[SORT_TILE];
     u32 win[SORT_RUN_WINDOW + 1];
     u32 warp_sum[SORT_WARPS];
-    u32 pair[2];
 };
 
 __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
@@ -307,7 +337,7 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
             u32* z = reinterpret_cast<u32*>(&S.cnt[0][0]);
             for (u32 i = tid; i < sizeof(S.cnt) / 4; i += SORT_TPB) z[i] = 0;
         }
-        const TileSrc T = tile_src_setup(a, pass, seg, off, n, S.win, S.pair);
+        const TileSrc T = tile_src_setup(a, pass, t, seg, off, S.win);
         __syncthreads();
 
         u32 key[SORT_KPT], val[SORT_KPT];
@@ -324,7 +354,7 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = wbase + k * 32;
             const u32 d = idx < n ? ((key[k] >> shift) & dmask) : nbins;     // padding lanes share the dummy bin
-            const u32 m = __match_any_sync(FULL_MASK, d);
+            const u32 m = peer_mask(d, w + 1);
             const int leader = __ffs(m) - 1;
             u32 old = 0;
             if (lane == leader) { old = S.cnt[warp][d]; S.cnt[warp][d] = (unsigned short)(old + __popc(m)); }
@@ -387,15 +417,23 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
                 vout[obase + pos] = vv;
             }
             if (last) {                                       // foreground flags per destination tile (warp-aggregated)
-                const u32 dt = valid && (vv & 1u) ? (pos / SORT_TILE) : 0xFFFFFFFFu;
-                const u32 m = __match_any_sync(FULL_MASK, dt);
-                if (dt != 0xFFFFFFFFu && lane == __ffs(m) - 1) atomicAdd(a.tile_fg + tseg0 + dt, (u32)__popc(m));
+                const bool fg = valid && (vv & 1u);
+                const u32 dt = pos / SORT_TILE;
+                const u32 fgm = __ballot_sync(FULL_MASK, fg);
+                if (fgm) {
+                    const u32 dt0 = __shfl_sync(FULL_MASK, dt, __ffs(fgm) - 1);
+                    if (__all_sync(FULL_MASK, !fg || dt == dt0)) {       // one destination tile for the whole warp: usual
+                        if (lane == 0) atomicAdd(a.tile_fg + tseg0 + dt0, (u32)__popc(fgm));
+                    } else if (fg) {
+                        atomicAdd(a.tile_fg + tseg0 + dt, 1u);
+                    }
+                }
             }
         }
     }
 }
 
-// Enqueue plan + descriptors + three (count, scan, scatter) passes.  Result in keys/vals[1].
+// Enqueue plan + descriptors + three (count+scan, scatter) passes.  Result in keys/vals[1].
 static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStream_t st) {
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -416,8 +454,6 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     for (int p = 0; p < SORT_PASSES; ++p) {
         sort_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_count_kernel");
-        sort_scan_kernel<<<a.n_seg, SORT_MAX_BINS, 0, st>>>(a);
-        LAUNCH_CHECK("sort_scan_kernel");
         sort_scatter_kernel<<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_scatter_kernel");
     }
