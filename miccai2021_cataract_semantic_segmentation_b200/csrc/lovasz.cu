@@ -18,6 +18,7 @@
 #include "b200seg.h"
 #include "common.cuh"
 #include "sort.cuh"
+#include "pipe.cuh"
 
 #define STATS_TPB 128
 #define EMIT_TPB 256
@@ -180,21 +181,22 @@ __device__ __forceinline__ void stats_pixel_tail(const LovaszParams& p, StatsSme
     }
 }
 
-template <int CT, typename LT>
-__global__ void __launch_bounds__(STATS_TPB) stats_kernel_v4(LovaszParams p) {
+// VEC consecutive pixels per thread, all C logits of those pixels in registers (C*VEC independent exp chains).
+template <int CT, int VEC, int TPB, typename LT>
+__global__ void __launch_bounds__(TPB) stats_kernel_vec(LovaszParams p) {
     __shared__ StatsSmem sm;
     const int tid = threadIdx.x;
-    constexpr int TILE_PX = STATS_TPB * 4;
+    constexpr int TILE_PX = TPB * VEC;
     const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
     const long long ntiles = tpi * p.N;
     const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
-    for (int i = tid; i < (int)(sizeof(StatsSmem) / 4); i += STATS_TPB) ((u32*)&sm)[i] = 0;
+    for (int i = tid; i < (int)(sizeof(StatsSmem) / 4); i += TPB) ((u32*)&sm)[i] = 0;
     __syncthreads();
     int cur_g = -1;
     u32 nvalid = 0;
     for (long long t = t0; t < t1; ++t) {
         const int n = (int)(t / tpi);
-        const long long q0 = (t - (long long)n * tpi) * TILE_PX + tid * 4;
+        const long long q0 = (t - (long long)n * tpi) * TILE_PX + tid * VEC;
         const int g = p.per_image ? n : 0;
         if (g != cur_g) {
             if (cur_g >= 0) { if (nvalid) atomicAdd(&sm.valid, nvalid); nvalid = 0; stats_flush_group(p, sm, cur_g); }
@@ -202,34 +204,58 @@ __global__ void __launch_bounds__(STATS_TPB) stats_kernel_v4(LovaszParams p) {
         }
         if (q0 >= p.HW) continue;
         const float* lp = p.logits + (size_t)n * CT * p.HW + q0;
-        float z[CT][4];
+        const size_t px = (size_t)n * p.HW + q0;
+        int lab[VEC];
+        if constexpr (VEC == 4) load_labels4<LT>(p.labels, px, lab);
+        else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) lab[j] = load_label<LT>(p.labels, px + j);
+        }
+        float z[CT][VEC];
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
-            const float4 v = ld_stream4(lp + (size_t)c * p.HW);
-            z[c][0] = v.x; z[c][1] = v.y; z[c][2] = v.z; z[c][3] = v.w;
+            if constexpr (VEC == 4) {
+                const float4 v = ld_stream4(lp + (size_t)c * p.HW);
+                z[c][0] = v.x; z[c][1] = v.y; z[c][2] = v.z; z[c][3] = v.w;
+            } else {
+                const float2 v = ld_stream2(lp + (size_t)c * p.HW);
+                z[c][0] = v.x; z[c][1] = v.y;
+            }
         }
-        int lab[4];
-        const size_t px = (size_t)n * p.HW + q0;
-        load_labels4<LT>(p.labels, px, lab);
-        float mo[4], so[4];
+        // the logit of the pixel's own class: a dependent re-read (L2 hit) is cheaper than a C-way select chain
+        float zl[VEC];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float m = z[0][j], best = z[0][j];
+        for (int j = 0; j < VEC; ++j) zl[j] = (unsigned)lab[j] < (unsigned)CT ? __ldg(lp + (size_t)lab[j] * p.HW + j) : 0.f;
+        float mo[VEC], so[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float m = z[0][j];
+#pragma unroll
+            for (int c = 1; c < CT; ++c) m = fmaxf(m, z[c][j]);
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) s = __fadd_rn(s, sm_exp(z[c][j], m));
             int arg = 0;
+            if (p.cm) {
 #pragma unroll
-            for (int c = 1; c < CT; ++c) { m = fmaxf(m, z[c][j]); argmax_step(z[c][j], c, best, arg); }
-            float s = 0.f, e_lab = 0.f;
+                for (int c = CT - 1; c >= 0; --c) arg = (z[c][j] == m) ? c : arg;      // first maximum
+                if (s != s || m != m) {                   // NaN / inf among the logits: torch's argmax lets NaN win
+                    float best = z[0][j];
+                    arg = 0;
 #pragma unroll
-            for (int c = 0; c < CT; ++c) {
-                const float e = sm_exp(z[c][j], m);
-                s = __fadd_rn(s, e);
-                e_lab = (c == lab[j]) ? e : e_lab;
+                    for (int c = 1; c < CT; ++c) argmax_step(z[c][j], c, best, arg);
+                }
             }
             mo[j] = m; so[j] = s;
-            stats_pixel_tail(p, sm, lab[j], e_lab, s, arg, CT, nvalid);
+            stats_pixel_tail(p, sm, lab[j], sm_exp(zl[j], m), s, arg, CT, nvalid);
         }
-        *(float4*)(p.pix_m + px) = make_float4(mo[0], mo[1], mo[2], mo[3]);
-        *(float4*)(p.pix_s + px) = make_float4(so[0], so[1], so[2], so[3]);
+        if constexpr (VEC == 4) {
+            *(float4*)(p.pix_m + px) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+            *(float4*)(p.pix_s + px) = make_float4(so[0], so[1], so[2], so[3]);
+        } else {
+            *(float2*)(p.pix_m + px) = make_float2(mo[0], mo[1]);
+            *(float2*)(p.pix_s + px) = make_float2(so[0], so[1]);
+        }
     }
     if (cur_g >= 0) { if (nvalid) atomicAdd(&sm.valid, nvalid); stats_flush_group(p, sm, cur_g); }
     stats_flush_cm(p, sm);
@@ -889,9 +915,9 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     if (v4 && (c == 8 || c == 17 || c == 25)) {
         const int grid = sms * 3;
         DISPATCH_LABEL(label_dtype, {
-            if (c == 8) stats_kernel_v4<8, LT><<<grid, STATS_TPB, 0, st>>>(p);
-            else if (c == 17) stats_kernel_v4<17, LT><<<grid, STATS_TPB, 0, st>>>(p);
-            else stats_kernel_v4<25, LT><<<grid, STATS_TPB, 0, st>>>(p);
+            if (c == 8) stats_kernel_vec<8, 4, STATS_TPB, LT><<<grid, STATS_TPB, 0, st>>>(p);
+            else if (c == 17) stats_kernel_vec<17, 4, STATS_TPB, LT><<<grid, STATS_TPB, 0, st>>>(p);
+            else stats_kernel_vec<25, 4, STATS_TPB, LT><<<grid, STATS_TPB, 0, st>>>(p);
         });
     } else {
         DISPATCH_LABEL(label_dtype, stats_kernel_generic<LT><<<sms * 8, STATS_TPB, 0, st>>>(p));
