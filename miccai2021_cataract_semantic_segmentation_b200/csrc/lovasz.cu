@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "sort.cuh"
 #include "pipe.cuh"
+#include <cstdlib>
 
 #define STATS_TPB 128
 #define EMIT_TPB 256
@@ -32,7 +33,7 @@ struct LovaszParams {
     const void* labels;
     int N, C;
     long long HW, P, cap;
-    int per_image, has_filter, filter, keep_absent, need_grad;
+    int per_image, has_filter, filter, keep_absent, need_grad, dbg;
     u32 class_mask;
     int groups, n_seg;
     // workspace
@@ -62,13 +63,15 @@ struct LovaszLayout {
 // Emission geometry for one pixel-vector width: tiles of EMIT_TPB*vec pixels never straddle images; a chunk is
 // `tpc` consecutive tiles of one group and owns run_stride = tpc * tile_px candidate slots per class.
 struct EmitGeom { long long tile_px, tpi, tpg, tpc, n_runs, run_stride, src_cap; };
-static EmitGeom emit_geom(int N, long long HW, int per_image, int vec) {
+#define EMIT_WARP_TILE 32            // pixels per warp tile of the pipelined emission kernel
+static EmitGeom emit_geom(int N, long long HW, int per_image, long long tile_px) {
     EmitGeom G;
-    G.tile_px = (long long)EMIT_TPB * vec;
+    G.tile_px = tile_px;
     G.tpi = (HW + G.tile_px - 1) / G.tile_px;
     G.tpg = per_image ? G.tpi : G.tpi * N;
     const long long total_tiles = G.tpi * N;
-    G.tpc = (total_tiles + 1023) / 1024;                 // ~1000 chunks in flight over the whole batch
+    const long long target_chunks = tile_px <= 64 ? 4096 : 1024;   // chunks over the whole batch
+    G.tpc = (total_tiles + target_chunks - 1) / target_chunks;
     if (G.tpc < 1) G.tpc = 1;
     G.n_runs = (G.tpg + G.tpc - 1) / G.tpc;
     if (G.n_runs < 1) G.n_runs = 1;
@@ -83,9 +86,14 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     const int groups = per_image ? N : 1;
     const size_t S = (size_t)groups * C;
     const size_t CP = (size_t)C * P;
-    const EmitGeom G4 = emit_geom(N, HW, per_image, 4), G1 = emit_geom(N, HW, per_image, 1);
-    const size_t holey = S * (size_t)(G4.src_cap > G1.src_cap ? G4.src_cap : G1.src_cap);   // >= CP
-    const size_t runs = (size_t)groups * (size_t)(G4.n_runs > G1.n_runs ? G4.n_runs : G1.n_runs);
+    size_t cap_max = 0, runs_max = 0;                      // every emission variant must fit
+    for (long long tile_px : {(long long)EMIT_TPB * 4, (long long)EMIT_TPB, (long long)EMIT_WARP_TILE}) {
+        const EmitGeom G = emit_geom(N, HW, per_image, tile_px);
+        if ((size_t)G.src_cap > cap_max) cap_max = (size_t)G.src_cap;
+        if ((size_t)G.n_runs > runs_max) runs_max = (size_t)G.n_runs;
+    }
+    const size_t holey = S * cap_max;                      // >= CP
+    const size_t runs = (size_t)groups * runs_max;
     size_t o = 0;
     L.ctrl = o;       o = align_up(o + 256, 256);
     L.seg_fg = o;     o = align_up(o + 4 * S, 256);
@@ -511,6 +519,113 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
     }
 }
 
+// Pipelined emission (the fast path): one warp per chunk of consecutive 32-pixel warp tiles, logits prefetched with the
+// warp-private cp.async ring (see WarpTile).  Ranks inside a tile come from ballots, the running per-class offset of
+// the chunk lives in lane c's register: no shared-memory bitmasks, no CTA barriers.
+template <int CT, int TPB, int STAGES, typename LT>
+__global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
+    using W = WarpTile<CT, 1>;
+    constexpr int WT = W::WT, NW = TPB / 32;
+    extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
+    float (*Zall)[STAGES][CT][WT] = reinterpret_cast<float (*)[STAGES][CT][WT]>(pipe_smem_raw);
+    __shared__ float s_thr[NW][B200SEG_MAX_CLASSES], s_logthr[NW][B200SEG_MAX_CLASSES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt_mask = (1u << lane) - 1;
+    float (*Z)[CT][WT] = Zall[warp];
+    // all tile / chunk counts fit 32 bits (n_images * plane < 2^30): keep the index math off the 64-bit divider
+    const u32 wtpi = (u32)((p.HW + WT - 1) / WT);
+    const u32 tpg = p.per_image ? wtpi : wtpi * (u32)p.N;
+    const u32 tpc = (u32)p.tiles_per_chunk, n_runs = (u32)p.n_runs;
+    const u32 total_chunks = (u32)p.groups * n_runs;
+    const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
+    const u32 ch0 = (u32)((u64)total_chunks * gw / nwarps), ch1 = (u32)((u64)total_chunks * (gw + 1) / nwarps);
+    const u32 T0 = ch0 * tpc, T1 = ch1 * tpc;            // this warp's slice of the (chunk, tile-in-chunk) sequence
+
+    // tile sequence index -> (group, run, image, first pixel); false if the slot lies beyond the group's last tile
+    auto locate = [&](u32 T, int& g, u32& r, int& n, u32& q0) -> bool {
+        const u32 chunk = T / tpc;
+        g = (int)(chunk / n_runs);
+        r = chunk - (u32)g * n_runs;
+        const u32 gt = r * tpc + (T - chunk * tpc);
+        if (gt >= tpg) return false;
+        n = p.per_image ? g : (int)(gt / wtpi);
+        q0 = (p.per_image ? gt : gt - (u32)n * wtpi) * WT;
+        return true;
+    };
+    auto prefetch = [&](u32 T, int stage) {
+        int g, n; u32 r, q0;
+        if (T < T1 && locate(T, g, r, n, q0)) W::prefetch(Z[stage], p.logits, n, q0, p.HW, lane);
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) prefetch(T0 + s, s);
+
+    int cur_g = -1;
+    u32 run = 0;                                          // lane c: candidates of class c emitted so far in this chunk
+    u32 it = 0;
+    for (u32 T = T0; T < T1; ++T, ++it) {
+        const int stage = (int)(it % STAGES);
+        __syncwarp();
+        prefetch(T + STAGES - 1, (int)((it + STAGES - 1) % STAGES));
+        int g, n = 0; u32 r, q0 = 0;
+        const bool exists = locate(T, g, r, n, q0);
+        const u32 k = T % tpc;
+        if (k == 0) run = 0;
+        if (g != cur_g) {
+            if (lane < CT) { s_thr[warp][lane] = p.seg_thr[(size_t)g * CT + lane]; s_logthr[warp][lane] = p.seg_logthr[(size_t)g * CT + lane]; }
+            cur_g = g;
+            __syncwarp();
+        }
+        const long long q = (long long)q0 + lane;
+        const bool inb = exists && q < p.HW;
+        float m = 0.f, s = 1.f;
+        int lab = -1;
+        const size_t px = (size_t)n * p.HW + q;
+        if (inb) { m = p.pix_m[px]; s = p.pix_s[px]; lab = load_label<LT>(p.labels, px); }
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        const float (*Tz)[WT] = Z[stage];
+        const float* thr = s_thr[warp];
+        u32 acc = 0;
+        if (inb) {
+            const float theta = pre_theta(m, s);
+            u32 pre = 0;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) pre |= (Tz[c][lane] >= theta + s_logthr[warp][c]) ? (1u << c) : 0u;
+            if (p.has_filter && lab == p.filter) pre = 0;
+            else if ((unsigned)lab < (unsigned)CT && thr_active(thr[lab & 31])) pre |= 1u << lab;
+            u32 mm = pre;
+            while (mm) {
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                float err, pr;
+                if (exact_accept(Tz[c][lane], m, s, c == lab, thr[c], err, pr)) acc |= 1u << c;
+            }
+        }
+        if (__any_sync(FULL_MASK, acc != 0)) {
+#pragma unroll 1
+            for (int c = 0; c < CT; ++c) {
+                const bool flag = (acc >> c) & 1u;
+                const u32 b = __ballot_sync(FULL_MASK, flag);
+                if (b == 0) continue;
+                const u32 base = __shfl_sync(FULL_MASK, run, c);
+                if (flag) {
+                    float err, pr;
+                    const bool fg = c == lab;
+                    exact_accept(Tz[c][lane], m, s, fg, thr[c], err, pr);
+                    const size_t slot = ((size_t)g * CT + c) * (size_t)p.src_cap + (size_t)r * p.run_stride + base +
+                                        __popc(b & lt_mask);
+                    p.keysA[slot] = err_key(err);
+                    p.valsA[slot] = ((u32)px << 1) | (fg ? 1u : 0u);
+                }
+                if (lane == c) run += __popc(b);
+            }
+        }
+        if (k == tpc - 1 && lane < CT) p.run_cnt[(size_t)(T / tpc) * CT + lane] = run;
+    }
+    cp_async_wait<0>();
+}
+
 // per segment: exclusive prefix of the chunk counts (the sort's run prefix) and the segment's candidate count
 __global__ void __launch_bounds__(256) run_scan_kernel(LovaszParams p) {
     const int lane = threadIdx.x & 31;
@@ -752,6 +867,141 @@ __global__ void __launch_bounds__(BWD_TPB) backward_kernel_v4(LovaszParams p, co
     }
 }
 
+// Pipelined backward (the fast path): lane l of a warp owns pixels [l*VEC, l*VEC+VEC) of the warp tile.
+template <int CT, int VEC, int TPB, int STAGES, typename LT>
+__global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, const float* __restrict__ go,
+                                                              float* __restrict__ dlogits) {
+    using W = WarpTile<CT, VEC>;
+    constexpr int WT = W::WT, NW = TPB / 32;
+    extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
+    float (*Zall)[STAGES][CT][WT] = reinterpret_cast<float (*)[STAGES][CT][WT]>(pipe_smem_raw);   // [NW][STAGES][CT][WT]
+    __shared__ float s_thr[NW][B200SEG_MAX_CLASSES], s_logthr[NW][B200SEG_MAX_CLASSES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float (*Z)[CT][WT] = Zall[warp];
+    const int l0 = lane * VEC;
+    const u32 wtpi = (u32)((p.HW + WT - 1) / WT);         // tile counts fit 32 bits: keep the index math off the 64-bit divider
+    const u32 nwt = wtpi * (u32)p.N;
+    const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
+    const u32 t0 = (u32)((u64)nwt * gw / nwarps), t1 = (u32)((u64)nwt * (gw + 1) / nwarps);
+    const float gsc = __ldg(go);
+
+    auto prefetch = [&](u32 t, int stage) {
+        if (t < t1) {
+            const u32 n = t / wtpi;
+            W::prefetch(Z[stage], p.logits, (int)n, (long long)(t - n * wtpi) * WT, p.HW, lane);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) prefetch(t0 + s, s);
+
+    int cur_g = -1;
+    u32 it = 0;
+    for (u32 t = t0; t < t1; ++t, ++it) {
+        const int stage = (int)(it % STAGES);
+        __syncwarp();                                     // every lane is done reading the stage about to be refilled
+        prefetch(t + STAGES - 1, (int)((it + STAGES - 1) % STAGES));
+        const int n = (int)(t / wtpi);
+        const long long q = (long long)(t - (u32)n * wtpi) * WT + l0;
+        const int g = p.per_image ? n : 0;
+        if (g != cur_g) {
+            if (lane < CT) { s_thr[warp][lane] = p.seg_thr[(size_t)g * CT + lane]; s_logthr[warp][lane] = p.seg_logthr[(size_t)g * CT + lane]; }
+            cur_g = g;
+            __syncwarp();
+        }
+        const bool inb = q < p.HW;
+        // per-pixel state straight from global memory (issued before the wait so it overlaps)
+        float m[VEC], s[VEC], gl[VEC];
+        int lab[VEC];
+        const size_t px = (size_t)n * p.HW + q;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { m[j] = 0.f; s[j] = 1.f; gl[j] = 0.f; lab[j] = -1; }
+        if (inb) {
+            if constexpr (VEC == 4) {
+                const float4 mv = *(const float4*)(p.pix_m + px), sv = *(const float4*)(p.pix_s + px), gv = *(const float4*)(p.gown + px);
+                m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+                s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
+                gl[0] = gv.x; gl[1] = gv.y; gl[2] = gv.z; gl[3] = gv.w;
+                load_labels4<LT>(p.labels, px, lab);
+            } else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    m[j] = p.pix_m[px + j]; s[j] = p.pix_s[px + j]; gl[j] = p.gown[px + j];
+                    lab[j] = load_label<LT>(p.labels, px + j);
+                }
+            }
+        }
+        cp_async_wait<STAGES - 1>();                      // this lane's copies for tile t have landed ...
+        __syncwarp();                                     // ... and so have the other lanes'
+        if (!inb) continue;
+        const float (*T)[WT] = Z[stage];
+        const size_t off = (size_t)n * CT * p.HW + q;
+        const float* gb = p.gbg + off;
+        float* dp = dlogits + off;
+        const float* thr = s_thr[warp];
+        float theta[VEC];
+        u32 pre[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { theta[j] = pre_theta(m[j], s[j]); pre[j] = 0; }
+        // sweep 1 (branch-free): conservative candidate bits
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float lt = s_logthr[warp][c];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) pre[j] |= (T[c][l0 + j] >= theta[j] + lt) ? (1u << c) : 0u;
+        }
+        // exact stage on the flagged classes: same predicate as the emission kernel
+        float dot[VEC], nd[VEC], ownv[VEC];
+        u32 fix[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const bool filt = p.has_filter && lab[j] == p.filter;
+            const bool own = !filt && (unsigned)lab[j] < (unsigned)CT && thr_active(thr[lab[j] & 31]);
+            const u32 ownbit = (unsigned)lab[j] < (unsigned)CT ? (1u << lab[j]) : 0u;
+            float d = 0.f;
+            u32 cm = 0;
+            u32 mm = filt ? 0u : (pre[j] & ~ownbit);
+            while (mm) {
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const float pr = sm_prob(T[c][l0 + j], m[j], s[j]);
+                if (pr >= thr[c]) { cm |= 1u << c; d += gb[(size_t)c * p.HW + j] * pr; }
+            }
+            float pown = 0.f;
+            if (own) { pown = sm_prob(T[lab[j]][l0 + j], m[j], s[j]); d += gl[j] * pown; }
+            else lab[j] = -1;                              // no class of this pixel takes the own-class path below
+            dot[j] = d; fix[j] = cm;
+            nd[j] = filt ? 0.f : -gsc * d * __fdiv_rn(1.0f, s[j]);
+            ownv[j] = gsc * pown * (gl[j] - d);            // exact value of the own class
+        }
+        // sweep 2 (branch-free): -go * p_k * dot with the fast exponential, the own class takes its exact value ...
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            float o[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float fast = nd[j] * __expf(T[c][l0 + j] - m[j]);
+                o[j] = (c == lab[j]) ? ownv[j] : fast;
+            }
+            if constexpr (VEC == 4) st_stream4(dp + (size_t)c * p.HW, make_float4(o[0], o[1], o[2], o[3]));
+            else if constexpr (VEC == 2) st_stream2(dp + (size_t)c * p.HW, make_float2(o[0], o[1]));
+            else dp[(size_t)c * p.HW] = o[0];
+        }
+        // ... then the (few) background-candidate classes are overwritten with the exact go * p_k * (g_k - dot)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            u32 mm = fix[j];
+            while (mm) {
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const float pk = sm_prob(T[c][l0 + j], m[j], s[j]);
+                dp[(size_t)c * p.HW + j] = gsc * pk * (gb[(size_t)c * p.HW + j] - dot[j]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
 template <typename LT>
 __global__ void __launch_bounds__(BWD_TPB) backward_kernel_generic(LovaszParams p, const float* __restrict__ go,
                                                                    float* __restrict__ dlogits) {
@@ -849,7 +1099,7 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.gbg = (float*)(ws + L.keysA);      // free again once the sort result sits in buffer B
     p.cm = nullptr; p.has_drop = 0; p.drop = 0;
     p.status = (int*)(p.ctrl + CTRL_STATUS);
-    p.loss_out = nullptr; p.need_grad = 1;
+    p.loss_out = nullptr; p.need_grad = 1; p.dbg = 0;
     return true;
 }
 
@@ -934,12 +1184,34 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
 
     // K2
     {
-        const EmitGeom G = emit_geom(n, hw, per_image, v4 ? 4 : 1);
+        const bool pipe_ok = v4 && (c == 8 || c == 17 || c == 25);
+        const EmitGeom G = emit_geom(n, hw, per_image, pipe_ok ? EMIT_WARP_TILE : (long long)EMIT_TPB * (v4 ? 4 : 1));
         p.n_runs = (int)G.n_runs; p.tiles_per_chunk = (int)G.tpc; p.run_stride = G.run_stride; p.src_cap = G.src_cap;
         const long long chunks = (long long)p.groups * G.n_runs;
-        const int grid = (int)(chunks < (long long)sms * 8 ? chunks : (long long)sms * 8);
-        if (v4) { DISPATCH_LABEL(label_dtype, emit_kernel<4, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
-        else { DISPATCH_LABEL(label_dtype, emit_kernel<1, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
+        if (pipe_ok) {
+#define LAUNCH_EMIT_ASYNC(CC)                                                                                   \
+    {                                                                                                           \
+        constexpr int ET = 128, ES = 2;                                                                         \
+        const size_t smem = sizeof(float) * (size_t)ES * CC * ET;                                               \
+        CUDA_TRY(cudaFuncSetAttribute(emit_kernel_async<CC, ET, ES, LT>,                                        \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        int per_sm = (int)((224 * 1024) / (smem + 2048));                                                       \
+        if (per_sm * ET > 2048) per_sm = 2048 / ET;                                                             \
+        long long grid = (long long)sms * per_sm;                                                               \
+        if (grid * (ET / 32) > chunks) grid = (chunks + ET / 32 - 1) / (ET / 32);                               \
+        emit_kernel_async<CC, ET, ES, LT><<<(int)grid, ET, smem, st>>>(p);                                      \
+    }
+            DISPATCH_LABEL(label_dtype, {
+                if (c == 8) LAUNCH_EMIT_ASYNC(8)
+                else if (c == 17) LAUNCH_EMIT_ASYNC(17)
+                else LAUNCH_EMIT_ASYNC(25)
+            });
+#undef LAUNCH_EMIT_ASYNC
+        } else {
+            const int grid = (int)(chunks < (long long)sms * 8 ? chunks : (long long)sms * 8);
+            if (v4) { DISPATCH_LABEL(label_dtype, emit_kernel<4, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
+            else { DISPATCH_LABEL(label_dtype, emit_kernel<1, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
+        }
         LAUNCH_CHECK("emit_kernel");
         run_scan_kernel<<<(p.n_seg + 7) / 8, 256, 0, st>>>(p);
         LAUNCH_CHECK("run_scan_kernel");
@@ -991,8 +1263,42 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
     if (p.P == 0) return 0;
     const int sms = b200seg_sm_count();
     const bool v4 = vec4_ok(logits, labels, label_dtype, hw) && aligned16(dlogits);
+    const bool pipe_ok = v4 && (label_dtype != B200SEG_LABEL_U8 || hw % 16 == 0) && aligned16(labels) &&
+                         (c == 8 || c == 17 || c == 25);
     b200seg_stage(7, st);
-    if (v4 && (c == 8 || c == 17 || c == 25)) {
+    if (pipe_ok) {
+        const char* e = getenv("B200SEG_BWD_VARIANT");
+        const int variant = e ? atoi(e) : 0;
+#define LAUNCH_BWD_ASYNC(CC, VV, TT, SS)                                                                         \
+    {                                                                                                            \
+        const size_t smem = sizeof(float) * (size_t)SS * CC * TT * VV;                                           \
+        CUDA_TRY(cudaFuncSetAttribute(backward_kernel_async<CC, VV, TT, SS, LT>,                                 \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+        int per_sm = (int)((224 * 1024) / (smem + 2048));                                                        \
+        if (per_sm < 1) per_sm = 1;                                                                              \
+        if (per_sm * TT > 2048) per_sm = 2048 / TT;                                                              \
+        backward_kernel_async<CC, VV, TT, SS, LT><<<sms * per_sm, TT, smem, st>>>(p, grad_out, dlogits);         \
+    }
+#define LAUNCH_BWD_C(VV, TT, SS)                                       \
+    {                                                                  \
+        if (c == 8) LAUNCH_BWD_ASYNC(8, VV, TT, SS)                    \
+        else if (c == 17) LAUNCH_BWD_ASYNC(17, VV, TT, SS)             \
+        else LAUNCH_BWD_ASYNC(25, VV, TT, SS)                          \
+    }
+        DISPATCH_LABEL(label_dtype, {
+            switch (variant) {
+                case 1: LAUNCH_BWD_C(1, 128, 4) break;
+                case 2: LAUNCH_BWD_C(2, 128, 2) break;
+                case 3: LAUNCH_BWD_C(2, 128, 3) break;
+                case 4: LAUNCH_BWD_C(1, 256, 3) break;
+                case 5: LAUNCH_BWD_C(1, 128, 2) break;
+                case 6: LAUNCH_BWD_C(4, 128, 2) break;
+                default: LAUNCH_BWD_C(1, 128, 2) break;
+            }
+        });
+#undef LAUNCH_BWD_C
+#undef LAUNCH_BWD_ASYNC
+    } else if (v4 && (c == 8 || c == 17 || c == 25)) {
         const int grid = sms * 3 * 4;
         DISPATCH_LABEL(label_dtype, {
             if (c == 8) backward_kernel_v4<8, LT><<<grid, BWD_TPB, 0, st>>>(p, grad_out, dlogits);

@@ -45,3 +45,46 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
     }
     __trap();
 }
+
+// ---- per-thread cp.async (LDGSTS) helpers -------------------------------------------------------------------------
+// Each thread copies the bytes it will later read itself, so completion is tracked per thread with commit/wait
+// groups and no CTA-wide barrier is needed.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async moves 4, 8 or 16 bytes");
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- warp-private cp.async tile pipeline -------------------------------------------------------------------------------
+// A warp tile is WT = 32*VEC consecutive pixels of one image: C rows of WT*4 bytes.  The warp copies the rows with
+// 16-byte cp.async (LDGSTS.128: one instruction moves 512 bytes) into its private ring of STAGES buffers, STAGES-1
+// tiles ahead of the math.  HBM reads never wait for the math, no registers are tied up by data in flight, there is no
+// CTA barrier (cp.async.wait_group + __syncwarp), and dynamic class indices address shared memory.
+template <int CT, int VEC>
+struct WarpTile {
+    static constexpr int WT = 32 * VEC;                 // pixels per warp tile
+    static constexpr int CHUNKS = WT / 4;               // 16-byte chunks per row
+    static constexpr int ROWS_PER_INSTR = 32 / CHUNKS;  // rows covered by one warp-wide cp.async
+    static constexpr int NINSTR = (CT + ROWS_PER_INSTR - 1) / ROWS_PER_INSTR;
+    // copy the tile whose first pixel is (image n, pixel q0) into buf[CT][WT]
+    static __device__ __forceinline__ void prefetch(float (*buf)[WT], const float* logits, int n, long long q0,
+                                                    long long HW, int lane) {
+        const int ch = lane % CHUNKS, r0 = lane / CHUNKS;
+        const long long q = q0 + 4 * ch;
+        if (q < HW) {
+            const float* src = logits + (size_t)n * CT * HW + q;
+#pragma unroll
+            for (int i = 0; i < NINSTR; ++i) {
+                const int c = i * ROWS_PER_INSTR + r0;
+                if (c < CT) cp_async<16>(&buf[c][4 * ch], src + (size_t)c * HW);
+            }
+        }
+    }
+};
+
