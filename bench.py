@@ -35,8 +35,9 @@ import torch  # noqa: E402
 
 METRIC = "Mpixel/s Lovasz fwd+bwd + mIoU @540x960 C=25"
 UNIT = "Mpixel/s"
-STAGES = ["stats(+fused confmat)", "finalize", "emit", "sort_hist", "sort_passes", "jaccard+loss", None, "backward"]
-KERNELS_PER_STEP = 13       # stats, finalize, emit, sort plan/hist/scan + 3 passes, jaccard, loss, backward, metrics
+STAGES = ["stats(+fused confmat)", "finalize", "emit", "sort_plan", "sort_passes", "jaccard+loss", None, "backward"]
+# stats, finalize, emit, run_scan, sort plan + desc, 3 x (count, scatter), fg_count, jaccard, loss, backward, metrics
+KERNELS_PER_STEP = 17
 
 
 def parse():

@@ -529,6 +529,7 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
     extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
     float (*Zall)[STAGES][CT][WT] = reinterpret_cast<float (*)[STAGES][CT][WT]>(pipe_smem_raw);
     __shared__ float s_thr[NW][B200SEG_MAX_CLASSES], s_logthr[NW][B200SEG_MAX_CLASSES];
+    __shared__ u32 s_ballot[NW][B200SEG_MAX_CLASSES], s_base[NW][B200SEG_MAX_CLASSES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt_mask = (1u << lane) - 1;
     float (*Z)[CT][WT] = Zall[warp];
@@ -586,7 +587,8 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
         __syncwarp();
         const float (*Tz)[WT] = Z[stage];
         const float* thr = s_thr[warp];
-        u32 acc = 0;
+        u32 acc = 0;                                      // accepted classes of this lane's pixel
+        float e0 = 0.f, e1 = 0.f;                         // errors of the first two of them (the rest is recomputed)
         if (inb) {
             const float theta = pre_theta(m, s);
             u32 pre = 0;
@@ -599,26 +601,36 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
                 const int c = __ffs(mm) - 1;
                 mm &= mm - 1;
                 float err, pr;
-                if (exact_accept(Tz[c][lane], m, s, c == lab, thr[c], err, pr)) acc |= 1u << c;
+                if (exact_accept(Tz[c][lane], m, s, c == lab, thr[c], err, pr)) {
+                    if (acc == 0) e0 = err; else if ((acc & (acc - 1)) == 0) e1 = err;
+                    acc |= 1u << c;
+                }
             }
         }
         if (__any_sync(FULL_MASK, acc != 0)) {
-#pragma unroll 1
+            // lane c collects the ballot of class c and reserves the slots; the table goes through shared memory
+            u32 mine = 0;
+#pragma unroll
             for (int c = 0; c < CT; ++c) {
-                const bool flag = (acc >> c) & 1u;
-                const u32 b = __ballot_sync(FULL_MASK, flag);
-                if (b == 0) continue;
-                const u32 base = __shfl_sync(FULL_MASK, run, c);
-                if (flag) {
-                    float err, pr;
-                    const bool fg = c == lab;
-                    exact_accept(Tz[c][lane], m, s, fg, thr[c], err, pr);
-                    const size_t slot = ((size_t)g * CT + c) * (size_t)p.src_cap + (size_t)r * p.run_stride + base +
-                                        __popc(b & lt_mask);
-                    p.keysA[slot] = err_key(err);
-                    p.valsA[slot] = ((u32)px << 1) | (fg ? 1u : 0u);
-                }
-                if (lane == c) run += __popc(b);
+                const u32 b = __ballot_sync(FULL_MASK, (acc >> c) & 1u);
+                if (lane == c) mine = b;
+            }
+            __syncwarp();
+            if (lane < CT) { s_ballot[warp][lane] = mine; s_base[warp][lane] = run; run += __popc(mine); }
+            __syncwarp();
+            u32 mm = acc;
+            int i = 0;
+            while (mm) {                                   // this lane's own candidates
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const bool fg = c == lab;
+                float err = i == 0 ? e0 : e1;
+                if (i >= 2) { float pr; exact_accept(Tz[c][lane], m, s, fg, thr[c], err, pr); }
+                ++i;
+                const u32 rank = s_base[warp][c] + __popc(s_ballot[warp][c] & lt_mask);
+                const size_t slot = ((size_t)g * CT + c) * (size_t)p.src_cap + (size_t)r * p.run_stride + rank;
+                p.keysA[slot] = err_key(err);
+                p.valsA[slot] = ((u32)px << 1) | (fg ? 1u : 0u);
             }
         }
         if (k == tpc - 1 && lane < CT) p.run_cnt[(size_t)(T / tpc) * CT + lane] = run;

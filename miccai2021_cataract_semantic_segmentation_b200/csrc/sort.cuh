@@ -14,7 +14,7 @@
 // The first pass can read a "holey" source: every segment is a concatenation of n_runs runs, run r starting at
 // s*src_cap + r*run_stride with run_prefix[s][r+1]-run_prefix[s][r] elements (what the emission kernel leaves
 // behind without any cross-CTA ordering); elements are gathered by binary search over the run prefix.
-// The last pass also counts foreground flags (value bit 0) per destination tile for the Jaccard scan.
+// A last small kernel counts the foreground flags (value bit 0) per tile of the final order for the Jaccard scan.
 #pragma once
 #include "common.cuh"
 
@@ -46,7 +46,7 @@ struct SortArgs {
     u32* seg_done;          // [SORT_PASSES][n_seg] tiles counted so far (last CTA of a segment runs its scan)
     u32* tilehist;          // [max_tiles][1024]
     u32* bin_base;          // [n_seg][1024]
-    u32* tile_fg;           // [max_tiles] foreground flags per tile of the final order (zeroed by sort_plan_kernel)
+    u32* tile_fg;           // [max_tiles] foreground flags per tile of the final order (sort_fg_count_kernel)
     int* status;
 };
 
@@ -114,8 +114,6 @@ __global__ void __launch_bounds__(1024) sort_plan_kernel(SortArgs a, u32 max_til
         __syncthreads();
     }
     if (tid == 0) a.tile_start[a.n_seg] = s_carry;
-    const u32 total = s_carry;
-    for (u32 i = tid; i < total && i < max_tiles; i += 1024) a.tile_fg[i] = 0;
     for (int i = tid; i < a.n_seg * SORT_PASSES; i += 1024) a.seg_done[i] = 0;
 }
 
@@ -323,13 +321,11 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
     const bool odd = pass & 1;
     u32* __restrict__ kout = odd ? a.keys[0] : a.keys[1];
     u32* __restrict__ vout = odd ? a.vals[0] : a.vals[1];
-    const bool last = pass == SORT_PASSES - 1;
 
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const uint4 d4 = a.tile_desc[t];
         const int seg = (int)d4.x;
         const u32 off = d4.y, n = d4.z, w = d4.w;
-        const u32 tseg0 = t - off / SORT_TILE;
         const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
         const size_t obase = (size_t)seg * a.cap;
         __syncthreads();
@@ -408,27 +404,40 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 i = k * SORT_TPB + tid;
             const bool valid = i < n;
-            u32 pos = 0, vv = 0;
             if (valid) {
                 const u32 kk = S.keys[i];
-                vv = S.vals[i];
-                pos = S.binoff[(kk >> shift) & dmask] + i;
+                const u32 pos = S.binoff[(kk >> shift) & dmask] + i;
                 kout[obase + pos] = kk;
-                vout[obase + pos] = vv;
+                vout[obase + pos] = S.vals[i];
             }
-            if (last) {                                       // foreground flags per destination tile (warp-aggregated)
-                const bool fg = valid && (vv & 1u);
-                const u32 dt = pos / SORT_TILE;
-                const u32 fgm = __ballot_sync(FULL_MASK, fg);
-                if (fgm) {
-                    const u32 dt0 = __shfl_sync(FULL_MASK, dt, __ffs(fgm) - 1);
-                    if (__all_sync(FULL_MASK, !fg || dt == dt0)) {       // one destination tile for the whole warp: usual
-                        if (lane == 0) atomicAdd(a.tile_fg + tseg0 + dt0, (u32)__popc(fgm));
-                    } else if (fg) {
-                        atomicAdd(a.tile_fg + tseg0 + dt, 1u);
-                    }
-                }
-            }
+        }
+    }
+}
+
+// foreground flags (value bit 0) per tile of the final order, for the Jaccard scan
+__global__ void __launch_bounds__(SORT_TPB) sort_fg_count_kernel(SortArgs a, u32 total_bound) {
+    __shared__ u32 s_w[SORT_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 total_tiles = min(a.tile_start[a.n_seg], total_bound);
+    for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const uint4 d4 = a.tile_desc[t];
+        const u32* v = a.vals[1] + (size_t)d4.x * a.cap + d4.y;
+        u32 c = 0;
+#pragma unroll
+        for (int k = 0; k < SORT_KPT; ++k) {
+            const u32 i = k * SORT_TPB + tid;
+            c += (i < d4.z) ? (v[i] & 1u) : 0u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+        __syncthreads();
+        if (lane == 0) s_w[warp] = c;
+        __syncthreads();
+        if (tid == 0) {
+            u32 tot = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < SORT_WARPS; ++w2) tot += s_w[w2];
+            a.tile_fg[t] = tot;
         }
     }
 }
@@ -457,6 +466,8 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
         sort_scatter_kernel<<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_scatter_kernel");
     }
+    sort_fg_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, L.max_tiles);
+    LAUNCH_CHECK("sort_fg_count_kernel");
     b200seg_stage(5, st);
     return 0;
 }
