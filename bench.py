@@ -35,7 +35,9 @@ import torch  # noqa: E402
 
 METRIC = "Mpixel/s Lovasz fwd+bwd + mIoU @540x960 C=25"
 UNIT = "Mpixel/s"
-STAGES = ["stats(+fused confmat)", "finalize", "emit", "sort_plan", "sort_passes", "jaccard+loss", None, "backward"]
+STAGES = ["stats(+fused confmat)", "finalize", "emit", "sort_plan", "sort_pass0", "sort_pass1", "sort_pass2",
+          "jaccard+loss", None, "backward"]
+N_EV = len(STAGES) + 1
 # stats, finalize, emit, run_scan, sort plan + desc, 3 x (count, scatter), fg_count, jaccard, loss, backward, metrics
 KERNELS_PER_STEP = 17
 
@@ -293,22 +295,22 @@ def main():
 
     # ---- per-kernel-group times, live, via stage events ------------------------------------------------------------
     import ctypes
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(N_EV)]
     for ev in evs:
         ev.record()                                  # creates the underlying cudaEvent_t
     torch.cuda.synchronize()
-    arr = (ctypes.c_void_p * 9)(*[ctypes.c_void_p(ev.cuda_event) for ev in evs])
-    _native.check(lib.b200seg_set_stage_events(arr, 9), "set_stage_events")
-    acc = [0.0] * 8
+    arr = (ctypes.c_void_p * N_EV)(*[ctypes.c_void_p(ev.cuda_event) for ev in evs])
+    _native.check(lib.b200seg_set_stage_events(arr, N_EV), "set_stage_events")
+    acc = [0.0] * len(STAGES)
     prof_steps = min(args.steps, 10)
     for _ in range(prof_steps):
         step(xr, y)
         torch.cuda.synchronize()
-        for i in range(8):
+        for i in range(len(STAGES)):
             if STAGES[i] is not None:
                 acc[i] += evs[i].elapsed_time(evs[i + 1])
     _native.check(lib.b200seg_set_stage_events(None, 0), "clear stage events")
-    stage_ms = {STAGES[i]: acc[i] / prof_steps for i in range(8) if STAGES[i] is not None}
+    stage_ms = {STAGES[i]: acc[i] / prof_steps for i in range(len(STAGES)) if STAGES[i] is not None}
 
     if rank != 0:
         if world > 1:
@@ -321,8 +323,8 @@ def main():
     # algorithmic bytes per launch of each kernel group (DESIGN.md "Kernels"): compulsory reads + writes of that stage
     alg = {
         "stats(+fused confmat)": p * (4 * c + lab_bytes),
-        "emit": p * (4 * c + lab_bytes),
-        "backward": p * (2 * 4 * c + lab_bytes),
+        "emit": p * (4 * c + lab_bytes + 8),            # logits + labels + the 8 B/px softmax state
+        "backward": p * (2 * 4 * c + lab_bytes + 12),     # logits in, gradients out, labels, 12 B/px state
     }
     dom = max(stage_ms, key=stage_ms.get)
     traffic = None

@@ -116,12 +116,13 @@ int b200seg_metrics_from_confmat(const int64_t* cm, int32_t n_classes, uint32_t 
  * Measurement hook (no reference counterpart): process-wide, hand the library up to B200SEG_N_STAGES
  * cudaEvent_t handles; while set, b200seg_lovasz_forward / _backward record events[i] on their stream at stage
  * boundary i, so a caller can time each kernel group with cudaEventElapsedTime without a profiler.
- *   0 forward entry      1 stats kernel done        2 threshold finalisation done   3 candidate emission done
- *   4 sort plan+histogram+scan done   5 three sort passes done   6 Jaccard + loss done
- *   7 backward entry     8 backward kernel done
+ *   0 forward entry        1 stats kernel done          2 threshold finalisation done
+ *   3 candidate emission (+ run scan) done                4 sort plan + tile descriptors done
+ *   5 / 6 / 7 sort pass 0 / 1 / 2 (count + scatter) done (7 includes the per-tile foreground count)
+ *   8 Jaccard + loss done  9 backward entry            10 backward kernel done
  * Pass NULL / 0 to clear.  Entries that are NULL are skipped.
  * ------------------------------------------------------------------------------------------------ */
-#define B200SEG_N_STAGES 9
+#define B200SEG_N_STAGES 11
 int b200seg_set_stage_events(void* const* events, int32_t n_events);
 
 /* ------------------------------------------------------------------------------------------------

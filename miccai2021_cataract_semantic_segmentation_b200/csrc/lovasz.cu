@@ -1249,7 +1249,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     LAUNCH_CHECK("jaccard_kernel");
     loss_finalize_kernel<<<1, 32, 0, st>>>(p);
     LAUNCH_CHECK("loss_finalize_kernel");
-    b200seg_stage(6, st);
+    b200seg_stage(8, st);
     return 0;
 }
 
@@ -1277,7 +1277,7 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
     const bool v4 = vec4_ok(logits, labels, label_dtype, hw) && aligned16(dlogits);
     const bool pipe_ok = v4 && (label_dtype != B200SEG_LABEL_U8 || hw % 16 == 0) && aligned16(labels) &&
                          (c == 8 || c == 17 || c == 25);
-    b200seg_stage(7, st);
+    b200seg_stage(9, st);
     if (pipe_ok) {
         const char* e = getenv("B200SEG_BWD_VARIANT");
         const int variant = e ? atoi(e) : 0;
@@ -1321,7 +1321,7 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
         DISPATCH_LABEL(label_dtype, backward_kernel_generic<LT><<<sms * 16, BWD_TPB, 0, st>>>(p, grad_out, dlogits));
     }
     LAUNCH_CHECK("backward_kernel");
-    b200seg_stage(8, st);
+    b200seg_stage(10, st);
     return 0;
 }
 

@@ -465,9 +465,10 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
         LAUNCH_CHECK("sort_count_kernel");
         sort_scatter_kernel<<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_scatter_kernel");
+        if (p + 1 < SORT_PASSES) b200seg_stage(5 + p, st);
     }
     sort_fg_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, L.max_tiles);
     LAUNCH_CHECK("sort_fg_count_kernel");
-    b200seg_stage(5, st);
+    b200seg_stage(7, st);
     return 0;
 }
