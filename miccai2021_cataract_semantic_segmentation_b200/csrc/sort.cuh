@@ -182,20 +182,20 @@ __device__ __forceinline__ TileSrc tile_src_setup(const SortArgs& a, int pass, u
     return T;
 }
 
-__device__ __forceinline__ size_t tile_src_index(const TileSrc& T, const u32* s_win, u32 idx) {
+// Source index of tile element idx.  `r` is the caller's running run cursor (relative to r_lo when the window is
+// staged): a thread visits its elements in increasing order, so the run index only moves forward.
+__device__ __forceinline__ size_t tile_src_index(const TileSrc& T, const u32* s_win, u32 idx, u32& r) {
     if (!T.gather) return T.base + idx;
     const u32 v = T.voff + idx;
-    u32 r, start;
     if (T.window) {
-        r = upper_run(s_win, 0, T.r_hi - T.r_lo, v);
-        start = s_win[r];
-        r += T.r_lo;
-    } else {
-        r = upper_run(T.prefix, T.r_lo, T.r_hi, v);
-        start = T.prefix[r];
+        const u32 last = T.r_hi - T.r_lo;
+        while (r < last && s_win[r + 1] <= v) ++r;
+        return T.seg_base + (size_t)(r + T.r_lo) * T.run_stride + (v - s_win[r]);
     }
-    return T.seg_base + (size_t)r * T.run_stride + (v - start);
+    while (r < T.r_hi && T.prefix[r + 1] <= v) ++r;
+    return T.seg_base + (size_t)r * T.run_stride + (v - T.prefix[r]);
 }
+__device__ __forceinline__ u32 tile_src_cursor(const TileSrc& T) { return T.window ? 0u : T.r_lo; }
 
 // ---- per-segment scan, run by the CTA that counted the segment's last tile ---------------------------------------------
 // column scan over the segment's tiles (tilehist[tile][bin] -> exclusive offset of the tile within the bin) and
@@ -257,10 +257,11 @@ __global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pa
         const TileSrc T = tile_src_setup(a, pass, t, seg, off, s_win);
         __syncthreads();
         u32 key[SORT_KPT];
+        u32 cur = tile_src_cursor(T);
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = k * SORT_TPB + tid;
-            key[k] = idx < n ? T.keys[tile_src_index(T, s_win, idx)] : 0;
+            key[k] = idx < n ? T.keys[tile_src_index(T, s_win, idx, cur)] : 0;
         }
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k)
@@ -287,22 +288,25 @@ __global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pa
 // lanes of a warp write consecutive addresses within each digit bin (a fully scattered 4-byte store costs the LSU
 // one wavefront per lane).
 // lanes holding the same digit (what match.any returns, but built from ballots: MATCH.ANY costs ~250 cycles per warp
-// instruction on this part, a ballot a few)
-__device__ __forceinline__ u32 peer_mask(u32 d, u32 nbits) {
+// instruction on this part, a ballot a few).  A warp whose 32 digits agree (the usual case in the top-digit pass,
+// where keys cluster) skips the loop.
+template <int NBITS>
+__device__ __forceinline__ u32 peer_mask(u32 d) {
+    const u32 d0 = __shfl_sync(FULL_MASK, d, 0);
+    if (__all_sync(FULL_MASK, d == d0)) return FULL_MASK;
     u32 peers = FULL_MASK;
 #pragma unroll
-    for (u32 b = 0; b < 11; ++b) {
-        if (b < nbits) {
-            const bool bit = (d >> b) & 1u;
-            const u32 m = __ballot_sync(FULL_MASK, bit);
-            peers &= bit ? m : ~m;
-        }
+    for (int b = 0; b < NBITS; ++b) {
+        const u32 x = 0u - ((d >> b) & 1u);               // all ones if bit b of d is set
+        const u32 m = __ballot_sync(FULL_MASK, x != 0u);
+        peers &= ~(m ^ x);                                  // keep lanes whose bit b equals mine
     }
     return peers;
 }
 
+#define SORT_CNT_STRIDE (SORT_MAX_BINS + 4)                // u16 row stride, keeps 4-bin groups 8-byte aligned
 struct ScatterSmem {
-    unsigned short cnt[SORT_WARPS][SORT_MAX_BINS + 2];   // per-warp digit counters -> exclusive offsets across warps
+    unsigned short cnt[SORT_WARPS][SORT_CNT_STRIDE];     // per-warp digit counters -> exclusive offsets across warps
     unsigned short binexcl[SORT_MAX_BINS];               // exclusive prefix of the tile's bin totals
     u32 binoff[SORT_MAX_BINS];                           // global position of local sorted index i in bin d: binoff[d] + i
     u32 keys[SORT_TILE];
@@ -311,11 +315,32 @@ struct ScatterSmem {
     u32 warp_sum[SORT_WARPS];
 };
 
-__global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
+// stable rank of each of the warp's SORT_KPT rows within (warp, digit); NBITS = digit width + 1 (the extra bit is
+// the dummy bin of padding lanes)
+template <int NBITS>
+__device__ __forceinline__ void rank_rows(ScatterSmem& S, const u32 (&key)[SORT_KPT], u32 (&rnk)[SORT_KPT], u32 n,
+                                          u32 wbase, u32 shift, u32 dmask, u32 nbins, int warp, int lane) {
+    const u32 lt_mask = (1u << lane) - 1;
+#pragma unroll
+    for (int k = 0; k < SORT_KPT; ++k) {
+        const u32 d = (wbase + k * 32 < n) ? ((key[k] >> shift) & dmask) : nbins;
+        const u32 m = peer_mask<NBITS>(d);
+        const int leader = __ffs(m) - 1;
+        u32 old = 0;
+        if (lane == leader) { old = S.cnt[warp][d]; S.cnt[warp][d] = (unsigned short)(old + __popc(m)); }
+        rnk[k] = __shfl_sync(FULL_MASK, old, leader) + __popc(m & lt_mask);
+        __syncwarp();
+    }
+}
+
+// ---- scatter ----------------------------------------------------------------------------------------------------------------
+// Elements are first placed at their tile-local sorted position in shared memory, then streamed out so that the
+// lanes of a warp write consecutive addresses within each digit bin (a fully scattered 4-byte store costs the LSU
+// one wavefront per lane).
+__global__ void __launch_bounds__(SORT_TPB, 3) sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 lt_mask = (1u << lane) - 1;
     const u32 total_tiles = min(a.tile_start[a.n_seg], total_bound);
     // (static indexing only: a dynamically indexed kernel-parameter array would be copied to local memory)
     const bool odd = pass & 1;
@@ -327,50 +352,59 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
         const int seg = (int)d4.x;
         const u32 off = d4.y, n = d4.z, w = d4.w;
         const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
-        const size_t obase = (size_t)seg * a.cap;
+        u32* __restrict__ ko = kout + (size_t)seg * a.cap;
+        u32* __restrict__ vo = vout + (size_t)seg * a.cap;
         __syncthreads();
         {
-            u32* z = reinterpret_cast<u32*>(&S.cnt[0][0]);
-            for (u32 i = tid; i < sizeof(S.cnt) / 4; i += SORT_TPB) z[i] = 0;
+            uint2* z = reinterpret_cast<uint2*>(&S.cnt[0][0]);
+            for (u32 i = tid; i < sizeof(S.cnt) / 8; i += SORT_TPB) z[i] = make_uint2(0, 0);
         }
         const TileSrc T = tile_src_setup(a, pass, t, seg, off, S.win);
         __syncthreads();
 
-        u32 key[SORT_KPT], val[SORT_KPT];
-        unsigned short rnk[SORT_KPT];
+        u32 key[SORT_KPT], val[SORT_KPT], rnk[SORT_KPT];
         const u32 wbase = warp * (32 * SORT_KPT) + lane;
+        if (!T.gather) {
+            const u32* __restrict__ kp = T.keys + T.base + wbase;
+            const u32* __restrict__ vp = T.vals + T.base + wbase;
 #pragma unroll
-        for (int k = 0; k < SORT_KPT; ++k) {
-            const u32 idx = wbase + k * 32;
-            const u32 src = idx < n ? (u32)tile_src_index(T, S.win, idx) : 0;
-            key[k] = idx < n ? T.keys[src] : 0xFFFFFFFFu;
-            val[k] = idx < n ? T.vals[src] : 0;
+            for (int k = 0; k < SORT_KPT; ++k) {
+                const bool valid = wbase + k * 32 < n;
+                key[k] = valid ? kp[k * 32] : 0xFFFFFFFFu;
+                val[k] = valid ? vp[k * 32] : 0u;
+            }
+        } else {
+            u32 cur = tile_src_cursor(T);
+#pragma unroll
+            for (int k = 0; k < SORT_KPT; ++k) {
+                const u32 idx = wbase + k * 32;
+                const size_t src = idx < n ? tile_src_index(T, S.win, idx, cur) : 0;
+                key[k] = idx < n ? T.keys[src] : 0xFFFFFFFFu;
+                val[k] = idx < n ? T.vals[src] : 0u;
+            }
         }
-#pragma unroll
-        for (int k = 0; k < SORT_KPT; ++k) {
-            const u32 idx = wbase + k * 32;
-            const u32 d = idx < n ? ((key[k] >> shift) & dmask) : nbins;     // padding lanes share the dummy bin
-            const u32 m = peer_mask(d, w + 1);
-            const int leader = __ffs(m) - 1;
-            u32 old = 0;
-            if (lane == leader) { old = S.cnt[warp][d]; S.cnt[warp][d] = (unsigned short)(old + __popc(m)); }
-            old = __shfl_sync(FULL_MASK, old, leader);
-            rnk[k] = (unsigned short)(old + __popc(m & lt_mask));
-            __syncwarp();
+        switch (w) {                                      // uniform per tile
+            case 10: rank_rows<11>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+            case 9: rank_rows<10>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+            case 8: rank_rows<9>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+            default: rank_rows<8>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
         }
         __syncthreads();
-        // thread b owns bins [4b, 4b+4): per-warp counts -> exclusive offsets across warps, bin totals -> block scan
-        u32 tot[4], tsum = 0;
+        // thread b owns bins [4b, 4b+4): four u16 counters travel as one 64-bit word (no carries: totals <= 4096)
+        u64 run = 0;
+        if ((u32)(4 * tid) < nbins + 1) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const u32 b = 4 * tid + j;
-            u32 run = 0;
-            if (b < nbins) {
-#pragma unroll
-                for (int w2 = 0; w2 < SORT_WARPS; ++w2) { const u32 c = S.cnt[w2][b]; S.cnt[w2][b] = (unsigned short)run; run += c; }
+            for (int w2 = 0; w2 < SORT_WARPS; ++w2) {
+                u64* c4 = reinterpret_cast<u64*>(&S.cnt[w2][4 * tid]);
+                const u64 c = *c4;
+                *c4 = run;
+                run += c;
             }
-            tot[j] = run; tsum += run;
         }
+        u32 tot[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tot[j] = (4 * tid + j < (int)nbins) ? (u32)((run >> (16 * j)) & 0xFFFFu) : 0u;
+        const u32 tsum = tot[0] + tot[1] + tot[2] + tot[3];
         u32 v = tsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
@@ -379,20 +413,18 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
         u32 excl = v - tsum;
 #pragma unroll
         for (int w2 = 0; w2 < SORT_WARPS; ++w2) if (w2 < warp) excl += S.warp_sum[w2];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const u32 b = 4 * tid + j;
-            if (b < nbins) {
-                S.binexcl[b] = (unsigned short)excl;
-                S.binoff[b] = a.bin_base[(size_t)seg * SORT_MAX_BINS + b] + a.tilehist[(size_t)t * SORT_MAX_BINS + b] - excl;
-            }
-            excl += tot[j];
+        if ((u32)(4 * tid) < nbins) {
+            const uint4 bb = *reinterpret_cast<const uint4*>(a.bin_base + (size_t)seg * SORT_MAX_BINS + 4 * tid);
+            const uint4 th = *reinterpret_cast<const uint4*>(a.tilehist + (size_t)t * SORT_MAX_BINS + 4 * tid);
+            const u32 e0 = excl, e1 = e0 + tot[0], e2 = e1 + tot[1], e3 = e2 + tot[2];
+            *reinterpret_cast<uint2*>(&S.binexcl[4 * tid]) = make_uint2(e0 | (e1 << 16), e2 | (e3 << 16));
+            *reinterpret_cast<uint4*>(&S.binoff[4 * tid]) =
+                make_uint4(bb.x + th.x - e0, bb.y + th.y - e1, bb.z + th.z - e2, bb.w + th.w - e3);
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
-            const u32 idx = wbase + k * 32;
-            if (idx < n) {
+            if (wbase + k * 32 < n) {
                 const u32 d = (key[k] >> shift) & dmask;
                 const u32 lpos = (u32)S.binexcl[d] + S.cnt[warp][d] + rnk[k];
                 S.keys[lpos] = key[k];
@@ -400,15 +432,14 @@ __global__ void __launch_bounds__(SORT_TPB) sort_scatter_kernel(SortArgs a, int 
             }
         }
         __syncthreads();
-#pragma unroll 4
+#pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 i = k * SORT_TPB + tid;
-            const bool valid = i < n;
-            if (valid) {
+            if (i < n) {
                 const u32 kk = S.keys[i];
                 const u32 pos = S.binoff[(kk >> shift) & dmask] + i;
-                kout[obase + pos] = kk;
-                vout[obase + pos] = S.vals[i];
+                ko[pos] = kk;
+                vo[pos] = S.vals[i];
             }
         }
     }
