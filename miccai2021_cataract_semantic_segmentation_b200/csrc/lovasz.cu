@@ -520,64 +520,77 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
 }
 
 // Pipelined emission (the fast path): one warp per chunk of consecutive 32-pixel warp tiles, logits prefetched with the
-// warp-private cp.async ring (see WarpTile).  Ranks inside a tile come from ballots, the running per-class offset of
-// the chunk lives in lane c's register: no shared-memory bitmasks, no CTA barriers.
+// warp-private cp.async ring (see WarpTile).  Ranks inside a tile come from per-class ballots, the running per-class
+// offset of the chunk lives in lane c's register: no CTA barriers, no cross-warp traffic.  The tile sequence is walked with increments only (no integer divisions).
+struct EmitCursor {                                       // position in the (group, chunk, tile-in-chunk) sequence
+    u32 k, r, gt, ti;                                     // tile in chunk, chunk in group, tile in group, tile in image
+    int g, n;                                             // group, image
+};
+__device__ __forceinline__ void emit_cursor_init(EmitCursor& c, u32 chunk, u32 tpc, u32 n_runs, u32 wtpi, int per_image) {
+    c.g = (int)(chunk / n_runs);
+    c.r = chunk - (u32)c.g * n_runs;
+    c.k = 0;
+    c.gt = c.r * tpc;
+    c.n = per_image ? c.g : (int)(c.gt / wtpi);
+    c.ti = per_image ? c.gt : c.gt - (u32)c.n * wtpi;
+}
+__device__ __forceinline__ void emit_cursor_next(EmitCursor& c, u32 tpc, u32 n_runs, u32 wtpi, int per_image) {
+    ++c.k; ++c.gt; ++c.ti;
+    if (!per_image && c.ti == wtpi) { c.ti = 0; ++c.n; }
+    if (c.k == tpc) {
+        c.k = 0;
+        if (++c.r == n_runs) { c.r = 0; ++c.g; c.gt = 0; c.ti = 0; c.n = per_image ? c.g : 0; }
+    }
+}
+
 template <int CT, int TPB, int STAGES, typename LT>
 __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
     using W = WarpTile<CT, 1>;
     constexpr int WT = W::WT, NW = TPB / 32;
+    static_assert(STAGES == 2, "the prefetch cursor runs exactly one tile ahead");
     extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
     float (*Zall)[STAGES][CT][WT] = reinterpret_cast<float (*)[STAGES][CT][WT]>(pipe_smem_raw);
     __shared__ float s_thr[NW][B200SEG_MAX_CLASSES], s_logthr[NW][B200SEG_MAX_CLASSES];
-    __shared__ u32 s_ballot[NW][B200SEG_MAX_CLASSES], s_base[NW][B200SEG_MAX_CLASSES];
+    __shared__ u32 s_mask[NW][B200SEG_MAX_CLASSES], s_base[NW][B200SEG_MAX_CLASSES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt_mask = (1u << lane) - 1;
     float (*Z)[CT][WT] = Zall[warp];
-    // all tile / chunk counts fit 32 bits (n_images * plane < 2^30): keep the index math off the 64-bit divider
+    // all tile / chunk counts fit 32 bits (n_images * plane < 2^30)
     const u32 wtpi = (u32)((p.HW + WT - 1) / WT);
     const u32 tpg = p.per_image ? wtpi : wtpi * (u32)p.N;
     const u32 tpc = (u32)p.tiles_per_chunk, n_runs = (u32)p.n_runs;
     const u32 total_chunks = (u32)p.groups * n_runs;
     const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
     const u32 ch0 = (u32)((u64)total_chunks * gw / nwarps), ch1 = (u32)((u64)total_chunks * (gw + 1) / nwarps);
-    const u32 T0 = ch0 * tpc, T1 = ch1 * tpc;            // this warp's slice of the (chunk, tile-in-chunk) sequence
+    const u32 ntile = (ch1 - ch0) * tpc;                  // this warp's slice of the (chunk, tile-in-chunk) sequence
+    if (ntile == 0) return;
 
-    // tile sequence index -> (group, run, image, first pixel); false if the slot lies beyond the group's last tile
-    auto locate = [&](u32 T, int& g, u32& r, int& n, u32& q0) -> bool {
-        const u32 chunk = T / tpc;
-        g = (int)(chunk / n_runs);
-        r = chunk - (u32)g * n_runs;
-        const u32 gt = r * tpc + (T - chunk * tpc);
-        if (gt >= tpg) return false;
-        n = p.per_image ? g : (int)(gt / wtpi);
-        q0 = (p.per_image ? gt : gt - (u32)n * wtpi) * WT;
-        return true;
-    };
-    auto prefetch = [&](u32 T, int stage) {
-        int g, n; u32 r, q0;
-        if (T < T1 && locate(T, g, r, n, q0)) W::prefetch(Z[stage], p.logits, n, q0, p.HW, lane);
+    EmitCursor cur, pre;
+    emit_cursor_init(cur, ch0, tpc, n_runs, wtpi, p.per_image);
+    pre = cur;
+    auto prefetch = [&](const EmitCursor& c, bool live, int stage) {
+        if (live && c.gt < tpg) W::prefetch(Z[stage], p.logits, c.n, (long long)c.ti * WT, p.HW, lane);
         cp_async_commit();
     };
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) prefetch(T0 + s, s);
+    prefetch(pre, true, 0);
 
     int cur_g = -1;
     u32 run = 0;                                          // lane c: candidates of class c emitted so far in this chunk
-    u32 it = 0;
-    for (u32 T = T0; T < T1; ++T, ++it) {
-        const int stage = (int)(it % STAGES);
+    for (u32 it = 0; it < ntile; ++it) {
+        const int stage = (int)(it & 1);
         __syncwarp();
-        prefetch(T + STAGES - 1, (int)((it + STAGES - 1) % STAGES));
-        int g, n = 0; u32 r, q0 = 0;
-        const bool exists = locate(T, g, r, n, q0);
-        const u32 k = T % tpc;
+        emit_cursor_next(pre, tpc, n_runs, wtpi, p.per_image);
+        prefetch(pre, it + 1 < ntile, stage ^ 1);
+        const int g = cur.g, n = cur.n;
+        const u32 r = cur.r, k = cur.k;
+        const bool exists = cur.gt < tpg;
         if (k == 0) run = 0;
         if (g != cur_g) {
             if (lane < CT) { s_thr[warp][lane] = p.seg_thr[(size_t)g * CT + lane]; s_logthr[warp][lane] = p.seg_logthr[(size_t)g * CT + lane]; }
             cur_g = g;
             __syncwarp();
         }
-        const long long q = (long long)q0 + lane;
+        const long long q = (long long)cur.ti * WT + lane;
         const bool inb = exists && q < p.HW;
         float m = 0.f, s = 1.f;
         int lab = -1;
@@ -591,15 +604,14 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
         float e0 = 0.f, e1 = 0.f;                         // errors of the first two of them (the rest is recomputed)
         if (inb) {
             const float theta = pre_theta(m, s);
-            u32 pre = 0;
+            u32 pm = 0;
 #pragma unroll
-            for (int c = 0; c < CT; ++c) pre |= (Tz[c][lane] >= theta + s_logthr[warp][c]) ? (1u << c) : 0u;
-            if (p.has_filter && lab == p.filter) pre = 0;
-            else if ((unsigned)lab < (unsigned)CT && thr_active(thr[lab & 31])) pre |= 1u << lab;
-            u32 mm = pre;
-            while (mm) {
-                const int c = __ffs(mm) - 1;
-                mm &= mm - 1;
+            for (int c = 0; c < CT; ++c) pm |= (Tz[c][lane] >= theta + s_logthr[warp][c]) ? (1u << c) : 0u;
+            if (p.has_filter && lab == p.filter) pm = 0;
+            else if ((unsigned)lab < (unsigned)CT && thr_active(thr[lab & 31])) pm |= 1u << lab;
+            while (pm) {
+                const int c = __ffs(pm) - 1;
+                pm &= pm - 1;
                 float err, pr;
                 if (exact_accept(Tz[c][lane], m, s, c == lab, thr[c], err, pr)) {
                     if (acc == 0) e0 = err; else if ((acc & (acc - 1)) == 0) e1 = err;
@@ -616,7 +628,7 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
                 if (lane == c) mine = b;
             }
             __syncwarp();
-            if (lane < CT) { s_ballot[warp][lane] = mine; s_base[warp][lane] = run; run += __popc(mine); }
+            if (lane < CT) { s_mask[warp][lane] = mine; s_base[warp][lane] = run; run += __popc(mine); }
             __syncwarp();
             u32 mm = acc;
             int i = 0;
@@ -627,13 +639,14 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
                 float err = i == 0 ? e0 : e1;
                 if (i >= 2) { float pr; exact_accept(Tz[c][lane], m, s, fg, thr[c], err, pr); }
                 ++i;
-                const u32 rank = s_base[warp][c] + __popc(s_ballot[warp][c] & lt_mask);
+                const u32 rank = s_base[warp][c] + __popc(s_mask[warp][c] & lt_mask);
                 const size_t slot = ((size_t)g * CT + c) * (size_t)p.src_cap + (size_t)r * p.run_stride + rank;
                 p.keysA[slot] = err_key(err);
                 p.valsA[slot] = ((u32)px << 1) | (fg ? 1u : 0u);
             }
         }
-        if (k == tpc - 1 && lane < CT) p.run_cnt[(size_t)(T / tpc) * CT + lane] = run;
+        if (k == tpc - 1 && lane < CT) p.run_cnt[((size_t)g * n_runs + r) * CT + lane] = run;
+        emit_cursor_next(cur, tpc, n_runs, wtpi, p.per_image);
     }
     cp_async_wait<0>();
 }
@@ -881,7 +894,7 @@ __global__ void __launch_bounds__(BWD_TPB) backward_kernel_v4(LovaszParams p, co
 
 // Pipelined backward (the fast path): lane l of a warp owns pixels [l*VEC, l*VEC+VEC) of the warp tile.
 template <int CT, int VEC, int TPB, int STAGES, typename LT>
-__global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, const float* __restrict__ go,
+__global__ void __launch_bounds__(TPB, (VEC == 1 && TPB == 128) ? 8 : 1) backward_kernel_async(LovaszParams p, const float* __restrict__ go,
                                                               float* __restrict__ dlogits) {
     using W = WarpTile<CT, VEC>;
     constexpr int WT = W::WT, NW = TPB / 32;
@@ -897,24 +910,27 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
     const u32 t0 = (u32)((u64)nwt * gw / nwarps), t1 = (u32)((u64)nwt * (gw + 1) / nwarps);
     const float gsc = __ldg(go);
 
-    auto prefetch = [&](u32 t, int stage) {
-        if (t < t1) {
-            const u32 n = t / wtpi;
-            W::prefetch(Z[stage], p.logits, (int)n, (long long)(t - n * wtpi) * WT, p.HW, lane);
-        }
+    // (image, tile-in-image) cursors advance by increments: no integer division per tile
+    u32 cn = t0 / wtpi, cti = t0 - cn * wtpi;             // tile being consumed
+    u32 pn = cn, pti = cti, pt = t0;                       // next tile to prefetch
+    auto prefetch_next = [&](int stage) {
+        if (pt < t1) W::prefetch(Z[stage], p.logits, (int)pn, (long long)pti * WT, p.HW, lane);
         cp_async_commit();
+        ++pt;
+        if (++pti == wtpi) { pti = 0; ++pn; }
     };
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) prefetch(t0 + s, s);
+    for (int s = 0; s < STAGES - 1; ++s) prefetch_next(s);
 
     int cur_g = -1;
     u32 it = 0;
     for (u32 t = t0; t < t1; ++t, ++it) {
         const int stage = (int)(it % STAGES);
         __syncwarp();                                     // every lane is done reading the stage about to be refilled
-        prefetch(t + STAGES - 1, (int)((it + STAGES - 1) % STAGES));
-        const int n = (int)(t / wtpi);
-        const long long q = (long long)(t - (u32)n * wtpi) * WT + l0;
+        prefetch_next((int)((it + STAGES - 1) % STAGES));
+        const int n = (int)cn;
+        const long long q = (long long)cti * WT + l0;
+        if (++cti == wtpi) { cti = 0; ++cn; }
         const int g = p.per_image ? n : 0;
         if (g != cur_g) {
             if (lane < CT) { s_thr[warp][lane] = p.seg_thr[(size_t)g * CT + lane]; s_logthr[warp][lane] = p.seg_logthr[(size_t)g * CT + lane]; }
@@ -958,9 +974,8 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
         // sweep 1 (branch-free): conservative candidate bits
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
-            const float lt = s_logthr[warp][c];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) pre[j] |= (T[c][l0 + j] >= theta[j] + lt) ? (1u << c) : 0u;
+            for (int j = 0; j < VEC; ++j) pre[j] |= (T[c][l0 + j] >= theta[j] + s_logthr[warp][c]) ? (1u << c) : 0u;
         }
         // exact stage on the flagged classes: same predicate as the emission kernel
         float dot[VEC], nd[VEC], ownv[VEC];
