@@ -137,6 +137,12 @@ int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_o
                           const uint32_t* counts, const uint32_t* key_bits, int32_t n_segments, int64_t capacity,
                           void* scratch, size_t scratch_bytes, int32_t* status, void* stream);
 
+/* Test hook: byte offsets inside the Lovasz workspace of {pix_m, pix_s, label8, candidate mask, rec16, rec4,
+ * seg_thr, grp_tmin} (see DESIGN.md "Data layout"), so tests can check the per-pixel candidate records that
+ * b200seg_lovasz_forward leaves behind against a straightforward softmax / top-k. */
+int b200seg_debug_layout(int32_t n_images, int32_t n_classes, int64_t plane, int32_t per_image,
+                         size_t* offsets, int32_t n_offsets);
+
 #ifdef __cplusplus
 }
 #endif

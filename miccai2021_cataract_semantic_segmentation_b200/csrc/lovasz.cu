@@ -26,7 +26,8 @@
 #define BWD_TPB 128
 #define JAC_TPB SORT_TPB
 
-enum { CTRL_STATUS = 8 };
+enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_GEO = 32 };
+enum { EMIT_PATH_STREAM = 0, EMIT_PATH_RECORDS = 1 };
 
 struct LovaszParams {
     const float* logits;
@@ -41,10 +42,18 @@ struct LovaszParams {
     u32 *seg_fg, *seg_maxkey, *seg_maxp, *seg_count, *grp_valid, *seg_bits;
     double* seg_loss;
     float *seg_thr, *seg_logthr, *seg_w;
+    float* grp_tmin;                    // [groups] smallest threshold among the group's summed classes
+    int have_records;                   // stats_kernel_async ran: rec16 / rec4 are valid
+    int emit_force;                     // 0 = decide on the device, 1 = record path, 2 = streaming path (B200SEG_EMIT_PATH)
     float *pix_m, *pix_s, *gown, *gbg;
+    unsigned char* lab8;                // per pixel: class 0..C-1, LAB8_NONE (not a class), LAB8_FILTERED
+    u32* cmask;                         // per pixel: classes emitted as BACKGROUND candidates (written by K2)
+    uint4* rec16;                       // per pixel candidate record (stats_kernel_async): {key_fg, p1, p2, guard p3}
+    u32* rec4;                          //   label8 | class1 << 8 | class2 << 16
+    u32* flags;                         // [0] emission path chosen by K1b (EMIT_PATH_*)
     u32 *run_cnt, *run_prefix;          // [groups*n_runs][C] candidate counts per emission chunk; [n_seg][n_runs+1]
-    int n_runs, tiles_per_chunk;        // emission chunks per group, emission tiles per chunk
-    long long run_stride, src_cap;      // slots per chunk, holey segment stride (= n_runs * run_stride)
+    EmitGeomDev geo_stream, geo_rec;    // chunk geometry of the streaming / record-driven emission kernels
+    EmitGeomDev* geo;                   // the one in force (device memory; written by K1b / K1d, read by K2 and the sort)
     u32 *keysA, *valsA, *keysB, *valsB;
     // fused confusion matrix
     unsigned long long* cm;
@@ -55,8 +64,8 @@ struct LovaszParams {
 
 struct LovaszLayout {
     size_t ctrl, seg_fg, seg_maxkey, seg_maxp, seg_count, grp_valid, seg_loss, zero_end;
-    size_t seg_thr, seg_logthr, seg_w, seg_bits, run_cnt, run_prefix;
-    size_t pix_m, pix_s, gown, keysA, valsA, keysB, valsB, sort_scratch, total;
+    size_t seg_thr, seg_logthr, seg_w, seg_bits, grp_tmin, run_cnt, run_prefix;
+    size_t pix_m, pix_s, gown, lab8, cmask, rec16, rec4, keysA, valsA, keysB, valsB, sort_scratch, total;
     SortScratch sort;
 };
 
@@ -70,7 +79,9 @@ static EmitGeom emit_geom(int N, long long HW, int per_image, long long tile_px)
     G.tpi = (HW + G.tile_px - 1) / G.tile_px;
     G.tpg = per_image ? G.tpi : G.tpi * N;
     const long long total_tiles = G.tpi * N;
-    const long long target_chunks = tile_px <= 64 ? 4096 : 1024;   // chunks over the whole batch
+    // chunks over the whole batch: the pipelined kernel (32-pixel tiles) runs one chunk per resident warp
+    // and the record-driven CTA kernel (1024-pixel tiles) one chunk per resident CTA
+    const long long target_chunks = (long long)b200seg_sm_count() * (tile_px <= 64 ? 32 : (tile_px == 1024 ? 4 : 8));
     G.tpc = (total_tiles + target_chunks - 1) / target_chunks;
     if (G.tpc < 1) G.tpc = 1;
     G.n_runs = (G.tpg + G.tpc - 1) / G.tpc;
@@ -107,11 +118,16 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     L.seg_logthr = o; o = align_up(o + 4 * S, 256);
     L.seg_w = o;      o = align_up(o + 4 * S, 256);
     L.seg_bits = o;   o = align_up(o + 4 * S, 256);
+    L.grp_tmin = o;   o = align_up(o + 4 * (size_t)groups, 256);
     L.run_cnt = o;    o = align_up(o + 4 * runs * C, 256);
     L.run_prefix = o; o = align_up(o + 4 * (runs + (size_t)groups) * C, 256);
     L.pix_m = o;      o = align_up(o + 4 * (size_t)P, 256);
     L.pix_s = o;      o = align_up(o + 4 * (size_t)P, 256);
     L.gown = o;       o = align_up(o + 4 * (size_t)P, 256);
+    L.lab8 = o;       o = align_up(o + (size_t)P + 16, 256);
+    L.cmask = o;      o = align_up(o + 4 * (size_t)P, 256);
+    L.rec16 = o;      o = align_up(o + 16 * (size_t)P, 256);
+    L.rec4 = o;       o = align_up(o + 4 * (size_t)P, 256);
     L.keysA = o;      o = align_up(o + 4 * holey, 256);
     L.valsA = o;      o = align_up(o + 4 * holey, 256);
     L.keysB = o;      o = align_up(o + 4 * CP, 256);
@@ -137,6 +153,12 @@ __device__ __forceinline__ bool exact_accept(float z, float m, float s, bool fg,
     return pr >= thr;
 }
 #define THR_INACTIVE 2.0f
+#define LAB8_NONE 255u               // label outside [0, C): the pixel is background for every class
+#define LAB8_FILTERED 254u           // label == classes_to_ignore: the pixel is removed from the loss
+__device__ __forceinline__ u32 lab8_encode(int lab, int C, int has_filter, int filter) {
+    if (has_filter && lab == filter) return LAB8_FILTERED;
+    return (unsigned)lab < (unsigned)C ? (u32)lab : LAB8_NONE;
+}
 __device__ __forceinline__ bool thr_active(float thr) { return thr <= 1.5f; }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -260,9 +282,15 @@ __global__ void __launch_bounds__(TPB) stats_kernel_vec(LovaszParams p) {
         if constexpr (VEC == 4) {
             *(float4*)(p.pix_m + px) = make_float4(mo[0], mo[1], mo[2], mo[3]);
             *(float4*)(p.pix_s + px) = make_float4(so[0], so[1], so[2], so[3]);
+            u32 l4 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) l4 |= lab8_encode(lab[j], CT, p.has_filter, p.filter) << (8 * j);
+            *(u32*)(p.lab8 + px) = l4;
         } else {
             *(float2*)(p.pix_m + px) = make_float2(mo[0], mo[1]);
             *(float2*)(p.pix_s + px) = make_float2(so[0], so[1]);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) p.lab8[px + j] = (unsigned char)lab8_encode(lab[j], CT, p.has_filter, p.filter);
         }
     }
     if (cur_g >= 0) { if (nvalid) atomicAdd(&sm.valid, nvalid); stats_flush_group(p, sm, cur_g); }
@@ -305,10 +333,182 @@ __global__ void __launch_bounds__(STATS_TPB) stats_kernel_generic(LovaszParams p
             e_lab = (c == lab) ? e : e_lab;
         }
         p.pix_m[px] = m; p.pix_s[px] = s;
+        p.lab8[px] = (unsigned char)lab8_encode(lab, C, p.has_filter, p.filter);
         stats_pixel_tail(p, sm, lab, e_lab, s, arg, C, nvalid);
     }
     if (cur_g >= 0) { if (nvalid) atomicAdd(&sm.valid, nvalid); stats_flush_group(p, sm, cur_g); }
     stats_flush_cm(p, sm);
+}
+
+// Pipelined stats (the fast path): one warp owns a contiguous range of 32-pixel warp tiles; logits AND labels arrive
+// through the warp-private cp.async ring STAGES-1 tiles ahead of the math (completion tracked by wait_group, so no
+// global-load scoreboard sits on the critical path).  Lane l owns pixel l of the tile: C exps in registers, dynamic
+// class indices address shared memory.  Per-class counters are warp-private in shared memory (no CTA barrier in the loop).
+//
+// Besides the softmax state the kernel leaves a 20-byte candidate record per pixel, so that the emission pass does not
+// have to read the logits again:
+//   rec16 = { key of the own-class error 1 - p_label, p of the two most probable OTHER classes, upper bound of the third }
+//   rec4  = label8 | class of p1 << 8 | class of p2 << 16
+// Every class outside {label, c1, c2} has p <= the guard, so a pixel whose guard is below the smallest class threshold
+// has no further candidates (always true when that threshold exceeds 1/3); the rest take emit_kernel_rec's slow path.
+template <int CT, int TPB, int STAGES, typename LT>
+__global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
+    using W = WarpTile<CT, 1>;
+    constexpr int WT = W::WT, NW = TPB / 32;
+    constexpr int LAB_BYTES = WT * (int)sizeof(LT);       // label bytes of one tile
+    constexpr int LCH = LAB_BYTES / 16 > 0 ? LAB_BYTES / 16 : 1;   // 16-byte chunks of the label row
+    constexpr int PX_PER_CH = 16 / (int)sizeof(LT);
+    constexpr int STAGE_BYTES = CT * WT * 4 + 256;
+    extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
+    __shared__ u32 s_cm[B200SEG_MAX_CLASSES * B200SEG_MAX_CLASSES];
+    __shared__ u32 s_fg[NW][B200SEG_MAX_CLASSES], s_key[NW][B200SEG_MAX_CLASSES];
+    __shared__ u32 s_valid, s_oob;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* ring = pipe_smem_raw + (size_t)warp * STAGES * STAGE_BYTES;
+    for (int i = tid; i < CT * CT; i += TPB) s_cm[i] = 0;
+    s_fg[warp][lane] = 0; s_key[warp][lane] = 0;
+    if (tid == 0) { s_valid = 0; s_oob = 0; }
+    __syncthreads();
+
+    const u32 wtpi = (u32)((p.HW + WT - 1) / WT);
+    const u32 nwt = wtpi * (u32)p.N;
+    const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
+    const u32 t0 = (u32)((u64)nwt * gw / nwarps), t1 = (u32)((u64)nwt * (gw + 1) / nwarps);
+    u32 cn = t0 / wtpi, cti = t0 - cn * wtpi;             // tile being consumed
+    u32 pn = cn, pti = cti, pt = t0;                       // next tile to prefetch
+    auto prefetch_next = [&](int stage) {
+        if (pt < t1) {
+            unsigned char* sb = ring + (size_t)stage * STAGE_BYTES;
+            const long long q0 = (long long)pti * WT;
+            W::prefetch(reinterpret_cast<float (*)[WT]>(sb), p.logits, (int)pn, q0, p.HW, lane);
+            if (lane < LCH && q0 + (long long)lane * PX_PER_CH < p.HW)
+                cp_async<16>(sb + CT * WT * 4 + lane * 16,
+                             (const unsigned char*)p.labels + ((size_t)pn * p.HW + q0) * sizeof(LT) + lane * 16);
+        }
+        cp_async_commit();
+        ++pt;
+        if (++pti == wtpi) { pti = 0; ++pn; }
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) prefetch_next(s);
+
+    auto flush_group = [&](int g, u32 nvalid) {           // warp-private counters -> global (per-image mode)
+        __syncwarp();
+        if (lane < CT) {
+            const size_t seg = (size_t)g * CT + lane;
+            const u32 f = s_fg[warp][lane];
+            if (f) { atomicAdd(p.seg_fg + seg, f); atomicMax(p.seg_maxkey + seg, s_key[warp][lane]); }
+            s_fg[warp][lane] = 0; s_key[warp][lane] = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(FULL_MASK, nvalid, o);
+        if (lane == 0 && nvalid) atomicAdd(p.grp_valid + g, nvalid);
+        __syncwarp();
+    };
+
+    int cur_g = -1, stage = 0, pstage = STAGES - 1;
+    u32 nvalid = 0, oob = 0;
+    for (u32 t = t0; t < t1; ++t) {
+        __syncwarp();                                     // every lane is done reading the stage about to be refilled
+        prefetch_next(pstage);
+        if (++pstage == STAGES) pstage = 0;
+        const int n = (int)cn;
+        const long long q = (long long)cti * WT + lane;
+        if (++cti == wtpi) { cti = 0; ++cn; }
+        const int g = p.per_image ? n : 0;
+        if (g != cur_g) {
+            if (cur_g >= 0) { flush_group(cur_g, nvalid); nvalid = 0; }
+            cur_g = g;
+        }
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        const unsigned char* sb = ring + (size_t)stage * STAGE_BYTES;
+        const float (*T)[WT] = reinterpret_cast<const float (*)[WT]>(sb);
+        if (++stage == STAGES) stage = 0;
+        if (q >= p.HW) continue;
+        const size_t px = (size_t)n * p.HW + q;
+        int lab;
+        if constexpr (sizeof(LT) == 8) lab = sat_i32(reinterpret_cast<const long long*>(sb + CT * WT * 4)[lane]);
+        else lab = (int)reinterpret_cast<const LT*>(sb + CT * WT * 4)[lane];
+        float z[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) z[c] = T[c][lane];
+        float m = z[0];
+#pragma unroll
+        for (int c = 1; c < CT; ++c) m = fmaxf(m, z[c]);
+        // softmax denominator (ascending class order, like ATen) and the three largest exps among the other classes:
+        // exps are positive, so their bit patterns order like integers; the class index rides in the low 5 bits
+        float s = 0.f;
+        int b1 = -1, b2 = -1, b3 = -1;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float e = sm_exp(z[c], m);
+            s = __fadd_rn(s, e);
+            int v = (int)((__float_as_uint(e) & ~31u) | (u32)c);
+            v = (c == lab) ? -1 : v;
+            const int t1v = min(b1, v); b1 = max(b1, v);
+            const int t2v = min(b2, t1v); b2 = max(b2, t1v);
+            b3 = max(b3, t2v);
+        }
+        p.pix_m[px] = m; p.pix_s[px] = s;
+        const u32 l8 = lab8_encode(lab, CT, p.has_filter, p.filter);
+        p.lab8[px] = (unsigned char)l8;
+        u32 kfg = 0;
+        if (l8 != LAB8_FILTERED) {
+            ++nvalid;
+            if (l8 < (u32)CT) {
+                const float pr = sm_prob(T[l8][lane], m, s);
+                kfg = err_key(__fsub_rn(1.0f, pr));
+                atomicAdd(&s_fg[warp][l8], 1u);
+                atomicMax(&s_key[warp][l8], kfg);
+            }
+        }
+        {
+            const int c1 = b1 & 31, c2 = b2 & 31;          // CT >= 4: b1..b3 are real classes
+            const float p1 = sm_prob(T[c1][lane], m, s), p2 = sm_prob(T[c2][lane], m, s);
+            const float p3 = __fdiv_ru(__uint_as_float((u32)b3 | 31u), s);   // >= p of every class not recorded
+            p.rec16[px] = make_uint4(kfg, __float_as_uint(p1), __float_as_uint(p2), __float_as_uint(p3));
+            p.rec4[px] = l8 | ((u32)c1 << 8) | ((u32)c2 << 16);
+        }
+        if (p.cm && !(p.has_drop && lab == p.drop)) {
+            if ((unsigned)lab < (unsigned)CT) {
+                int arg = 0;
+#pragma unroll
+                for (int c = CT - 1; c >= 0; --c) arg = (z[c] == m) ? c : arg;          // first maximum
+                if (s != s || m != m) {                   // NaN / inf among the logits: torch's argmax lets NaN win
+                    float best = z[0];
+                    arg = 0;
+#pragma unroll
+                    for (int c = 1; c < CT; ++c) argmax_step(z[c], c, best, arg);
+                }
+                atomicAdd(&s_cm[arg * CT + lab], 1u);
+            } else oob = 1;
+        }
+    }
+    cp_async_wait<0>();
+    if (cur_g >= 0 && p.per_image) { flush_group(cur_g, nvalid); nvalid = 0; }
+    // flat mode: combine the CTA's warps first (one global atomic per class and CTA)
+    if (oob) s_oob = 1;
+    if (!p.per_image) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(FULL_MASK, nvalid, o);
+        if (lane == 0 && nvalid) atomicAdd(&s_valid, nvalid);
+    }
+    __syncthreads();
+    if (!p.per_image) {
+        if (tid < CT) {
+            u32 f = 0, k = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { f += s_fg[w][tid]; k = max(k, s_key[w][tid]); }
+            if (f) { atomicAdd(p.seg_fg + tid, f); atomicMax(p.seg_maxkey + tid, k); }
+        }
+        if (tid == 0 && s_valid) atomicAdd(p.grp_valid, s_valid);
+    }
+    if (p.cm) {
+        for (int i = tid; i < CT * CT; i += TPB)
+            if (s_cm[i]) atomicAdd(p.cm + i, (unsigned long long)s_cm[i]);
+        if (tid == 0 && s_oob) atomicOr(p.status, STATUS_LABEL_OOB);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -346,8 +546,10 @@ __global__ void __launch_bounds__(256) absent_max_kernel(LovaszParams p) {
 // --------------------------------------------------------------------------------------------------------------
 __global__ void finalize_stats_kernel(LovaszParams p) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) *p.geo = p.geo_stream;
     if (g >= p.groups) return;
     int nkept = 0;
+    float tmin = THR_INACTIVE;
     const bool any_valid = p.grp_valid[g] > 0;
     for (int c = 0; c < p.C; ++c) {
         const size_t seg = (size_t)g * p.C + c;
@@ -361,12 +563,14 @@ __global__ void finalize_stats_kernel(LovaszParams p) {
             logthr = thr > 0.f ? logf(thr) : __int_as_float(0xff800000);
             const u32 maxkey = ONE_BITS - thr_bits;
             bits = maxkey ? (32 - __clz(maxkey)) : 1;
+            tmin = fminf(tmin, thr);
             ++nkept;
         }
         p.seg_thr[seg] = thr;
         p.seg_logthr[seg] = logthr;
         p.seg_bits[seg] = bits;
     }
+    p.grp_tmin[g] = tmin;
     // d(mean)/d(term): the reference's mean() divides only when it averaged more than one value
     float w = 1.0f;
     if (p.groups > 1) w = w / (float)p.groups;
@@ -374,6 +578,41 @@ __global__ void finalize_stats_kernel(LovaszParams p) {
     for (int c = 0; c < p.C; ++c) {
         const size_t seg = (size_t)g * p.C + c;
         p.seg_w[seg] = thr_active(p.seg_thr[seg]) ? w : 0.f;
+    }
+}
+
+// K1d: choose the emission path.  The record path is exact for any input but pays a gather per pixel whose guard
+// reaches the smallest threshold; a sample of the guards estimates how many there are (a performance heuristic only).
+#define DECIDE_BLOCKS 32
+#define DECIDE_TPB 256
+__global__ void __launch_bounds__(DECIDE_TPB) emit_decide_kernel(LovaszParams p) {
+    __shared__ u32 s_slow, s_n;
+    if (threadIdx.x == 0) { s_slow = 0; s_n = 0; }
+    __syncthreads();
+    const long long target = 65536;
+    const long long stride = p.P > target ? p.P / target : 1;
+    u32 slow = 0, n = 0;
+    for (long long i = (long long)blockIdx.x * DECIDE_TPB + threadIdx.x; i * stride < p.P; i += (long long)DECIDE_BLOCKS * DECIDE_TPB) {
+        const long long px = i * stride;
+        const int g = p.per_image ? (int)(px / p.HW) : 0;
+        slow += __uint_as_float(p.rec16[px].w) >= p.grp_tmin[g];
+        ++n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { slow += __shfl_xor_sync(FULL_MASK, slow, o); n += __shfl_xor_sync(FULL_MASK, n, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_slow, slow); atomicAdd(&s_n, n); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(p.ctrl + CTRL_SLOW, s_slow);
+        atomicAdd(p.ctrl + CTRL_SAMPLES, s_n);
+        __threadfence();
+        if (atomicAdd(p.ctrl + CTRL_TICKET, 1u) == DECIDE_BLOCKS - 1) {
+            __threadfence();
+            const u32 ts = ld_relaxed(p.ctrl + CTRL_SLOW), tn = ld_relaxed(p.ctrl + CTRL_SAMPLES);
+            const bool rec = p.emit_force == 1 || (p.emit_force == 0 && (u64)ts * 32 <= tn);
+            p.flags[0] = rec ? EMIT_PATH_RECORDS : EMIT_PATH_STREAM;
+            if (rec) *p.geo = p.geo_rec;
+        }
     }
 }
 
@@ -397,14 +636,15 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
     const int C = p.C;
     const long long tpi = (p.HW + TILE_PX - 1) / TILE_PX;
     const long long tpg = p.per_image ? tpi : tpi * p.N;
-    const long long total_chunks = (long long)p.groups * p.n_runs;
+    const EmitGeomDev G = *p.geo;
+    const long long total_chunks = (long long)p.groups * G.n_runs;
     int cur_g = -1;
 
     for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
-        const int g = (int)(chunk / p.n_runs);
-        const long long r = chunk - (long long)g * p.n_runs;
-        const long long gt0 = r * p.tiles_per_chunk;
-        const long long gt1 = min(gt0 + (long long)p.tiles_per_chunk, tpg);
+        const int g = (int)(chunk / G.n_runs);
+        const long long r = chunk - (long long)g * G.n_runs;
+        const long long gt0 = r * G.tiles_per_chunk;
+        const long long gt1 = min(gt0 + (long long)G.tiles_per_chunk, tpg);
         __syncthreads();                                   // previous chunk fully written out
         if (g != cur_g) {
             if (tid < C) { s_thr[tid] = p.seg_thr[(size_t)g * C + tid]; s_logthr[tid] = p.seg_logthr[(size_t)g * C + tid]; }
@@ -465,6 +705,9 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
                             acc[j] |= 1u << c;
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)        // background candidates of the pixel, for the backward pass
+                    p.cmask[px0 + j] = (unsigned)lab[j] < (unsigned)C ? (acc[j] & ~(1u << lab[j])) : acc[j];
                 u32 uni = 0;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) uni |= acc[j];
@@ -504,7 +747,7 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
                         exact_accept(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j], fg, s_thr[c], err, pr);
                         const u32 rank = s_run[c] + s_wpre[c][bit >> 5] +
                                          __popc(s_mask[c][bit >> 5] & ((1u << (bit & 31)) - 1u));
-                        const size_t slot = ((size_t)g * C + c) * (size_t)p.src_cap + (size_t)r * p.run_stride + rank;
+                        const size_t slot = ((size_t)g * C + c) * (size_t)G.src_cap + (size_t)r * G.run_stride + rank;
                         p.keysA[slot] = err_key(err);
                         p.valsA[slot] = ((u32)(px0 + j) << 1) | (fg ? 1u : 0u);
                     }
@@ -543,14 +786,15 @@ __device__ __forceinline__ void emit_cursor_next(EmitCursor& c, u32 tpc, u32 n_r
     }
 }
 
-template <int CT, int TPB, int STAGES, typename LT>
+template <int CT, int TPB>
 __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
+    if (p.flags[0] != EMIT_PATH_STREAM) return;           // ctrl is zeroed per call: the default path is this one
     using W = WarpTile<CT, 1>;
-    constexpr int WT = W::WT, NW = TPB / 32;
-    static_assert(STAGES == 2, "the prefetch cursor runs exactly one tile ahead");
+    constexpr int WT = W::WT, NW = TPB / 32, STAGES = 2;  // the prefetch cursor runs exactly one tile ahead
     extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
     float (*Zall)[STAGES][CT][WT] = reinterpret_cast<float (*)[STAGES][CT][WT]>(pipe_smem_raw);
-    __shared__ float s_thr[NW][B200SEG_MAX_CLASSES], s_logthr[NW][B200SEG_MAX_CLASSES];
+    __shared__ float s_thr[NW][B200SEG_MAX_CLASSES];
+    __shared__ __align__(16) float s_logthr[NW][B200SEG_MAX_CLASSES];
     __shared__ u32 s_mask[NW][B200SEG_MAX_CLASSES], s_base[NW][B200SEG_MAX_CLASSES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt_mask = (1u << lane) - 1;
@@ -558,7 +802,8 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
     // all tile / chunk counts fit 32 bits (n_images * plane < 2^30)
     const u32 wtpi = (u32)((p.HW + WT - 1) / WT);
     const u32 tpg = p.per_image ? wtpi : wtpi * (u32)p.N;
-    const u32 tpc = (u32)p.tiles_per_chunk, n_runs = (u32)p.n_runs;
+    const EmitGeomDev G = *p.geo;
+    const u32 tpc = (u32)G.tiles_per_chunk, n_runs = (u32)G.n_runs;
     const u32 total_chunks = (u32)p.groups * n_runs;
     const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
     const u32 ch0 = (u32)((u64)total_chunks * gw / nwarps), ch1 = (u32)((u64)total_chunks * (gw + 1) / nwarps);
@@ -568,8 +813,20 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
     EmitCursor cur, pre;
     emit_cursor_init(cur, ch0, tpc, n_runs, wtpi, p.per_image);
     pre = cur;
+    // per-pixel state of the tile in flight (softmax max / denominator, compact label): loaded with the prefetch,
+    // consumed one iteration later
+    float nm = 0.f, ns = 1.f;
+    u32 nl8 = LAB8_FILTERED;
     auto prefetch = [&](const EmitCursor& c, bool live, int stage) {
-        if (live && c.gt < tpg) W::prefetch(Z[stage], p.logits, c.n, (long long)c.ti * WT, p.HW, lane);
+        nm = 0.f; ns = 1.f; nl8 = LAB8_FILTERED;
+        if (live && c.gt < tpg) {
+            W::prefetch(Z[stage], p.logits, c.n, (long long)c.ti * WT, p.HW, lane);
+            const long long q = (long long)c.ti * WT + lane;
+            if (q < p.HW) {
+                const size_t px = (size_t)c.n * p.HW + q;
+                nm = p.pix_m[px]; ns = p.pix_s[px]; nl8 = p.lab8[px];
+            }
+        }
         cp_async_commit();
     };
     prefetch(pre, true, 0);
@@ -578,6 +835,8 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
     u32 run = 0;                                          // lane c: candidates of class c emitted so far in this chunk
     for (u32 it = 0; it < ntile; ++it) {
         const int stage = (int)(it & 1);
+        const float m = nm, s = ns;
+        const u32 l8 = nl8;
         __syncwarp();
         emit_cursor_next(pre, tpc, n_runs, wtpi, p.per_image);
         prefetch(pre, it + 1 < ntile, stage ^ 1);
@@ -586,29 +845,37 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
         const bool exists = cur.gt < tpg;
         if (k == 0) run = 0;
         if (g != cur_g) {
+            __syncwarp();
             if (lane < CT) { s_thr[warp][lane] = p.seg_thr[(size_t)g * CT + lane]; s_logthr[warp][lane] = p.seg_logthr[(size_t)g * CT + lane]; }
             cur_g = g;
             __syncwarp();
         }
         const long long q = (long long)cur.ti * WT + lane;
         const bool inb = exists && q < p.HW;
-        float m = 0.f, s = 1.f;
-        int lab = -1;
         const size_t px = (size_t)n * p.HW + q;
-        if (inb) { m = p.pix_m[px]; s = p.pix_s[px]; lab = load_label<LT>(p.labels, px); }
         cp_async_wait<STAGES - 1>();
         __syncwarp();
         const float (*Tz)[WT] = Z[stage];
         const float* thr = s_thr[warp];
         u32 acc = 0;                                      // accepted classes of this lane's pixel
         float e0 = 0.f, e1 = 0.f;                         // errors of the first two of them (the rest is recomputed)
+        const int lab = l8 < (u32)CT ? (int)l8 : -1;
         if (inb) {
             const float theta = pre_theta(m, s);
             u32 pm = 0;
+            const float4* lt4 = reinterpret_cast<const float4*>(s_logthr[warp]);   // broadcast 128-bit reads
 #pragma unroll
-            for (int c = 0; c < CT; ++c) pm |= (Tz[c][lane] >= theta + s_logthr[warp][c]) ? (1u << c) : 0u;
-            if (p.has_filter && lab == p.filter) pm = 0;
-            else if ((unsigned)lab < (unsigned)CT && thr_active(thr[lab & 31])) pm |= 1u << lab;
+            for (int c4 = 0; c4 < (CT + 3) / 4; ++c4) {
+                const float4 lt = lt4[c4];
+                const float l[4] = {lt.x, lt.y, lt.z, lt.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = 4 * c4 + j;
+                    if (c < CT) pm |= (Tz[c][lane] >= theta + l[j]) ? (1u << c) : 0u;
+                }
+            }
+            if (l8 == LAB8_FILTERED) pm = 0;
+            else if (lab >= 0 && thr_active(thr[lab])) pm |= 1u << lab;
             while (pm) {
                 const int c = __ffs(pm) - 1;
                 pm &= pm - 1;
@@ -618,9 +885,11 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
                     acc |= 1u << c;
                 }
             }
+            p.cmask[px] = lab >= 0 ? (acc & ~(1u << lab)) : acc;
         }
         if (__any_sync(FULL_MASK, acc != 0)) {
-            // lane c collects the ballot of class c and reserves the slots; the table goes through shared memory
+            // lane c collects the ballot of class c (independent votes, unrolled: a data-dependent loop over the classes
+            // present would serialise their latencies) and reserves the slots; the table goes through shared memory
             u32 mine = 0;
 #pragma unroll
             for (int c = 0; c < CT; ++c) {
@@ -640,7 +909,7 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
                 if (i >= 2) { float pr; exact_accept(Tz[c][lane], m, s, fg, thr[c], err, pr); }
                 ++i;
                 const u32 rank = s_base[warp][c] + __popc(s_mask[warp][c] & lt_mask);
-                const size_t slot = ((size_t)g * CT + c) * (size_t)p.src_cap + (size_t)r * p.run_stride + rank;
+                const size_t slot = ((size_t)g * CT + c) * (size_t)G.src_cap + (size_t)r * G.run_stride + rank;
                 p.keysA[slot] = err_key(err);
                 p.valsA[slot] = ((u32)px << 1) | (fg ? 1u : 0u);
             }
@@ -651,20 +920,260 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
     cp_async_wait<0>();
 }
 
+// Record-driven emission (the fast path after stats_kernel_async): candidates come from the 20-byte per-pixel records;
+// the logits are only touched by pixels whose guard says a class beyond the two recorded ones could qualify.
+// One CTA per chunk of consecutive 1024-pixel tiles.  Per tile: every thread decodes 4 pixels, sets one bit per
+// (pixel, class) candidate in a shared bit matrix, a popcount prefix over the 32 words of each class gives the ranks in
+// pixel order, candidates are staged in shared memory grouped by class and written out by whole warps in multiples of 8
+// elements (full 32-byte sectors, each written exactly once: a partially written sector costs an L2 fill from DRAM and
+// a scattered 4-byte store a whole LSU wavefront); the < 8 leftovers of each class are carried to the next tile.
+// Same slot layout (chunk-private runs), outputs and tie order as the streaming kernel.  Exits at once unless K1d
+// selected this path.
+// classes outside `skip` whose probability reaches their threshold, for one pixel (the rare path of the record kernel;
+// deliberately not inlined so that the common path carries neither its instructions nor its registers)
+__device__ __noinline__ u32 emit_scan_pixel(const float* lp, long long plane, int C, float m, float sden,
+                                            const float* thr, u32 skip) {
+    u32 more = 0;
+    for (int c0 = 0; c0 < C; c0 += 8) {                    // 8 independent loads in flight
+        float z[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = c0 + i < C ? __ldg(lp + (size_t)(c0 + i) * plane) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + i;
+            if (c < C && !((skip >> c) & 1u) && sm_prob(z[i], m, sden) >= thr[c]) more |= 1u << c;
+        }
+    }
+    return more;
+}
+
+#define ECTA_TPB 256
+#define ECTA_TILE (ECTA_TPB * 4)
+#define ECTA_WORDS (ECTA_TILE / 32)
+#define ECTA_CAP 4096                                     // staged candidates per pass over the classes of a tile
+struct EctaSmem {
+    u32 mask[B200SEG_MAX_CLASSES][ECTA_WORDS];            // bit (pixel in tile) set = candidate of the class
+    u32 wpre[B200SEG_MAX_CLASSES][ECTA_WORDS];            // exclusive popcount prefix over the words
+    u32 tot[B200SEG_MAX_CLASSES];                         // candidates of the class in this tile
+    u32 coff[B200SEG_MAX_CLASSES];                        // offset of the class in the stage (current pass)
+    u32 carry_cnt[B200SEG_MAX_CLASSES];                   // leftovers (< 8) waiting for the next tile
+    u32 emitted[B200SEG_MAX_CLASSES];                     // elements of the chunk already written (multiple of 8)
+    u32 carryK[B200SEG_MAX_CLASSES][8], carryV[B200SEG_MAX_CLASSES][8];
+    float thr[B200SEG_MAX_CLASSES];
+    u32 stageK[ECTA_CAP], stageV[ECTA_CAP];
+};
+
+template <int CT>
+__global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
+    if (p.flags[0] != EMIT_PATH_RECORDS) return;
+    extern __shared__ __align__(16) unsigned char ecta_smem_raw[];
+    EctaSmem& S = *reinterpret_cast<EctaSmem*>(ecta_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = ECTA_TPB / 32;
+    const EmitGeomDev G = *p.geo;
+    const long long tpi = (p.HW + ECTA_TILE - 1) / ECTA_TILE;
+    const long long tpg = p.per_image ? tpi : tpi * p.N;
+    const long long total_chunks = (long long)p.groups * G.n_runs;
+    const int word = tid >> 3, shift = (tid & 7) * 4;     // this thread's 4 pixels: bits [shift, shift + 4) of `word`
+    int cur_g = -1;
+    float tmin = 0.f;
+
+    for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+        const int g = (int)(chunk / G.n_runs);
+        const long long r = chunk - (long long)g * G.n_runs;
+        const long long gt0 = r * G.tiles_per_chunk;
+        const long long gt1 = min(gt0 + (long long)G.tiles_per_chunk, tpg);
+        __syncthreads();                                   // previous chunk fully written out
+        if (g != cur_g) {
+            if (tid < B200SEG_MAX_CLASSES) S.thr[tid] = tid < CT ? p.seg_thr[(size_t)g * CT + tid] : THR_INACTIVE;
+            tmin = p.grp_tmin[g];
+            cur_g = g;
+        }
+        if (tid < B200SEG_MAX_CLASSES) { S.carry_cnt[tid] = 0; S.emitted[tid] = 0; }
+        for (int i = tid; i < B200SEG_MAX_CLASSES * ECTA_WORDS; i += ECTA_TPB) (&S.mask[0][0])[i] = 0;
+        __syncthreads();
+        const size_t chunk_slot0 = (size_t)g * CT * (size_t)G.src_cap + (size_t)r * G.run_stride;
+
+        for (long long gt = gt0; gt < gt1; ++gt) {
+            const int n = p.per_image ? g : (int)(gt / tpi);
+            const long long ti = p.per_image ? gt : gt - (long long)n * tpi;
+            const long long q0 = ti * ECTA_TILE + (long long)tid * 4;
+            const bool inb = q0 < p.HW;                    // plane % 4 == 0: a thread's 4 pixels are in or out together
+            const size_t px0 = (size_t)n * p.HW + q0;
+            // ---- decode: per pixel up to three recorded candidates (own class, c1, c2), rarely more ----------------------
+            u32 kfg[4], kc1[4], kc2[4], acc[4], cls[4];      // cls = label8 | c1 << 8 | c2 << 16
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { kfg[j] = 0; kc1[j] = 0; kc2[j] = 0; acc[j] = 0; cls[j] = LAB8_FILTERED; }
+            u32 extra = 0;                                 // pixels (bits 0..3) with candidates beyond the recorded ones
+            if (inb) {
+                const uint4 r4v = *reinterpret_cast<const uint4*>(p.rec4 + px0);
+                const u32 r4[4] = {r4v.x, r4v.y, r4v.z, r4v.w};
+                uint4 rec[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rec[j] = p.rec16[px0 + j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const u32 l8 = r4[j] & 255u, c1 = (r4[j] >> 8) & 31u, c2 = (r4[j] >> 16) & 31u;
+                    cls[j] = r4[j] & 0x00FFFFFFu;
+                    const float p1 = __uint_as_float(rec[j].y), p2 = __uint_as_float(rec[j].z);
+                    kfg[j] = rec[j].x; kc1[j] = err_key(p1); kc2[j] = err_key(p2);
+                    if (l8 != LAB8_FILTERED) {
+                        u32 a = 0;
+                        if (l8 < (u32)CT && thr_active(S.thr[l8 & 31u])) a |= 1u << l8;
+                        if (p1 >= S.thr[c1]) a |= 1u << c1;
+                        if (p2 >= S.thr[c2]) a |= 1u << c2;
+                        if (__uint_as_float(rec[j].w) >= tmin) {          // rare: scan the other classes (a real call)
+                            const u32 skip = (l8 < (u32)CT ? 1u << l8 : 0u) | (1u << c1) | (1u << c2);
+                            const u32 more = emit_scan_pixel(p.logits + (size_t)n * CT * p.HW + q0 + j, p.HW, CT,
+                                                             p.pix_m[px0 + j], p.pix_s[px0 + j], S.thr, skip);
+                            if (more) { a |= more; extra |= 1u << j; }
+                        }
+                        acc[j] = a;
+                    }
+                }
+                uint4 cm4;
+                {
+                    u32 cmv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const u32 l8 = cls[j] & 255u;
+                        cmv[j] = l8 < (u32)CT ? (acc[j] & ~(1u << l8)) : acc[j];
+                    }
+                    cm4 = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
+                }
+                *reinterpret_cast<uint4*>(p.cmask + px0) = cm4;
+                // one shared-memory OR per class the thread's pixels touch
+                u32 uni = acc[0] | acc[1] | acc[2] | acc[3];
+                while (uni) {
+                    const int c = __ffs(uni) - 1;
+                    uni &= uni - 1;
+                    const u32 nib = ((acc[0] >> c) & 1u) | (((acc[1] >> c) & 1u) << 1) | (((acc[2] >> c) & 1u) << 2) |
+                                    (((acc[3] >> c) & 1u) << 3);
+                    atomicOr(&S.mask[c][word], nib << shift);
+                }
+            }
+            __syncthreads();
+            // ---- ranks: exclusive popcount prefix over the 32 words of every class --------------------------------------
+            for (int c = warp; c < CT; c += NW) {
+                const u32 cnt = __popc(S.mask[c][lane]);
+                u32 v = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
+                S.wpre[c][lane] = v - cnt;
+                if (lane == 31) S.tot[c] = v;
+            }
+            __syncthreads();
+            // ---- passes over class ranges whose candidates fit the stage (one pass unless > ECTA_CAP candidates) ---------
+            int lo = 0;
+            while (lo < CT) {
+                int hi = lo;
+                u32 sum = 0;
+                while (hi < CT && sum + S.tot[hi] <= ECTA_CAP) { sum += S.tot[hi]; ++hi; }     // tot <= 1024: hi > lo
+                if (tid == 0) {
+                    u32 o = 0;
+                    for (int c = lo; c < hi; ++c) { S.coff[c] = o; o += S.tot[c]; }
+                }
+                __syncthreads();
+                if (inb) {
+                    const u32 below = (1u << shift) - 1u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const u32 l8 = cls[j] & 255u, c1 = (cls[j] >> 8) & 31u, c2 = (cls[j] >> 16) & 31u;
+                        const u32 v0 = (u32)(px0 + j) << 1;
+                        const u32 bj = below | ((1u << j) - 1u) << shift;    // earlier pixels of the word
+                        u32 a = acc[j];
+                        if (l8 < (u32)CT && ((a >> l8) & 1u)) {
+                            a &= ~(1u << l8);
+                            if ((int)l8 >= lo && (int)l8 < hi) {
+                                const u32 pos = S.coff[l8] + S.wpre[l8][word] + __popc(S.mask[l8][word] & bj);
+                                S.stageK[pos] = kfg[j]; S.stageV[pos] = v0 | 1u;
+                            }
+                        }
+                        if ((a >> c1) & 1u) {
+                            a &= ~(1u << c1);
+                            if ((int)c1 >= lo && (int)c1 < hi) {
+                                const u32 pos = S.coff[c1] + S.wpre[c1][word] + __popc(S.mask[c1][word] & bj);
+                                S.stageK[pos] = kc1[j]; S.stageV[pos] = v0;
+                            }
+                        }
+                        if ((a >> c2) & 1u) {
+                            a &= ~(1u << c2);
+                            if ((int)c2 >= lo && (int)c2 < hi) {
+                                const u32 pos = S.coff[c2] + S.wpre[c2][word] + __popc(S.mask[c2][word] & bj);
+                                S.stageK[pos] = kc2[j]; S.stageV[pos] = v0;
+                            }
+                        }
+                        if ((extra >> j) & 1u) {            // rare: classes found by the scan
+                            while (a) {
+                                const int c = __ffs(a) - 1;
+                                a &= a - 1;
+                                if (c < lo || c >= hi) continue;
+                                const float pr = sm_prob(__ldg(p.logits + ((size_t)n * CT + c) * p.HW + q0 + j),
+                                                         p.pix_m[px0 + j], p.pix_s[px0 + j]);
+                                const u32 pos = S.coff[c] + S.wpre[c][word] + __popc(S.mask[c][word] & bj);
+                                S.stageK[pos] = err_key(pr); S.stageV[pos] = v0;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- write out: a warp per class, multiples of 8 elements = whole sectors; leftovers -> carry ----------------
+                for (int c = lo + warp; c < hi; c += NW) {
+                    const u32 cc = S.carry_cnt[c], nt = S.tot[c], total = cc + nt, w = total & ~7u;
+                    const u32 co = S.coff[c], done = S.emitted[c];
+                    u32* kd = p.keysA + chunk_slot0 + (size_t)c * G.src_cap + done;
+                    u32* vd = p.valsA + chunk_slot0 + (size_t)c * G.src_cap + done;
+                    for (u32 e = lane; e < w; e += 32) {
+                        const bool fromc = e < cc;
+                        kd[e] = fromc ? S.carryK[c][e] : S.stageK[co + e - cc];
+                        vd[e] = fromc ? S.carryV[c][e] : S.stageV[co + e - cc];
+                    }
+                    // leftovers (< 8): lanes 0..7 read their element first, then all of them write the new carry
+                    const u32 e = w + lane;
+                    u32 lk = 0, lv = 0;
+                    if (lane < 8 && e < total) {
+                        const bool fromc = e < cc;
+                        lk = fromc ? S.carryK[c][e] : S.stageK[co + e - cc];
+                        lv = fromc ? S.carryV[c][e] : S.stageV[co + e - cc];
+                    }
+                    __syncwarp();
+                    if (lane < 8 && e < total) { S.carryK[c][lane] = lk; S.carryV[c][lane] = lv; }
+                    if (lane == 0) { S.carry_cnt[c] = total - w; S.emitted[c] = done + w; }
+                }
+                __syncthreads();
+                lo = hi;
+            }
+            // clear the bit matrix for the next tile
+            for (int i = tid; i < CT * ECTA_WORDS; i += ECTA_TPB) (&S.mask[0][0])[i] = 0;
+            __syncthreads();
+        }
+        // ---- chunk end: flush the carries, publish the run lengths --------------------------------------------------------
+        for (int c = warp; c < CT; c += NW) {
+            const u32 cc = S.carry_cnt[c], done = S.emitted[c];
+            if (lane < cc) {
+                p.keysA[chunk_slot0 + (size_t)c * G.src_cap + done + lane] = S.carryK[c][lane];
+                p.valsA[chunk_slot0 + (size_t)c * G.src_cap + done + lane] = S.carryV[c][lane];
+            }
+            if (lane == 0) p.run_cnt[(size_t)chunk * CT + c] = done + cc;
+        }
+    }
+}
+
 // per segment: exclusive prefix of the chunk counts (the sort's run prefix) and the segment's candidate count
 __global__ void __launch_bounds__(256) run_scan_kernel(LovaszParams p) {
     const int lane = threadIdx.x & 31;
     const int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (seg >= p.n_seg) return;
     const int g = seg / p.C, c = seg - g * p.C;
-    u32* out = p.run_prefix + (size_t)seg * (p.n_runs + 1);
+    const int n_runs = p.geo->n_runs;
+    u32* out = p.run_prefix + (size_t)seg * (n_runs + 1);
     u32 carry = 0;
-    for (int base = 0; base < p.n_runs; base += 1024) {                 // 32 independent loads per lane, then the scans
+    for (int base = 0; base < n_runs; base += 1024) {                 // 32 independent loads per lane, then the scans
         u32 x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const int r = base + i * 32 + lane;
-            x[i] = r < p.n_runs ? p.run_cnt[((size_t)g * p.n_runs + r) * p.C + c] : 0;
+            x[i] = r < n_runs ? p.run_cnt[((size_t)g * n_runs + r) * p.C + c] : 0;
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -672,11 +1181,11 @@ __global__ void __launch_bounds__(256) run_scan_kernel(LovaszParams p) {
             u32 v = x[i];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
-            if (r < p.n_runs) out[r] = carry + v - x[i];
+            if (r < n_runs) out[r] = carry + v - x[i];
             carry += __shfl_sync(FULL_MASK, v, 31);
         }
     }
-    if (lane == 0) { out[p.n_runs] = carry; p.seg_count[seg] = carry; }
+    if (lane == 0) { out[n_runs] = carry; p.seg_count[seg] = carry; }
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -892,137 +1401,151 @@ __global__ void __launch_bounds__(BWD_TPB) backward_kernel_v4(LovaszParams p, co
     }
 }
 
-// Pipelined backward (the fast path): lane l of a warp owns pixels [l*VEC, l*VEC+VEC) of the warp tile.
-template <int CT, int VEC, int TPB, int STAGES, typename LT>
-__global__ void __launch_bounds__(TPB, (VEC == 1 && TPB == 128) ? 8 : 1) backward_kernel_async(LovaszParams p, const float* __restrict__ go,
-                                                              float* __restrict__ dlogits) {
-    using W = WarpTile<CT, VEC>;
-    constexpr int WT = W::WT, NW = TPB / 32;
+// Pipelined backward (the fast path): lane l of a warp owns pixel l of a 32-pixel warp tile.  Everything a tile needs
+// arrives through the warp-private cp.async ring one tile ahead of the math -- the C logit rows, the per-pixel state
+// (softmax max / denominator, own-class gradient, compact label), the first two background-candidate gradients
+// (addressed through the candidate mask, which therefore travels two tiles ahead) -- and completion is tracked with
+// cp.async groups, so no global-load scoreboard sits on the critical path.
+template <int CT>
+struct BwdStage {
+    float z[CT][32];
+    float m[32], s[32], gl[32];
+    u32 maskn[32];                                        // candidate mask of the tile AFTER this one
+    float g1[32], g2[32];
+    unsigned char lab8[32];
+};
+template <int CT, int TPB>
+__global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, const float* __restrict__ go,
+                                                             float* __restrict__ dlogits) {
+    using W = WarpTile<CT, 1>;
+    using Stage = BwdStage<CT>;
+    constexpr int WT = W::WT, NW = TPB / 32, STAGES = 2;
+    static_assert(sizeof(Stage) % 16 == 0, "stage alignment");
     extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
-    float (*Zall)[STAGES][CT][WT] = reinterpret_cast<float (*)[STAGES][CT][WT]>(pipe_smem_raw);   // [NW][STAGES][CT][WT]
-    __shared__ float s_thr[NW][B200SEG_MAX_CLASSES], s_logthr[NW][B200SEG_MAX_CLASSES];
+    __shared__ float s_thr[NW][B200SEG_MAX_CLASSES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float (*Z)[CT][WT] = Zall[warp];
-    const int l0 = lane * VEC;
+    Stage* S = reinterpret_cast<Stage*>(pipe_smem_raw) + (size_t)warp * STAGES;
     const u32 wtpi = (u32)((p.HW + WT - 1) / WT);         // tile counts fit 32 bits: keep the index math off the 64-bit divider
     const u32 nwt = wtpi * (u32)p.N;
     const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
     const u32 t0 = (u32)((u64)nwt * gw / nwarps), t1 = (u32)((u64)nwt * (gw + 1) / nwarps);
+    if (t0 >= t1) return;
     const float gsc = __ldg(go);
+    const size_t plane = (size_t)p.HW;
 
     // (image, tile-in-image) cursors advance by increments: no integer division per tile
     u32 cn = t0 / wtpi, cti = t0 - cn * wtpi;             // tile being consumed
-    u32 pn = cn, pti = cti, pt = t0;                       // next tile to prefetch
-    auto prefetch_next = [&](int stage) {
-        if (pt < t1) W::prefetch(Z[stage], p.logits, (int)pn, (long long)pti * WT, p.HW, lane);
+    u32 n1 = cn, ti1 = cti, pt1 = t0;                      // next tile whose state / logits are requested
+    u32 n2 = cn, ti2 = cti + 1, pt2 = t0 + 1;              // next tile whose candidate mask is requested
+    if (ti2 == wtpi) { ti2 = 0; ++n2; }
+    const int sub = lane & 7, strm = lane >> 3;            // 16-byte chunk / stream of the combined state copy
+    // request tile pt1 (its mask is `mask1`) into stage `st`, and the mask of tile pt2 = pt1 + 1 along with it
+    auto request = [&](Stage& st, u32 mask1) {
+        if (pt1 < t1) {
+            const long long q0 = (long long)ti1 * WT;
+            W::prefetch(st.z, p.logits, (int)n1, q0, p.HW, lane);
+            const size_t px0 = (size_t)n1 * plane + q0;
+            if (strm < 3) {
+                if (q0 + 4 * sub < p.HW) {
+                    const float* src = strm == 0 ? p.pix_m : (strm == 1 ? p.pix_s : p.gown);
+                    float* dst = strm == 0 ? st.m : (strm == 1 ? st.s : st.gl);
+                    cp_async<16>(dst + 4 * sub, src + px0 + 4 * sub);
+                }
+            } else if (pt2 < t1) {
+                const long long q2 = (long long)ti2 * WT + 4 * sub;
+                if (q2 < p.HW) cp_async<16>(st.maskn + 4 * sub, p.cmask + (size_t)n2 * plane + q2);
+            }
+            if (lane < 2 && q0 + 16 * lane < p.HW) cp_async<16>(st.lab8 + 16 * lane, p.lab8 + px0 + 16 * lane);
+            if (mask1 && q0 + lane < p.HW) {
+                const float* gb = p.gbg + (size_t)n1 * CT * plane + q0 + lane;
+                cp_async<4>(st.g1 + lane, gb + (size_t)(__ffs(mask1) - 1) * plane);
+                const u32 rest = mask1 & (mask1 - 1);
+                if (rest) cp_async<4>(st.g2 + lane, gb + (size_t)(__ffs(rest) - 1) * plane);
+            }
+        }
         cp_async_commit();
-        ++pt;
-        if (++pti == wtpi) { pti = 0; ++pn; }
+        ++pt1; ++pt2;
+        if (++ti1 == wtpi) { ti1 = 0; ++n1; }
+        if (++ti2 == wtpi) { ti2 = 0; ++n2; }
     };
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) prefetch_next(s);
+    u32 mask = 0;                                          // candidate mask of the tile being consumed
+    {
+        const long long q = (long long)cti * WT + lane;
+        if (q < p.HW) mask = p.cmask[(size_t)cn * plane + q];
+    }
+    request(S[0], mask);
 
     int cur_g = -1;
     u32 it = 0;
     for (u32 t = t0; t < t1; ++t, ++it) {
-        const int stage = (int)(it % STAGES);
-        __syncwarp();                                     // every lane is done reading the stage about to be refilled
-        prefetch_next((int)((it + STAGES - 1) % STAGES));
+        Stage& C = S[it & 1];
+        cp_async_wait<0>();                               // this lane's copies for tile t have landed ...
+        __syncwarp();                                     // ... so have the other lanes', and nobody still reads the other stage
+        const u32 nmask = (t + 1 < t1) ? C.maskn[lane] : 0u;
+        request(S[(it & 1) ^ 1], nmask);
         const int n = (int)cn;
-        const long long q = (long long)cti * WT + l0;
+        const long long q = (long long)cti * WT + lane;
         if (++cti == wtpi) { cti = 0; ++cn; }
         const int g = p.per_image ? n : 0;
         if (g != cur_g) {
-            if (lane < CT) { s_thr[warp][lane] = p.seg_thr[(size_t)g * CT + lane]; s_logthr[warp][lane] = p.seg_logthr[(size_t)g * CT + lane]; }
+            __syncwarp();
+            if (lane < CT) s_thr[warp][lane] = p.seg_thr[(size_t)g * CT + lane];
             cur_g = g;
             __syncwarp();
         }
-        const bool inb = q < p.HW;
-        // per-pixel state straight from global memory (issued before the wait so it overlaps)
-        float m[VEC], s[VEC], gl[VEC];
-        int lab[VEC];
-        const size_t px = (size_t)n * p.HW + q;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { m[j] = 0.f; s[j] = 1.f; gl[j] = 0.f; lab[j] = -1; }
-        if (inb) {
-            if constexpr (VEC == 4) {
-                const float4 mv = *(const float4*)(p.pix_m + px), sv = *(const float4*)(p.pix_s + px), gv = *(const float4*)(p.gown + px);
-                m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
-                s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
-                gl[0] = gv.x; gl[1] = gv.y; gl[2] = gv.z; gl[3] = gv.w;
-                load_labels4<LT>(p.labels, px, lab);
-            } else {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    m[j] = p.pix_m[px + j]; s[j] = p.pix_s[px + j]; gl[j] = p.gown[px + j];
-                    lab[j] = load_label<LT>(p.labels, px + j);
-                }
-            }
-        }
-        cp_async_wait<STAGES - 1>();                      // this lane's copies for tile t have landed ...
-        __syncwarp();                                     // ... and so have the other lanes'
-        if (!inb) continue;
-        const float (*T)[WT] = Z[stage];
-        const size_t off = (size_t)n * CT * p.HW + q;
+        const u32 cmask_cur = mask;
+        mask = nmask;
+        if (q >= p.HW) continue;
+        const float (*T)[WT] = C.z;
+        const float m = C.m[lane], s = C.s[lane], gl = C.gl[lane];
+        const u32 l8 = C.lab8[lane];
+        const size_t off = (size_t)n * CT * plane + q;
         const float* gb = p.gbg + off;
         float* dp = dlogits + off;
-        const float* thr = s_thr[warp];
-        float theta[VEC];
-        u32 pre[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { theta[j] = pre_theta(m[j], s[j]); pre[j] = 0; }
-        // sweep 1 (branch-free): conservative candidate bits
-#pragma unroll
-        for (int c = 0; c < CT; ++c) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) pre[j] |= (T[c][l0 + j] >= theta[j] + s_logthr[warp][c]) ? (1u << c) : 0u;
-        }
-        // exact stage on the flagged classes: same predicate as the emission kernel
-        float dot[VEC], nd[VEC], ownv[VEC];
-        u32 fix[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const bool filt = p.has_filter && lab[j] == p.filter;
-            const bool own = !filt && (unsigned)lab[j] < (unsigned)CT && thr_active(thr[lab[j] & 31]);
-            const u32 ownbit = (unsigned)lab[j] < (unsigned)CT ? (1u << lab[j]) : 0u;
-            float d = 0.f;
-            u32 cm = 0;
-            u32 mm = filt ? 0u : (pre[j] & ~ownbit);
+        const bool filt = l8 == LAB8_FILTERED;
+        int lab = l8 < (u32)CT ? (int)l8 : -1;
+        if (lab >= 0 && !thr_active(s_thr[warp][lab])) lab = -1;   // class not summed: no own-class term
+        // dot = sum_j g_j p_j over the pixel's candidates (background candidates ascending, then the own class)
+        float d = 0.f, pk1 = 0.f, pk2 = 0.f, g1 = 0.f, g2 = 0.f;
+        if (cmask_cur) {
+            g1 = C.g1[lane]; g2 = C.g2[lane];
+            u32 mm = cmask_cur;
+            int i = 0;
             while (mm) {
                 const int c = __ffs(mm) - 1;
                 mm &= mm - 1;
-                const float pr = sm_prob(T[c][l0 + j], m[j], s[j]);
-                if (pr >= thr[c]) { cm |= 1u << c; d += gb[(size_t)c * p.HW + j] * pr; }
+                const float pr = sm_prob(T[c][lane], m, s);
+                float gk;
+                if (i == 0) { gk = g1; pk1 = pr; } else if (i == 1) { gk = g2; pk2 = pr; } else gk = gb[(size_t)c * plane];
+                d += gk * pr;
+                ++i;
             }
-            float pown = 0.f;
-            if (own) { pown = sm_prob(T[lab[j]][l0 + j], m[j], s[j]); d += gl[j] * pown; }
-            else lab[j] = -1;                              // no class of this pixel takes the own-class path below
-            dot[j] = d; fix[j] = cm;
-            nd[j] = filt ? 0.f : -gsc * d * __fdiv_rn(1.0f, s[j]);
-            ownv[j] = gsc * pown * (gl[j] - d);            // exact value of the own class
         }
-        // sweep 2 (branch-free): -go * p_k * dot with the fast exponential, the own class takes its exact value ...
+        float ownv = 0.f;
+        if (lab >= 0) {
+            const float pown = sm_prob(T[lab][lane], m, s);
+            d += gl * pown;
+            ownv = gsc * pown * (gl - d);                  // exact value of the own class
+        }
+        const float nd = filt ? 0.f : -gsc * d * __fdiv_rn(1.0f, s);
+        // every class gets -go * p_k * dot with the fast exponential, the own class takes its exact value ...
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
-            float o[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const float fast = nd[j] * __expf(T[c][l0 + j] - m[j]);
-                o[j] = (c == lab[j]) ? ownv[j] : fast;
-            }
-            if constexpr (VEC == 4) st_stream4(dp + (size_t)c * p.HW, make_float4(o[0], o[1], o[2], o[3]));
-            else if constexpr (VEC == 2) st_stream2(dp + (size_t)c * p.HW, make_float2(o[0], o[1]));
-            else dp[(size_t)c * p.HW] = o[0];
+            const float fast = nd * __expf(T[c][lane] - m);
+            dp[(size_t)c * plane] = (c == lab) ? ownv : fast;
         }
         // ... then the (few) background-candidate classes are overwritten with the exact go * p_k * (g_k - dot)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            u32 mm = fix[j];
+        if (cmask_cur) {
+            u32 mm = cmask_cur;
+            int i = 0;
             while (mm) {
                 const int c = __ffs(mm) - 1;
                 mm &= mm - 1;
-                const float pk = sm_prob(T[c][l0 + j], m[j], s[j]);
-                dp[(size_t)c * p.HW + j] = gsc * pk * (gb[(size_t)c * p.HW + j] - dot[j]);
+                float gk, pk;
+                if (i == 0) { gk = g1; pk = pk1; } else if (i == 1) { gk = g2; pk = pk2; }
+                else { gk = gb[(size_t)c * plane]; pk = sm_prob(T[c][lane], m, s); }
+                dp[(size_t)c * plane] = gsc * pk * (gk - d);
+                ++i;
             }
         }
     }
@@ -1118,9 +1641,14 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.seg_count = (u32*)(ws + L.seg_count); p.grp_valid = (u32*)(ws + L.grp_valid); p.seg_bits = (u32*)(ws + L.seg_bits);
     p.seg_loss = (double*)(ws + L.seg_loss);
     p.seg_thr = (float*)(ws + L.seg_thr); p.seg_logthr = (float*)(ws + L.seg_logthr); p.seg_w = (float*)(ws + L.seg_w);
+    p.grp_tmin = (float*)(ws + L.grp_tmin); p.have_records = 0; p.emit_force = 0;
     p.pix_m = (float*)(ws + L.pix_m); p.pix_s = (float*)(ws + L.pix_s); p.gown = (float*)(ws + L.gown);
+    p.lab8 = (unsigned char*)(ws + L.lab8); p.cmask = (u32*)(ws + L.cmask);
+    p.rec16 = (uint4*)(ws + L.rec16); p.rec4 = (u32*)(ws + L.rec4);
+    p.flags = p.ctrl + CTRL_FLAGS;
+    p.geo = reinterpret_cast<EmitGeomDev*>(p.ctrl + CTRL_GEO);
     p.run_cnt = (u32*)(ws + L.run_cnt); p.run_prefix = (u32*)(ws + L.run_prefix);
-    p.n_runs = 0; p.tiles_per_chunk = 0; p.run_stride = 0; p.src_cap = 0;
+    p.geo_stream = EmitGeomDev{0, 0, 0, 0}; p.geo_rec = EmitGeomDev{0, 0, 0, 0};
     p.keysA = (u32*)(ws + L.keysA); p.valsA = (u32*)(ws + L.valsA);
     p.keysB = (u32*)(ws + L.keysB); p.valsB = (u32*)(ws + L.valsB);
     p.gbg = (float*)(ws + L.keysA);      // free again once the sort result sits in buffer B
@@ -1178,6 +1706,8 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     fill_params(p, L, ws, logits, labels, n, c, hw, per_image, filter_label, keep_absent, class_mask);
     p.loss_out = loss_out;
     p.need_grad = need_grad ? 1 : 0;
+    static const int dbg = getenv("B200SEG_DBG") ? atoi(getenv("B200SEG_DBG")) : 0;   // timing experiments only
+    p.dbg = dbg;
     p.cm = (unsigned long long*)cm;
     p.has_drop = (cm_drop_label != B200SEG_NO_LABEL && cm_drop_label >= INT_MIN && cm_drop_label <= INT_MAX) ? 1 : 0;
     p.drop = p.has_drop ? (int)cm_drop_label : 0;
@@ -1189,7 +1719,39 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     b200seg_stage(0, st);
 
     // K1
-    if (v4 && (c == 8 || c == 17 || c == 25)) {
+    const bool known_c = (c == 8 || c == 17 || c == 25);
+    static const int stats_variant = getenv("B200SEG_STATS_VARIANT") ? atoi(getenv("B200SEG_STATS_VARIANT")) : 0;
+    static const int emit_force = getenv("B200SEG_EMIT_PATH") ? atoi(getenv("B200SEG_EMIT_PATH")) : 0;
+    const bool async_ok = v4 && known_c && hw % 16 == 0 && aligned16(labels);
+    if (async_ok && stats_variant != 1) {
+        p.have_records = 1;
+        p.emit_force = emit_force;
+#define LAUNCH_STATS_ASYNC(CC, TT, SS)                                                                          \
+    {                                                                                                           \
+        const size_t smem = (size_t)(TT / 32) * SS * (CC * 32 * 4 + 256);                                       \
+        CUDA_TRY(cudaFuncSetAttribute(stats_kernel_async<CC, TT, SS, LT>,                                       \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        int per_sm = (int)((224 * 1024) / (smem + 6 * 1024));                                                   \
+        if (per_sm < 1) per_sm = 1;                                                                             \
+        if (per_sm * TT > 2048) per_sm = 2048 / TT;                                                             \
+        stats_kernel_async<CC, TT, SS, LT><<<sms * per_sm, TT, smem, st>>>(p);                                  \
+    }
+#define LAUNCH_STATS_C(TT, SS)                                         \
+    {                                                                  \
+        if (c == 8) LAUNCH_STATS_ASYNC(8, TT, SS)                      \
+        else if (c == 17) LAUNCH_STATS_ASYNC(17, TT, SS)               \
+        else LAUNCH_STATS_ASYNC(25, TT, SS)                            \
+    }
+        DISPATCH_LABEL(label_dtype, {
+            switch (stats_variant) {
+                case 2: LAUNCH_STATS_C(128, 2) break;
+                case 3: LAUNCH_STATS_C(128, 4) break;
+                default: LAUNCH_STATS_C(128, 3) break;
+            }
+        });
+#undef LAUNCH_STATS_C
+#undef LAUNCH_STATS_ASYNC
+    } else if (v4 && known_c) {
         const int grid = sms * 3;
         DISPATCH_LABEL(label_dtype, {
             if (c == 8) stats_kernel_vec<8, 4, STATS_TPB, LT><<<grid, STATS_TPB, 0, st>>>(p);
@@ -1205,34 +1767,48 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
         DISPATCH_LABEL(label_dtype, absent_max_kernel<LT><<<dim3(p.n_seg, 32), 256, 0, st>>>(p));
         LAUNCH_CHECK("absent_max_kernel");
     }
+    // emission geometries (the kernels read the one in force from device memory: the path is chosen on the device)
+    const bool pipe_ok = v4 && known_c;
+    const EmitGeom Gs = emit_geom(n, hw, per_image, pipe_ok ? EMIT_WARP_TILE : (long long)EMIT_TPB * (v4 ? 4 : 1));
+    const EmitGeom Gr = emit_geom(n, hw, per_image, ECTA_TILE);
+    p.geo_stream = EmitGeomDev{(int)Gs.n_runs, (int)Gs.tpc, Gs.run_stride, Gs.src_cap};
+    p.geo_rec = EmitGeomDev{(int)Gr.n_runs, (int)Gr.tpc, Gr.run_stride, Gr.src_cap};
     finalize_stats_kernel<<<(p.groups + 127) / 128, 128, 0, st>>>(p);
     LAUNCH_CHECK("finalize_stats_kernel");
+    if (p.have_records) {
+        emit_decide_kernel<<<DECIDE_BLOCKS, DECIDE_TPB, 0, st>>>(p);
+        LAUNCH_CHECK("emit_decide_kernel");
+    }
     b200seg_stage(2, st);
 
     // K2
     {
-        const bool pipe_ok = v4 && (c == 8 || c == 17 || c == 25);
-        const EmitGeom G = emit_geom(n, hw, per_image, pipe_ok ? EMIT_WARP_TILE : (long long)EMIT_TPB * (v4 ? 4 : 1));
-        p.n_runs = (int)G.n_runs; p.tiles_per_chunk = (int)G.tpc; p.run_stride = G.run_stride; p.src_cap = G.src_cap;
-        const long long chunks = (long long)p.groups * G.n_runs;
+        const long long chunks = (long long)p.groups * Gs.n_runs;
+        if (p.have_records) {                              // record path (no-op unless K1d selected it)
+            const long long rchunks = (long long)p.groups * Gr.n_runs;
+            const int grid = (int)(rchunks < (long long)sms * 4 ? rchunks : (long long)sms * 4);
+            const size_t smem = sizeof(EctaSmem);
+            if (c == 8) emit_kernel_cta<8><<<grid, ECTA_TPB, smem, st>>>(p);
+            else if (c == 17) emit_kernel_cta<17><<<grid, ECTA_TPB, smem, st>>>(p);
+            else emit_kernel_cta<25><<<grid, ECTA_TPB, smem, st>>>(p);
+            LAUNCH_CHECK("emit_kernel_cta");
+        }
         if (pipe_ok) {
 #define LAUNCH_EMIT_ASYNC(CC)                                                                                   \
     {                                                                                                           \
         constexpr int ET = 128, ES = 2;                                                                         \
         const size_t smem = sizeof(float) * (size_t)ES * CC * ET;                                               \
-        CUDA_TRY(cudaFuncSetAttribute(emit_kernel_async<CC, ET, ES, LT>,                                        \
+        CUDA_TRY(cudaFuncSetAttribute(emit_kernel_async<CC, ET>,                                                \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
         int per_sm = (int)((224 * 1024) / (smem + 2048));                                                       \
         if (per_sm * ET > 2048) per_sm = 2048 / ET;                                                             \
         long long grid = (long long)sms * per_sm;                                                               \
         if (grid * (ET / 32) > chunks) grid = (chunks + ET / 32 - 1) / (ET / 32);                               \
-        emit_kernel_async<CC, ET, ES, LT><<<(int)grid, ET, smem, st>>>(p);                                      \
+        emit_kernel_async<CC, ET><<<(int)grid, ET, smem, st>>>(p);                                              \
     }
-            DISPATCH_LABEL(label_dtype, {
-                if (c == 8) LAUNCH_EMIT_ASYNC(8)
-                else if (c == 17) LAUNCH_EMIT_ASYNC(17)
-                else LAUNCH_EMIT_ASYNC(25)
-            });
+            if (c == 8) LAUNCH_EMIT_ASYNC(8)
+            else if (c == 17) LAUNCH_EMIT_ASYNC(17)
+            else LAUNCH_EMIT_ASYNC(25)
 #undef LAUNCH_EMIT_ASYNC
         } else {
             const int grid = (int)(chunks < (long long)sms * 8 ? chunks : (long long)sms * 8);
@@ -1250,8 +1826,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     char* ss = ws + L.sort_scratch;
     a.keys[0] = p.keysA; a.vals[0] = p.valsA; a.keys[1] = p.keysB; a.vals[1] = p.valsB;
     a.seg_count = p.seg_count; a.seg_bits = p.seg_bits; a.n_seg = p.n_seg; a.cap = p.cap;
-    a.src_keys = p.keysA; a.src_vals = p.valsA; a.run_prefix = p.run_prefix; a.n_runs = p.n_runs;
-    a.run_stride = p.run_stride; a.src_cap = p.src_cap;
+    a.src_keys = p.keysA; a.src_vals = p.valsA; a.run_prefix = p.run_prefix; a.geo = p.geo;
     a.tile_start = (u32*)(ss + L.sort.tile_start); a.tilehist = (u32*)(ss + L.sort.tilehist);
     a.tile_desc = (uint4*)(ss + L.sort.tile_desc); a.tile_runs = (uint2*)(ss + L.sort.tile_runs);
     a.seg_done = (u32*)(ss + L.sort.seg_done);
@@ -1290,40 +1865,22 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
     if (p.P == 0) return 0;
     const int sms = b200seg_sm_count();
     const bool v4 = vec4_ok(logits, labels, label_dtype, hw) && aligned16(dlogits);
-    const bool pipe_ok = v4 && (label_dtype != B200SEG_LABEL_U8 || hw % 16 == 0) && aligned16(labels) &&
-                         (c == 8 || c == 17 || c == 25);
+    const bool pipe_ok = v4 && hw % 16 == 0 && (c == 8 || c == 17 || c == 25);
     b200seg_stage(9, st);
     if (pipe_ok) {
-        const char* e = getenv("B200SEG_BWD_VARIANT");
-        const int variant = e ? atoi(e) : 0;
-#define LAUNCH_BWD_ASYNC(CC, VV, TT, SS)                                                                         \
+#define LAUNCH_BWD_ASYNC(CC, TT)                                                                                 \
     {                                                                                                            \
-        const size_t smem = sizeof(float) * (size_t)SS * CC * TT * VV;                                           \
-        CUDA_TRY(cudaFuncSetAttribute(backward_kernel_async<CC, VV, TT, SS, LT>,                                 \
+        const size_t smem = (size_t)2 * (TT / 32) * sizeof(BwdStage<CC>);                                        \
+        CUDA_TRY(cudaFuncSetAttribute(backward_kernel_async<CC, TT>,                                             \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
         int per_sm = (int)((224 * 1024) / (smem + 2048));                                                        \
         if (per_sm < 1) per_sm = 1;                                                                              \
         if (per_sm * TT > 2048) per_sm = 2048 / TT;                                                              \
-        backward_kernel_async<CC, VV, TT, SS, LT><<<sms * per_sm, TT, smem, st>>>(p, grad_out, dlogits);         \
+        backward_kernel_async<CC, TT><<<sms * per_sm, TT, smem, st>>>(p, grad_out, dlogits);                     \
     }
-#define LAUNCH_BWD_C(VV, TT, SS)                                       \
-    {                                                                  \
-        if (c == 8) LAUNCH_BWD_ASYNC(8, VV, TT, SS)                    \
-        else if (c == 17) LAUNCH_BWD_ASYNC(17, VV, TT, SS)             \
-        else LAUNCH_BWD_ASYNC(25, VV, TT, SS)                          \
-    }
-        DISPATCH_LABEL(label_dtype, {
-            switch (variant) {
-                case 1: LAUNCH_BWD_C(1, 128, 4) break;
-                case 2: LAUNCH_BWD_C(2, 128, 2) break;
-                case 3: LAUNCH_BWD_C(2, 128, 3) break;
-                case 4: LAUNCH_BWD_C(1, 256, 3) break;
-                case 5: LAUNCH_BWD_C(1, 128, 2) break;
-                case 6: LAUNCH_BWD_C(4, 128, 2) break;
-                default: LAUNCH_BWD_C(1, 128, 2) break;
-            }
-        });
-#undef LAUNCH_BWD_C
+        if (c == 8) LAUNCH_BWD_ASYNC(8, 128)
+        else if (c == 17) LAUNCH_BWD_ASYNC(17, 128)
+        else LAUNCH_BWD_ASYNC(25, 128)
 #undef LAUNCH_BWD_ASYNC
     } else if (v4 && (c == 8 || c == 17 || c == 25)) {
         const int grid = sms * 3 * 4;
@@ -1337,6 +1894,16 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
     }
     LAUNCH_CHECK("backward_kernel");
     b200seg_stage(10, st);
+    return 0;
+}
+
+// ---- test hook: byte offsets of a few workspace regions (tests inspect the per-pixel records) -----------------------
+extern "C" int b200seg_debug_layout(int32_t n, int32_t c, int64_t hw, int32_t per_image, size_t* offsets, int32_t n_offsets) {
+    if (!offsets || n_offsets < 8) { b200seg_set_error("need room for 8 offsets"); return B200SEG_E_INVALID; }
+    if (int rc = check_shape(n, c, hw)) return rc;
+    const LovaszLayout L = lovasz_layout(n, c, hw, per_image);
+    offsets[0] = L.pix_m; offsets[1] = L.pix_s; offsets[2] = L.lab8; offsets[3] = L.cmask;
+    offsets[4] = L.rec16; offsets[5] = L.rec4; offsets[6] = L.seg_thr; offsets[7] = L.grp_tmin;
     return 0;
 }
 
@@ -1369,7 +1936,7 @@ extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint3
     SortArgs a;
     a.keys[0] = keys_in; a.vals[0] = vals_in; a.keys[1] = keys_out; a.vals[1] = vals_out;
     a.seg_count = counts; a.seg_bits = key_bits; a.n_seg = n_segments; a.cap = capacity;
-    a.src_keys = nullptr; a.src_vals = nullptr; a.run_prefix = nullptr; a.n_runs = 0; a.run_stride = 0; a.src_cap = 0;
+    a.src_keys = nullptr; a.src_vals = nullptr; a.run_prefix = nullptr; a.geo = nullptr;
     a.tile_start = (u32*)(ss + L.tile_start); a.tilehist = (u32*)(ss + L.tilehist);
     a.tile_desc = (uint4*)(ss + L.tile_desc); a.tile_runs = (uint2*)(ss + L.tile_runs);
     a.seg_done = (u32*)(ss + L.seg_done);

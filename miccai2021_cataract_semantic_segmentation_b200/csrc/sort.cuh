@@ -37,8 +37,7 @@ struct SortArgs {
     const u32* src_keys;
     const u32* src_vals;
     const u32* run_prefix;  // [n_seg][n_runs + 1]
-    int n_runs;
-    long long run_stride, src_cap;
+    const EmitGeomDev* geo; // n_runs, run_stride, src_cap of the holey source (device memory)
     // scratch
     u32* tile_start;        // [n_seg + 1] exclusive prefix of tiles per segment
     uint4* tile_desc;       // [max_tiles] {segment, first element, element count, digit width}
@@ -136,8 +135,9 @@ __global__ void __launch_bounds__(256) sort_desc_kernel(SortArgs a) {
     const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
     a.tile_desc[t] = make_uint4((u32)seg, off, n, sort_digit_width(a.seg_bits[seg]));
     if (a.run_prefix) {
-        const u32* prefix = a.run_prefix + (size_t)seg * (a.n_runs + 1);
-        a.tile_runs[t] = make_uint2(upper_run(prefix, 0, a.n_runs - 1, off), upper_run(prefix, 0, a.n_runs - 1, off + n - 1));
+        const int n_runs = a.geo->n_runs;
+        const u32* prefix = a.run_prefix + (size_t)seg * (n_runs + 1);
+        a.tile_runs[t] = make_uint2(upper_run(prefix, 0, n_runs - 1, off), upper_run(prefix, 0, n_runs - 1, off + n - 1));
     }
 }
 
@@ -168,11 +168,12 @@ __device__ __forceinline__ TileSrc tile_src_setup(const SortArgs& a, int pass, u
         T.base = (size_t)seg * a.cap + off;
         return T;
     }
+    const EmitGeomDev G = *a.geo;
     T.keys = a.src_keys; T.vals = a.src_vals;
-    T.prefix = a.run_prefix + (size_t)seg * (a.n_runs + 1);
+    T.prefix = a.run_prefix + (size_t)seg * (G.n_runs + 1);
     T.voff = off;
-    T.seg_base = (size_t)seg * a.src_cap;
-    T.run_stride = a.run_stride;
+    T.seg_base = (size_t)seg * G.src_cap;
+    T.run_stride = G.run_stride;
     const uint2 rr = a.tile_runs[t];
     T.r_lo = rr.x; T.r_hi = rr.y;
     T.window = (T.r_hi - T.r_lo + 2) <= SORT_RUN_WINDOW + 1;
