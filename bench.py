@@ -38,8 +38,9 @@ UNIT = "Mpixel/s"
 STAGES = ["stats(+fused confmat)", "finalize", "emit", "sort_plan", "sort_pass0", "sort_pass1", "sort_pass2",
           "jaccard+loss", None, "backward"]
 N_EV = len(STAGES) + 1
-# stats, finalize, emit, run_scan, sort plan + desc, 3 x (count, scatter), fg_count, jaccard, loss, backward, metrics
-KERNELS_PER_STEP = 17
+# stats, finalize+decide, emit (record path) + emit (streaming path, exits at once), sort prepare, 3 x (count, scatter),
+# fg_count, jaccard(+loss), backward, metrics
+KERNELS_PER_STEP = 15
 
 
 def parse():

@@ -158,11 +158,14 @@ __global__ void metrics_kernel(const long long* __restrict__ cm, int C, u32 miou
                                float* __restrict__ iou_out, float* __restrict__ summary) {
     __shared__ float s_iou[B200SEG_MAX_CLASSES], s_pac[B200SEG_MAX_CLASSES];
     __shared__ long long s_diag[B200SEG_MAX_CLASSES], s_row[B200SEG_MAX_CLASSES];
+    __shared__ long long s_cm[B200SEG_MAX_CLASSES * (B200SEG_MAX_CLASSES + 1)];     // rows padded: column reads conflict-free
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cm[(i / C) * (C + 1) + i % C] = cm[i];   // one coalesced sweep
+    __syncthreads();
     const int c = threadIdx.x;
     if (c < C) {
         long long row = 0, col = 0;                 // row: prediction totals (sum over dim 1); col: ground-truth totals
-        for (int k = 0; k < C; ++k) { row += cm[c * C + k]; col += cm[k * C + c]; }
-        const long long d = cm[c * C + c];
+        for (int k = 0; k < C; ++k) { row += s_cm[c * (C + 1) + k]; col += s_cm[k * (C + 1) + c]; }
+        const long long d = s_cm[c * (C + 1) + c];
         // utils/torch_utils.py:322-327: diag / (sum(dim=0) + sum(dim=1) - diag), NaN -> 0
         const float den = __fsub_rn(__fadd_rn((float)col, (float)row), (float)d);
         float iou = __fdiv_rn((float)d, den);
@@ -202,7 +205,7 @@ extern "C" int b200seg_metrics_from_confmat(const int64_t* cm, int32_t c, uint32
     MetricSets sets;
     sets.n = n_sets;
     for (int i = 0; i < MAX_SETS; ++i) sets.mask[i] = i < n_sets ? category_masks[i] : 0;
-    metrics_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const long long*)cm, c, miou_mask, sets, iou_out, summary_out);
+    metrics_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const long long*)cm, c, miou_mask, sets, iou_out, summary_out);
     LAUNCH_CHECK("metrics_kernel");
     return 0;
 }

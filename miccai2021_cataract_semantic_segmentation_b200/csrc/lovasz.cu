@@ -26,7 +26,7 @@
 #define BWD_TPB 128
 #define JAC_TPB SORT_TPB
 
-enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_GEO = 32 };
+enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_JTICKET = 27, CTRL_GEO = 32 };
 enum { EMIT_PATH_STREAM = 0, EMIT_PATH_RECORDS = 1 };
 
 struct LovaszParams {
@@ -43,6 +43,7 @@ struct LovaszParams {
     double* seg_loss;
     float *seg_thr, *seg_logthr, *seg_w;
     float* grp_tmin;                    // [groups] smallest threshold among the group's summed classes
+    unsigned char* seg_order;           // [groups][C] classes of the group by ascending threshold
     int have_records;                   // stats_kernel_async ran: rec16 / rec4 are valid
     int emit_force;                     // 0 = decide on the device, 1 = record path, 2 = streaming path (B200SEG_EMIT_PATH)
     float *pix_m, *pix_s, *gown, *gbg;
@@ -64,7 +65,7 @@ struct LovaszParams {
 
 struct LovaszLayout {
     size_t ctrl, seg_fg, seg_maxkey, seg_maxp, seg_count, grp_valid, seg_loss, zero_end;
-    size_t seg_thr, seg_logthr, seg_w, seg_bits, grp_tmin, run_cnt, run_prefix;
+    size_t seg_thr, seg_logthr, seg_w, seg_bits, grp_tmin, seg_order, run_cnt, run_prefix;
     size_t pix_m, pix_s, gown, lab8, cmask, rec16, rec4, keysA, valsA, keysB, valsB, sort_scratch, total;
     SortScratch sort;
 };
@@ -119,6 +120,7 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     L.seg_w = o;      o = align_up(o + 4 * S, 256);
     L.seg_bits = o;   o = align_up(o + 4 * S, 256);
     L.grp_tmin = o;   o = align_up(o + 4 * (size_t)groups, 256);
+    L.seg_order = o;  o = align_up(o + S, 256);
     L.run_cnt = o;    o = align_up(o + 4 * runs * C, 256);
     L.run_prefix = o; o = align_up(o + 4 * (runs + (size_t)groups) * C, 256);
     L.pix_m = o;      o = align_up(o + 4 * (size_t)P, 256);
@@ -544,69 +546,86 @@ __global__ void __launch_bounds__(256) absent_max_kernel(LovaszParams p) {
 // --------------------------------------------------------------------------------------------------------------
 // K1b: per-group finalisation of the segment table
 // --------------------------------------------------------------------------------------------------------------
-__global__ void finalize_stats_kernel(LovaszParams p) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g == 0) *p.geo = p.geo_stream;
-    if (g >= p.groups) return;
-    int nkept = 0;
-    float tmin = THR_INACTIVE;
-    const bool any_valid = p.grp_valid[g] > 0;
-    for (int c = 0; c < p.C; ++c) {
-        const size_t seg = (size_t)g * p.C + c;
-        const u32 fg = p.seg_fg[seg];
-        const bool active = ((p.class_mask >> c) & 1u) && any_valid && (fg > 0 || p.keep_absent);
-        float thr = THR_INACTIVE, logthr = __int_as_float(0x7f800000);
-        u32 bits = 1;
-        if (active) {
-            const u32 thr_bits = fg > 0 ? (ONE_BITS - p.seg_maxkey[seg]) : p.seg_maxp[seg];
-            thr = __uint_as_float(thr_bits);
-            logthr = thr > 0.f ? logf(thr) : __int_as_float(0xff800000);
-            const u32 maxkey = ONE_BITS - thr_bits;
-            bits = maxkey ? (32 - __clz(maxkey)) : 1;
-            tmin = fminf(tmin, thr);
-            ++nkept;
-        }
-        p.seg_thr[seg] = thr;
-        p.seg_logthr[seg] = logthr;
-        p.seg_bits[seg] = bits;
-    }
-    p.grp_tmin[g] = tmin;
-    // d(mean)/d(term): the reference's mean() divides only when it averaged more than one value
-    float w = 1.0f;
-    if (p.groups > 1) w = w / (float)p.groups;
-    if (nkept > 1) w = w / (float)nkept;
-    for (int c = 0; c < p.C; ++c) {
-        const size_t seg = (size_t)g * p.C + c;
-        p.seg_w[seg] = thr_active(p.seg_thr[seg]) ? w : 0.f;
-    }
-}
-
-// K1d: choose the emission path.  The record path is exact for any input but pays a gather per pixel whose guard
-// reaches the smallest threshold; a sample of the guards estimates how many there are (a performance heuristic only).
+// One kernel: a warp per group turns the counters of K1 into thresholds, key widths, class weights and the class order
+// (lane = class), then the block samples the guards of that group's records to choose the emission path.  The record
+// path is exact for any input but pays a gather per pixel whose guard reaches the smallest threshold; the sample
+// estimates how many there are (a performance heuristic only).  Flat mode (one group): every block repeats the tiny
+// per-class part for itself, block 0 publishes it, all blocks share the sampling.
 #define DECIDE_BLOCKS 32
 #define DECIDE_TPB 256
-__global__ void __launch_bounds__(DECIDE_TPB) emit_decide_kernel(LovaszParams p) {
+__global__ void __launch_bounds__(DECIDE_TPB) finalize_decide_kernel(LovaszParams p) {
+    __shared__ float s_tmin;
     __shared__ u32 s_slow, s_n;
-    if (threadIdx.x == 0) { s_slow = 0; s_n = 0; }
-    __syncthreads();
-    const long long target = 65536;
-    const long long stride = p.P > target ? p.P / target : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool flat = p.groups == 1;
+    if (blockIdx.x == 0 && tid == 0) *p.geo = p.geo_stream;       // default; the deciding block may override it
+    if (tid == 0) { s_slow = 0; s_n = 0; }
     u32 slow = 0, n = 0;
-    for (long long i = (long long)blockIdx.x * DECIDE_TPB + threadIdx.x; i * stride < p.P; i += (long long)DECIDE_BLOCKS * DECIDE_TPB) {
-        const long long px = i * stride;
-        const int g = p.per_image ? (int)(px / p.HW) : 0;
-        slow += __uint_as_float(p.rec16[px].w) >= p.grp_tmin[g];
-        ++n;
+    for (int g = flat ? 0 : blockIdx.x; g < p.groups; g += gridDim.x) {
+        __syncthreads();
+        if (warp == 0) {
+            const bool writer = !flat || blockIdx.x == 0;
+            const int c = lane;
+            const size_t seg = (size_t)g * p.C + c;
+            const bool any_valid = p.grp_valid[g] > 0;
+            bool active = false;
+            float thr = THR_INACTIVE, logthr = __int_as_float(0x7f800000);
+            u32 bits = 1;
+            if (c < p.C) {
+                const u32 fg = p.seg_fg[seg];
+                active = ((p.class_mask >> c) & 1u) && any_valid && (fg > 0 || p.keep_absent);
+                if (active) {
+                    const u32 thr_bits = fg > 0 ? (ONE_BITS - p.seg_maxkey[seg]) : p.seg_maxp[seg];
+                    thr = __uint_as_float(thr_bits);
+                    logthr = thr > 0.f ? logf(thr) : __int_as_float(0xff800000);
+                    const u32 maxkey = ONE_BITS - thr_bits;
+                    bits = maxkey ? (32 - __clz(maxkey)) : 1;
+                }
+            }
+            const int nkept = __popc(__ballot_sync(FULL_MASK, active));
+            float tmin = thr;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(FULL_MASK, tmin, o));
+            int rank = 0;                                  // position of class c in ascending (threshold, class) order
+            for (int j = 0; j < p.C; ++j) {
+                const float tj = __shfl_sync(FULL_MASK, thr, j);
+                rank += (tj < thr || (tj == thr && j < c)) ? 1 : 0;
+            }
+            // d(mean)/d(term): the reference's mean() divides only when it averaged more than one value
+            float w = 1.0f;
+            if (p.groups > 1) w = w / (float)p.groups;
+            if (nkept > 1) w = w / (float)nkept;
+            if (writer && c < p.C) {
+                p.seg_thr[seg] = thr; p.seg_logthr[seg] = logthr; p.seg_bits[seg] = bits;
+                p.seg_w[seg] = active ? w : 0.f;
+                p.seg_order[(size_t)g * p.C + rank] = (unsigned char)c;
+            }
+            if (lane == 0) { s_tmin = tmin; if (writer) p.grp_tmin[g] = tmin; }
+        }
+        __syncthreads();
+        if (p.have_records) {
+            const float tmin = s_tmin;
+            long long target = 65536 / p.groups;
+            if (target < 1024) target = 1024;
+            const long long stride = p.cap > target ? p.cap / target : 1;
+            const long long i0 = flat ? (long long)blockIdx.x * DECIDE_TPB + tid : tid;
+            const long long di = flat ? (long long)gridDim.x * DECIDE_TPB : DECIDE_TPB;
+            for (long long i = i0; i * stride < p.cap; i += di) {
+                slow += __uint_as_float(p.rec16[(size_t)g * p.cap + i * stride].w) >= tmin;
+                ++n;
+            }
+        }
     }
+    if (!p.have_records) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { slow += __shfl_xor_sync(FULL_MASK, slow, o); n += __shfl_xor_sync(FULL_MASK, n, o); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_slow, slow); atomicAdd(&s_n, n); }
+    if (lane == 0) { atomicAdd(&s_slow, slow); atomicAdd(&s_n, n); }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         atomicAdd(p.ctrl + CTRL_SLOW, s_slow);
         atomicAdd(p.ctrl + CTRL_SAMPLES, s_n);
         __threadfence();
-        if (atomicAdd(p.ctrl + CTRL_TICKET, 1u) == DECIDE_BLOCKS - 1) {
+        if (atomicAdd(p.ctrl + CTRL_TICKET, 1u) == gridDim.x - 1) {
             __threadfence();
             const u32 ts = ld_relaxed(p.ctrl + CTRL_SLOW), tn = ld_relaxed(p.ctrl + CTRL_SAMPLES);
             const bool rec = p.emit_force == 1 || (p.emit_force == 0 && (u64)ts * 32 <= tn);
@@ -929,20 +948,17 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
 // a scattered 4-byte store a whole LSU wavefront); the < 8 leftovers of each class are carried to the next tile.
 // Same slot layout (chunk-private runs), outputs and tie order as the streaming kernel.  Exits at once unless K1d
 // selected this path.
-// classes outside `skip` whose probability reaches their threshold, for one pixel (the rare path of the record kernel;
-// deliberately not inlined so that the common path carries neither its instructions nor its registers)
-__device__ __noinline__ u32 emit_scan_pixel(const float* lp, long long plane, int C, float m, float sden,
-                                            const float* thr, u32 skip) {
+// classes outside `skip` whose probability reaches their threshold, for one pixel whose unrecorded classes all have
+// p <= guard (the rare path of the record kernel; deliberately not inlined so that the common path carries neither its
+// instructions nor its registers).  `order` lists the classes by ascending threshold: only the leading ones with
+// threshold <= guard can qualify, typically a single class.
+__device__ __noinline__ u32 emit_scan_pixel(const float* lp, long long plane, int C, float m, float sden, float guard,
+                                            const float* thr, const unsigned char* order, u32 skip) {
     u32 more = 0;
-    for (int c0 = 0; c0 < C; c0 += 8) {                    // 8 independent loads in flight
-        float z[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = c0 + i < C ? __ldg(lp + (size_t)(c0 + i) * plane) : 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = c0 + i;
-            if (c < C && !((skip >> c) & 1u) && sm_prob(z[i], m, sden) >= thr[c]) more |= 1u << c;
-        }
+    for (int i = 0; i < C; ++i) {
+        const int c = order[i];
+        if (thr[c] > guard) break;
+        if (!((skip >> c) & 1u) && sm_prob(__ldg(lp + (size_t)c * plane), m, sden) >= thr[c]) more |= 1u << c;
     }
     return more;
 }
@@ -960,6 +976,8 @@ struct EctaSmem {
     u32 emitted[B200SEG_MAX_CLASSES];                     // elements of the chunk already written (multiple of 8)
     u32 carryK[B200SEG_MAX_CLASSES][8], carryV[B200SEG_MAX_CLASSES][8];
     float thr[B200SEG_MAX_CLASSES];
+    unsigned char order[B200SEG_MAX_CLASSES];             // classes by ascending threshold
+    u32 wcoff[ECTA_TPB / 32][B200SEG_MAX_CLASSES];        // per-warp copy of the stage offsets (single-pass tiles)
     u32 stageK[ECTA_CAP], stageV[ECTA_CAP];
 };
 
@@ -985,7 +1003,10 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
         const long long gt1 = min(gt0 + (long long)G.tiles_per_chunk, tpg);
         __syncthreads();                                   // previous chunk fully written out
         if (g != cur_g) {
-            if (tid < B200SEG_MAX_CLASSES) S.thr[tid] = tid < CT ? p.seg_thr[(size_t)g * CT + tid] : THR_INACTIVE;
+            if (tid < B200SEG_MAX_CLASSES) {
+                S.thr[tid] = tid < CT ? p.seg_thr[(size_t)g * CT + tid] : THR_INACTIVE;
+                S.order[tid] = tid < CT ? p.seg_order[(size_t)g * CT + tid] : 0;
+            }
             tmin = p.grp_tmin[g];
             cur_g = g;
         }
@@ -1024,8 +1045,9 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
                         if (p2 >= S.thr[c2]) a |= 1u << c2;
                         if (__uint_as_float(rec[j].w) >= tmin) {          // rare: scan the other classes (a real call)
                             const u32 skip = (l8 < (u32)CT ? 1u << l8 : 0u) | (1u << c1) | (1u << c2);
-                            const u32 more = emit_scan_pixel(p.logits + (size_t)n * CT * p.HW + q0 + j, p.HW, CT,
-                                                             p.pix_m[px0 + j], p.pix_s[px0 + j], S.thr, skip);
+                            const u32 more = (p.dbg & 4) ? 0u : emit_scan_pixel(p.logits + (size_t)n * CT * p.HW + q0 + j, p.HW, CT,
+                                                             p.pix_m[px0 + j], p.pix_s[px0 + j], __uint_as_float(rec[j].w),
+                                                             S.thr, S.order, skip);
                             if (more) { a |= more; extra |= 1u << j; }
                         }
                         acc[j] = a;
@@ -1063,17 +1085,29 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
                 if (lane == 31) S.tot[c] = v;
             }
             __syncthreads();
+            // ---- stage offsets: every warp scans the class totals for itself (no extra CTA barrier) ---------------------------
+            u32 total_all;
+            {
+                const u32 tc = lane < CT ? S.tot[lane] : 0u;
+                u32 v = tc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
+                S.wcoff[warp][lane] = v - tc;
+                total_all = __shfl_sync(FULL_MASK, v, 31);
+                __syncwarp();
+            }
             // ---- passes over class ranges whose candidates fit the stage (one pass unless > ECTA_CAP candidates) ---------
             int lo = 0;
             while (lo < CT) {
-                int hi = lo;
-                u32 sum = 0;
-                while (hi < CT && sum + S.tot[hi] <= ECTA_CAP) { sum += S.tot[hi]; ++hi; }     // tot <= 1024: hi > lo
-                if (tid == 0) {
-                    u32 o = 0;
-                    for (int c = lo; c < hi; ++c) { S.coff[c] = o; o += S.tot[c]; }
+                int hi = CT;
+                u32 base = 0;                              // stage offset of class lo
+                if (total_all > ECTA_CAP) {
+                    hi = lo;
+                    u32 sum = 0;
+                    while (hi < CT && sum + S.tot[hi] <= ECTA_CAP) { sum += S.tot[hi]; ++hi; }     // tot <= 1024: hi > lo
+                    base = S.wcoff[warp][lo];
                 }
-                __syncthreads();
+                const u32* coff = S.wcoff[warp];
                 if (inb) {
                     const u32 below = (1u << shift) - 1u;
 #pragma unroll
@@ -1085,21 +1119,21 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
                         if (l8 < (u32)CT && ((a >> l8) & 1u)) {
                             a &= ~(1u << l8);
                             if ((int)l8 >= lo && (int)l8 < hi) {
-                                const u32 pos = S.coff[l8] + S.wpre[l8][word] + __popc(S.mask[l8][word] & bj);
+                                const u32 pos = coff[l8] - base + S.wpre[l8][word] + __popc(S.mask[l8][word] & bj);
                                 S.stageK[pos] = kfg[j]; S.stageV[pos] = v0 | 1u;
                             }
                         }
                         if ((a >> c1) & 1u) {
                             a &= ~(1u << c1);
                             if ((int)c1 >= lo && (int)c1 < hi) {
-                                const u32 pos = S.coff[c1] + S.wpre[c1][word] + __popc(S.mask[c1][word] & bj);
+                                const u32 pos = coff[c1] - base + S.wpre[c1][word] + __popc(S.mask[c1][word] & bj);
                                 S.stageK[pos] = kc1[j]; S.stageV[pos] = v0;
                             }
                         }
                         if ((a >> c2) & 1u) {
                             a &= ~(1u << c2);
                             if ((int)c2 >= lo && (int)c2 < hi) {
-                                const u32 pos = S.coff[c2] + S.wpre[c2][word] + __popc(S.mask[c2][word] & bj);
+                                const u32 pos = coff[c2] - base + S.wpre[c2][word] + __popc(S.mask[c2][word] & bj);
                                 S.stageK[pos] = kc2[j]; S.stageV[pos] = v0;
                             }
                         }
@@ -1110,7 +1144,7 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
                                 if (c < lo || c >= hi) continue;
                                 const float pr = sm_prob(__ldg(p.logits + ((size_t)n * CT + c) * p.HW + q0 + j),
                                                          p.pix_m[px0 + j], p.pix_s[px0 + j]);
-                                const u32 pos = S.coff[c] + S.wpre[c][word] + __popc(S.mask[c][word] & bj);
+                                const u32 pos = coff[c] - base + S.wpre[c][word] + __popc(S.mask[c][word] & bj);
                                 S.stageK[pos] = err_key(pr); S.stageV[pos] = v0;
                             }
                         }
@@ -1120,7 +1154,7 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
                 // ---- write out: a warp per class, multiples of 8 elements = whole sectors; leftovers -> carry ----------------
                 for (int c = lo + warp; c < hi; c += NW) {
                     const u32 cc = S.carry_cnt[c], nt = S.tot[c], total = cc + nt, w = total & ~7u;
-                    const u32 co = S.coff[c], done = S.emitted[c];
+                    const u32 co = coff[c] - base, done = S.emitted[c];
                     u32* kd = p.keysA + chunk_slot0 + (size_t)c * G.src_cap + done;
                     u32* vd = p.valsA + chunk_slot0 + (size_t)c * G.src_cap + done;
                     for (u32 e = lane; e < w; e += 32) {
@@ -1140,12 +1174,11 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
                     if (lane < 8 && e < total) { S.carryK[c][lane] = lk; S.carryV[c][lane] = lv; }
                     if (lane == 0) { S.carry_cnt[c] = total - w; S.emitted[c] = done + w; }
                 }
-                __syncthreads();
                 lo = hi;
+                if (lo >= CT)                               // last pass: the bit matrix is free, clear it for the next tile
+                    for (int i = tid; i < CT * ECTA_WORDS; i += ECTA_TPB) (&S.mask[0][0])[i] = 0;
+                __syncthreads();
             }
-            // clear the bit matrix for the next tile
-            for (int i = tid; i < CT * ECTA_WORDS; i += ECTA_TPB) (&S.mask[0][0])[i] = 0;
-            __syncthreads();
         }
         // ---- chunk end: flush the carries, publish the run lengths --------------------------------------------------------
         for (int c = warp; c < CT; c += NW) {
@@ -1159,39 +1192,30 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
     }
 }
 
-// per segment: exclusive prefix of the chunk counts (the sort's run prefix) and the segment's candidate count
-__global__ void __launch_bounds__(256) run_scan_kernel(LovaszParams p) {
-    const int lane = threadIdx.x & 31;
-    const int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (seg >= p.n_seg) return;
-    const int g = seg / p.C, c = seg - g * p.C;
-    const int n_runs = p.geo->n_runs;
-    u32* out = p.run_prefix + (size_t)seg * (n_runs + 1);
-    u32 carry = 0;
-    for (int base = 0; base < n_runs; base += 1024) {                 // 32 independent loads per lane, then the scans
-        u32 x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int r = base + i * 32 + lane;
-            x[i] = r < n_runs ? p.run_cnt[((size_t)g * n_runs + r) * p.C + c] : 0;
+// K5b: loss = mean over groups of (mean over kept classes)      reference: mean(), losses/LovaszSoftmax.py:102-120
+__device__ void loss_finalize(const LovaszParams& p) {       // one thread
+    float total = 0.f;
+    for (int g = 0; g < p.groups; ++g) {
+        float acc = 0.f;
+        int n = 0;
+        for (int c = 0; c < p.C; ++c) {
+            const size_t seg = (size_t)g * p.C + c;
+            if (!thr_active(p.seg_thr[seg])) continue;
+            const float l = (float)__ldcg(p.seg_loss + seg);
+            acc = n ? acc + l : l;
+            ++n;
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int r = base + i * 32 + lane;
-            u32 v = x[i];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
-            if (r < n_runs) out[r] = carry + v - x[i];
-            carry += __shfl_sync(FULL_MASK, v, 31);
-        }
+        if (n > 1) acc = acc / (float)n;
+        total = g ? total + acc : acc;
     }
-    if (lane == 0) { out[n_runs] = carry; p.seg_count[seg] = carry; }
+    if (p.groups > 1) total = total / (float)p.groups;
+    *p.loss_out = total;
 }
 
 // --------------------------------------------------------------------------------------------------------------
 // K5: Jaccard gradient over the sorted candidates      reference: lovasz_grad, losses/LovaszSoftmax.py:83-95
 // --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(JAC_TPB) jaccard_kernel(LovaszParams p, SortArgs a) {
+__global__ void __launch_bounds__(JAC_TPB, 4) jaccard_kernel(LovaszParams p, SortArgs a) {
     __shared__ u32 s_wfg[SORT_WARPS];
     __shared__ double s_red[SORT_WARPS];
     __shared__ u32 s_excl;
@@ -1212,6 +1236,12 @@ __global__ void __launch_bounds__(JAC_TPB) jaccard_kernel(LovaszParams p, SortAr
         const float gts = (float)p.seg_fg[seg];
         const float w = p.seg_w[seg];
 
+        // foreground counts of the segment's earlier tiles: requested first, summed after the tile's own loads
+        u32 f0 = 0, f1 = 0;
+        if (warp == 0) {
+            if ((u32)lane < tis) f0 = a.tile_fg[tseg0 + lane];
+            if ((u32)lane + 32 < tis) f1 = a.tile_fg[tseg0 + lane + 32];
+        }
         u32 key[SORT_KPT], val[SORT_KPT];
         unsigned short floc[SORT_KPT];
         const u32 wbase = warp * (32 * SORT_KPT) + lane;
@@ -1232,8 +1262,8 @@ __global__ void __launch_bounds__(JAC_TPB) jaccard_kernel(LovaszParams p, SortAr
 #pragma unroll
         for (int w2 = 0; w2 < SORT_WARPS; ++w2) { const u32 x = s_wfg[w2]; if (w2 < warp) wexcl += x; ttot += x; }
         if (warp == 0) {                                   // foreground flags in the tiles before this one (last sort pass)
-            u32 e = 0;
-            for (u32 i = lane; i < tis; i += 32) e += a.tile_fg[tseg0 + i];
+            u32 e = f0 + f1;
+            for (u32 i = lane + 64; i < tis; i += 32) e += a.tile_fg[tseg0 + i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(FULL_MASK, e, o);
             if (lane == 0) s_excl = e;
@@ -1281,27 +1311,14 @@ __global__ void __launch_bounds__(JAC_TPB) jaccard_kernel(LovaszParams p, SortAr
             atomicAdd(p.seg_loss + seg, tot);
         }
     }
-}
-
-// K5b: loss = mean over groups of (mean over kept classes)      reference: mean(), losses/LovaszSoftmax.py:102-120
-__global__ void loss_finalize_kernel(LovaszParams p) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float total = 0.f;
-    for (int g = 0; g < p.groups; ++g) {
-        float acc = 0.f;
-        int n = 0;
-        for (int c = 0; c < p.C; ++c) {
-            const size_t seg = (size_t)g * p.C + c;
-            if (!thr_active(p.seg_thr[seg])) continue;
-            const float l = (float)p.seg_loss[seg];
-            acc = n ? acc + l : l;
-            ++n;
+    // the CTA that finishes last turns the per-segment sums into the loss (K5b)
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(p.ctrl + CTRL_JTICKET, 1u) == gridDim.x - 1) {
+            __threadfence();
+            loss_finalize(p);
         }
-        if (n > 1) acc = acc / (float)n;
-        total = g ? total + acc : acc;
     }
-    if (p.groups > 1) total = total / (float)p.groups;
-    *p.loss_out = total;
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -1641,7 +1658,7 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.seg_count = (u32*)(ws + L.seg_count); p.grp_valid = (u32*)(ws + L.grp_valid); p.seg_bits = (u32*)(ws + L.seg_bits);
     p.seg_loss = (double*)(ws + L.seg_loss);
     p.seg_thr = (float*)(ws + L.seg_thr); p.seg_logthr = (float*)(ws + L.seg_logthr); p.seg_w = (float*)(ws + L.seg_w);
-    p.grp_tmin = (float*)(ws + L.grp_tmin); p.have_records = 0; p.emit_force = 0;
+    p.grp_tmin = (float*)(ws + L.grp_tmin); p.seg_order = (unsigned char*)(ws + L.seg_order); p.have_records = 0; p.emit_force = 0;
     p.pix_m = (float*)(ws + L.pix_m); p.pix_s = (float*)(ws + L.pix_s); p.gown = (float*)(ws + L.gown);
     p.lab8 = (unsigned char*)(ws + L.lab8); p.cmask = (u32*)(ws + L.cmask);
     p.rec16 = (uint4*)(ws + L.rec16); p.rec4 = (u32*)(ws + L.rec4);
@@ -1773,12 +1790,8 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     const EmitGeom Gr = emit_geom(n, hw, per_image, ECTA_TILE);
     p.geo_stream = EmitGeomDev{(int)Gs.n_runs, (int)Gs.tpc, Gs.run_stride, Gs.src_cap};
     p.geo_rec = EmitGeomDev{(int)Gr.n_runs, (int)Gr.tpc, Gr.run_stride, Gr.src_cap};
-    finalize_stats_kernel<<<(p.groups + 127) / 128, 128, 0, st>>>(p);
-    LAUNCH_CHECK("finalize_stats_kernel");
-    if (p.have_records) {
-        emit_decide_kernel<<<DECIDE_BLOCKS, DECIDE_TPB, 0, st>>>(p);
-        LAUNCH_CHECK("emit_decide_kernel");
-    }
+    finalize_decide_kernel<<<DECIDE_BLOCKS, DECIDE_TPB, 0, st>>>(p);
+    LAUNCH_CHECK("finalize_decide_kernel");
     b200seg_stage(2, st);
 
     // K2
@@ -1816,8 +1829,6 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
             else { DISPATCH_LABEL(label_dtype, emit_kernel<1, LT><<<grid, EMIT_TPB, 0, st>>>(p)); }
         }
         LAUNCH_CHECK("emit_kernel");
-        run_scan_kernel<<<(p.n_seg + 7) / 8, 256, 0, st>>>(p);
-        LAUNCH_CHECK("run_scan_kernel");
     }
     b200seg_stage(3, st);
 
@@ -1827,6 +1838,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     a.keys[0] = p.keysA; a.vals[0] = p.valsA; a.keys[1] = p.keysB; a.vals[1] = p.valsB;
     a.seg_count = p.seg_count; a.seg_bits = p.seg_bits; a.n_seg = p.n_seg; a.cap = p.cap;
     a.src_keys = p.keysA; a.src_vals = p.valsA; a.run_prefix = p.run_prefix; a.geo = p.geo;
+    a.run_cnt = p.run_cnt; a.run_prefix_w = p.run_prefix; a.seg_count_w = p.seg_count; a.n_classes = c;
     a.tile_start = (u32*)(ss + L.sort.tile_start); a.tilehist = (u32*)(ss + L.sort.tilehist);
     a.tile_desc = (uint4*)(ss + L.sort.tile_desc); a.tile_runs = (uint2*)(ss + L.sort.tile_runs);
     a.seg_done = (u32*)(ss + L.sort.seg_done);
@@ -1837,8 +1849,6 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     // K5
     jaccard_kernel<<<sms * 4, JAC_TPB, 0, st>>>(p, a);
     LAUNCH_CHECK("jaccard_kernel");
-    loss_finalize_kernel<<<1, 32, 0, st>>>(p);
-    LAUNCH_CHECK("loss_finalize_kernel");
     b200seg_stage(8, st);
     return 0;
 }
@@ -1937,6 +1947,7 @@ extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint3
     a.keys[0] = keys_in; a.vals[0] = vals_in; a.keys[1] = keys_out; a.vals[1] = vals_out;
     a.seg_count = counts; a.seg_bits = key_bits; a.n_seg = n_segments; a.cap = capacity;
     a.src_keys = nullptr; a.src_vals = nullptr; a.run_prefix = nullptr; a.geo = nullptr;
+    a.run_cnt = nullptr; a.run_prefix_w = nullptr; a.seg_count_w = nullptr; a.n_classes = 1;
     a.tile_start = (u32*)(ss + L.tile_start); a.tilehist = (u32*)(ss + L.tilehist);
     a.tile_desc = (uint4*)(ss + L.tile_desc); a.tile_runs = (uint2*)(ss + L.tile_runs);
     a.seg_done = (u32*)(ss + L.seg_done);

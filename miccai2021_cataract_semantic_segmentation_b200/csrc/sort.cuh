@@ -17,6 +17,7 @@
 // A last small kernel counts the foreground flags (value bit 0) per tile of the final order for the Jaccard scan.
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 #define SORT_TPB 256
 #define SORT_KPT 16
@@ -38,6 +39,11 @@ struct SortArgs {
     const u32* src_vals;
     const u32* run_prefix;  // [n_seg][n_runs + 1]
     const EmitGeomDev* geo; // n_runs, run_stride, src_cap of the holey source (device memory)
+    // inputs of the run scan (holey source only): candidates per (group, chunk, class) as the emission kernels leave them
+    const u32* run_cnt;     // [groups * n_runs][n_classes]
+    u32* run_prefix_w;      // = run_prefix, writable: filled by sort_prepare_kernel
+    u32* seg_count_w;       // = seg_count, writable: filled by sort_prepare_kernel
+    int n_classes;
     // scratch
     u32* tile_start;        // [n_seg + 1] exclusive prefix of tiles per segment
     uint4* tile_desc;       // [max_tiles] {segment, first element, element count, digit width}
@@ -79,19 +85,59 @@ __device__ __forceinline__ int sort_find_segment(const u32* tile_start, int n_se
     int lo = 0, hi = n_seg - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(tile_start + mid) <= t) lo = mid; else hi = mid - 1;
+        if (tile_start[mid] <= t) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
 
-// ---- plan: tiles per segment -> exclusive prefix; clears the per-tile foreground counters -----------------------
-__global__ void __launch_bounds__(1024) sort_plan_kernel(SortArgs a, u32 max_tiles) {
+__device__ __forceinline__ u32 upper_run(const u32* prefix, u32 lo, u32 hi, u32 v) {   // largest r in [lo,hi]: prefix[r] <= v
+    while (lo < hi) {
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (prefix[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ---- prepare (one CTA): everything between the emission and the first digit pass -------------------------------------
+//   1. holey source only: per segment, exclusive prefix of the chunk counts (the run prefix) and the segment's count
+//   2. tiles per segment -> exclusive prefix (tile_start); clears the per-pass and per-tile counters
+//   3. one descriptor per tile {segment, first element, element count, digit width} (+ the source runs it intersects),
+//      so the per-tile prologue of every later kernel is a single 16-byte load instead of a chain of dependent ones
+#define SORT_PREP_TPB 1024
+__global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a, u32 max_tiles) {
     __shared__ u32 s_warp[32];
     __shared__ u32 s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.run_prefix) {
+        const int n_runs = a.geo->n_runs, C = a.n_classes;
+        for (int seg = warp; seg < a.n_seg; seg += SORT_PREP_TPB / 32) {
+            const int g = seg / C, c = seg - g * C;
+            u32* out = a.run_prefix_w + (size_t)seg * (n_runs + 1);
+            u32 carry = 0;
+            for (int base = 0; base < n_runs; base += 1024) {             // 32 independent loads per lane, then the scans
+                u32 x[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int r = base + i * 32 + lane;
+                    x[i] = r < n_runs ? a.run_cnt[((size_t)g * n_runs + r) * C + c] : 0;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int r = base + i * 32 + lane;
+                    u32 v = x[i];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
+                    if (r < n_runs) out[r] = carry + v - x[i];
+                    carry += __shfl_sync(FULL_MASK, v, 31);
+                }
+            }
+            if (lane == 0) { out[n_runs] = carry; a.seg_count_w[seg] = carry; }
+        }
+        __syncthreads();                                   // CTA-scope visibility of seg_count / run_prefix
+    }
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < a.n_seg; base += 1024) {
+    for (int base = 0; base < a.n_seg; base += SORT_PREP_TPB) {
         const int s = base + tid;
         const u32 nt = s < a.n_seg ? (a.seg_count[s] + SORT_TILE - 1) / SORT_TILE : 0;
         u32 v = nt;
@@ -109,35 +155,24 @@ __global__ void __launch_bounds__(1024) sort_plan_kernel(SortArgs a, u32 max_til
         const u32 incl = v + (warp ? s_warp[warp - 1] : 0) + s_carry;
         if (s < a.n_seg) a.tile_start[s] = incl - nt;
         __syncthreads();
-        if (tid == 1023) s_carry = incl;
+        if (tid == SORT_PREP_TPB - 1) s_carry = incl;
         __syncthreads();
     }
-    if (tid == 0) a.tile_start[a.n_seg] = s_carry;
-    for (int i = tid; i < a.n_seg * SORT_PASSES; i += 1024) a.seg_done[i] = 0;
-}
-
-__device__ __forceinline__ u32 upper_run(const u32* prefix, u32 lo, u32 hi, u32 v) {   // largest r in [lo,hi]: prefix[r] <= v
-    while (lo < hi) {
-        const u32 mid = (lo + hi + 1) >> 1;
-        if (prefix[mid] <= v) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
-// one thread per tile: {segment, offset of the tile's first element in its segment, element count, digit width}
-// so the per-tile prologue of every later kernel is a single 16-byte load instead of a chain of dependent ones
-__global__ void __launch_bounds__(256) sort_desc_kernel(SortArgs a) {
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 total = a.tile_start[a.n_seg];
-    if (t >= total) return;
-    const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
-    const u32 off = (t - a.tile_start[seg]) * SORT_TILE;
-    const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
-    a.tile_desc[t] = make_uint4((u32)seg, off, n, sort_digit_width(a.seg_bits[seg]));
-    if (a.run_prefix) {
-        const int n_runs = a.geo->n_runs;
-        const u32* prefix = a.run_prefix + (size_t)seg * (n_runs + 1);
-        a.tile_runs[t] = make_uint2(upper_run(prefix, 0, n_runs - 1, off), upper_run(prefix, 0, n_runs - 1, off + n - 1));
+    const u32 total = s_carry;
+    if (tid == 0) a.tile_start[a.n_seg] = total;
+    for (int i = tid; i < a.n_seg * SORT_PASSES; i += SORT_PREP_TPB) a.seg_done[i] = 0;
+    for (u32 i = tid; i < total && i < max_tiles; i += SORT_PREP_TPB) a.tile_fg[i] = 0;
+    __syncthreads();
+    for (u32 t = tid; t < total && t < max_tiles; t += SORT_PREP_TPB) {
+        const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
+        const u32 off = (t - a.tile_start[seg]) * SORT_TILE;
+        const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
+        a.tile_desc[t] = make_uint4((u32)seg, off, n, sort_digit_width(a.seg_bits[seg]));
+        if (a.run_prefix) {
+            const int n_runs = a.geo->n_runs;
+            const u32* prefix = a.run_prefix + (size_t)seg * (n_runs + 1);
+            a.tile_runs[t] = make_uint2(upper_run(prefix, 0, n_runs - 1, off), upper_run(prefix, 0, n_runs - 1, off + n - 1));
+        }
     }
 }
 
@@ -293,8 +328,6 @@ __global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pa
 // where keys cluster) skips the loop.
 template <int NBITS>
 __device__ __forceinline__ u32 peer_mask(u32 d) {
-    const u32 d0 = __shfl_sync(FULL_MASK, d, 0);
-    if (__all_sync(FULL_MASK, d == d0)) return FULL_MASK;
     u32 peers = FULL_MASK;
 #pragma unroll
     for (int b = 0; b < NBITS; ++b) {
@@ -317,15 +350,21 @@ struct ScatterSmem {
 };
 
 // stable rank of each of the warp's SORT_KPT rows within (warp, digit); NBITS = digit width + 1 (the extra bit is
-// the dummy bin of padding lanes)
-template <int NBITS>
+// the dummy bin of padding lanes).  Two loops on purpose: the peer masks of all rows are independent (their votes
+// pipeline), only the counter updates form a chain through shared memory.
+template <int NBITS, bool USE_MATCH>
 __device__ __forceinline__ void rank_rows(ScatterSmem& S, const u32 (&key)[SORT_KPT], u32 (&rnk)[SORT_KPT], u32 n,
                                           u32 wbase, u32 shift, u32 dmask, u32 nbins, int warp, int lane) {
     const u32 lt_mask = (1u << lane) - 1;
 #pragma unroll
     for (int k = 0; k < SORT_KPT; ++k) {
         const u32 d = (wbase + k * 32 < n) ? ((key[k] >> shift) & dmask) : nbins;
-        const u32 m = peer_mask<NBITS>(d);
+        rnk[k] = USE_MATCH ? __match_any_sync(FULL_MASK, d) : peer_mask<NBITS>(d);
+    }
+#pragma unroll
+    for (int k = 0; k < SORT_KPT; ++k) {
+        const u32 d = (wbase + k * 32 < n) ? ((key[k] >> shift) & dmask) : nbins;
+        const u32 m = rnk[k];
         const int leader = __ffs(m) - 1;
         u32 old = 0;
         if (lane == leader) { old = S.cnt[warp][d]; S.cnt[warp][d] = (unsigned short)(old + __popc(m)); }
@@ -338,6 +377,7 @@ __device__ __forceinline__ void rank_rows(ScatterSmem& S, const u32 (&key)[SORT_
 // Elements are first placed at their tile-local sorted position in shared memory, then streamed out so that the
 // lanes of a warp write consecutive addresses within each digit bin (a fully scattered 4-byte store costs the LSU
 // one wavefront per lane).
+template <bool USE_MATCH>
 __global__ void __launch_bounds__(SORT_TPB, 3) sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(smem_raw);
@@ -385,10 +425,10 @@ __global__ void __launch_bounds__(SORT_TPB, 3) sort_scatter_kernel(SortArgs a, i
             }
         }
         switch (w) {                                      // uniform per tile
-            case 10: rank_rows<11>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
-            case 9: rank_rows<10>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
-            case 8: rank_rows<9>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
-            default: rank_rows<8>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+            case 10: rank_rows<11, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+            case 9: rank_rows<10, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+            case 8: rank_rows<9, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+            default: rank_rows<8, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
         }
         __syncthreads();
         // thread b owns bins [4b, 4b+4): four u16 counters travel as one 64-bit word (no carries: totals <= 4096)
@@ -480,22 +520,24 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {          // opt in to > 48 KB of dynamic shared memory, once per device
-        CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(ScatterSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(ScatterSmem)));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    sort_plan_kernel<<<1, 1024, 0, st>>>(a, L.max_tiles);
-    LAUNCH_CHECK("sort_plan_kernel");
-    sort_desc_kernel<<<(L.max_tiles + 255) / 256, 256, 0, st>>>(a);
-    LAUNCH_CHECK("sort_desc_kernel");
+    sort_prepare_kernel<<<1, SORT_PREP_TPB, 0, st>>>(a, L.max_tiles);
+    LAUNCH_CHECK("sort_prepare_kernel");
     b200seg_stage(4, st);
+    static const bool use_match = getenv("B200SEG_SORT_MATCH") && atoi(getenv("B200SEG_SORT_MATCH")) != 0;   // A/B switch
     const int sms = b200seg_sm_count();
     const u32 cgrid = L.max_tiles < (u32)sms * 8 ? L.max_tiles : (u32)sms * 8;
     const u32 sgrid = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;
     for (int p = 0; p < SORT_PASSES; ++p) {
         sort_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_count_kernel");
-        sort_scatter_kernel<<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
+        if (use_match) sort_scatter_kernel<true><<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
+        else sort_scatter_kernel<false><<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_scatter_kernel");
         if (p + 1 < SORT_PASSES) b200seg_stage(5 + p, st);
     }
