@@ -34,7 +34,7 @@ struct LovaszParams {
     const void* labels;
     int N, C;
     long long HW, P, cap;
-    int per_image, has_filter, filter, keep_absent, need_grad, dbg;
+    int per_image, has_filter, filter, keep_absent, need_grad, dbg, interleave;
     u32 class_mask;
     int groups, n_seg;
     // workspace
@@ -375,7 +375,13 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
     const u32 wtpi = (u32)((p.HW + WT - 1) / WT);
     const u32 nwt = wtpi * (u32)p.N;
     const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
-    const u32 t0 = (u32)((u64)nwt * gw / nwarps), t1 = (u32)((u64)nwt * (gw + 1) / nwarps);
+    // tiles of a warp: interleaved (t = gw, gw + nwarps, ...: the warps running at any moment sweep one window of
+    // consecutive addresses per class plane, which DRAM likes) or a contiguous range
+    // (per-image mode keeps contiguous ranges: a warp flushes its counters whenever its image changes)
+    const bool il = p.interleave && !p.per_image;
+    const u32 step = il ? nwarps : 1u;
+    const u32 t0 = il ? gw : (u32)((u64)nwt * gw / nwarps);
+    const u32 t1 = il ? nwt : (u32)((u64)nwt * (gw + 1) / nwarps);
     u32 cn = t0 / wtpi, cti = t0 - cn * wtpi;             // tile being consumed
     u32 pn = cn, pti = cti, pt = t0;                       // next tile to prefetch
     auto prefetch_next = [&](int stage) {
@@ -388,8 +394,8 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
                              (const unsigned char*)p.labels + ((size_t)pn * p.HW + q0) * sizeof(LT) + lane * 16);
         }
         cp_async_commit();
-        ++pt;
-        if (++pti == wtpi) { pti = 0; ++pn; }
+        pt += step; pti += step;
+        while (pti >= wtpi) { pti -= wtpi; ++pn; }
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) prefetch_next(s);
@@ -410,13 +416,14 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
 
     int cur_g = -1, stage = 0, pstage = STAGES - 1;
     u32 nvalid = 0, oob = 0;
-    for (u32 t = t0; t < t1; ++t) {
+    for (u32 t = t0; t < t1; t += step) {
         __syncwarp();                                     // every lane is done reading the stage about to be refilled
         prefetch_next(pstage);
         if (++pstage == STAGES) pstage = 0;
         const int n = (int)cn;
         const long long q = (long long)cti * WT + lane;
-        if (++cti == wtpi) { cti = 0; ++cn; }
+        cti += step;
+        while (cti >= wtpi) { cti -= wtpi; ++cn; }
         const int g = p.per_image ? n : 0;
         if (g != cur_g) {
             if (cur_g >= 0) { flush_group(cur_g, nvalid); nvalid = 0; }
@@ -1445,7 +1452,9 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
     const u32 wtpi = (u32)((p.HW + WT - 1) / WT);         // tile counts fit 32 bits: keep the index math off the 64-bit divider
     const u32 nwt = wtpi * (u32)p.N;
     const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
-    const u32 t0 = (u32)((u64)nwt * gw / nwarps), t1 = (u32)((u64)nwt * (gw + 1) / nwarps);
+    const u32 step = p.interleave ? nwarps : 1u;         // see stats_kernel_async
+    const u32 t0 = p.interleave ? gw : (u32)((u64)nwt * gw / nwarps);
+    const u32 t1 = p.interleave ? nwt : (u32)((u64)nwt * (gw + 1) / nwarps);
     if (t0 >= t1) return;
     const float gsc = __ldg(go);
     const size_t plane = (size_t)p.HW;
@@ -1453,8 +1462,8 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
     // (image, tile-in-image) cursors advance by increments: no integer division per tile
     u32 cn = t0 / wtpi, cti = t0 - cn * wtpi;             // tile being consumed
     u32 n1 = cn, ti1 = cti, pt1 = t0;                      // next tile whose state / logits are requested
-    u32 n2 = cn, ti2 = cti + 1, pt2 = t0 + 1;              // next tile whose candidate mask is requested
-    if (ti2 == wtpi) { ti2 = 0; ++n2; }
+    u32 n2 = cn, ti2 = cti + step, pt2 = t0 + step;        // next tile whose candidate mask is requested
+    while (ti2 >= wtpi) { ti2 -= wtpi; ++n2; }
     const int sub = lane & 7, strm = lane >> 3;            // 16-byte chunk / stream of the combined state copy
     // request tile pt1 (its mask is `mask1`) into stage `st`, and the mask of tile pt2 = pt1 + 1 along with it
     auto request = [&](Stage& st, u32 mask1) {
@@ -1481,9 +1490,9 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
             }
         }
         cp_async_commit();
-        ++pt1; ++pt2;
-        if (++ti1 == wtpi) { ti1 = 0; ++n1; }
-        if (++ti2 == wtpi) { ti2 = 0; ++n2; }
+        pt1 += step; pt2 += step; ti1 += step; ti2 += step;
+        while (ti1 >= wtpi) { ti1 -= wtpi; ++n1; }
+        while (ti2 >= wtpi) { ti2 -= wtpi; ++n2; }
     };
     u32 mask = 0;                                          // candidate mask of the tile being consumed
     {
@@ -1494,15 +1503,16 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
 
     int cur_g = -1;
     u32 it = 0;
-    for (u32 t = t0; t < t1; ++t, ++it) {
+    for (u32 t = t0; t < t1; t += step, ++it) {
         Stage& C = S[it & 1];
         cp_async_wait<0>();                               // this lane's copies for tile t have landed ...
         __syncwarp();                                     // ... so have the other lanes', and nobody still reads the other stage
-        const u32 nmask = (t + 1 < t1) ? C.maskn[lane] : 0u;
+        const u32 nmask = (t + step < t1) ? C.maskn[lane] : 0u;
         request(S[(it & 1) ^ 1], nmask);
         const int n = (int)cn;
         const long long q = (long long)cti * WT + lane;
-        if (++cti == wtpi) { cti = 0; ++cn; }
+        cti += step;
+        while (cti >= wtpi) { cti -= wtpi; ++cn; }
         const int g = p.per_image ? n : 0;
         if (g != cur_g) {
             __syncwarp();
@@ -1672,6 +1682,8 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.cm = nullptr; p.has_drop = 0; p.drop = 0;
     p.status = (int*)(p.ctrl + CTRL_STATUS);
     p.loss_out = nullptr; p.need_grad = 1; p.dbg = 0;
+    static const int interleave = getenv("B200SEG_INTERLEAVE") ? atoi(getenv("B200SEG_INTERLEAVE")) : 1;
+    p.interleave = interleave;
     return true;
 }
 

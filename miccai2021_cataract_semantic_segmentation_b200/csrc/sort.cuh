@@ -529,13 +529,17 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     sort_prepare_kernel<<<1, SORT_PREP_TPB, 0, st>>>(a, L.max_tiles);
     LAUNCH_CHECK("sort_prepare_kernel");
     b200seg_stage(4, st);
-    static const bool use_match = getenv("B200SEG_SORT_MATCH") && atoi(getenv("B200SEG_SORT_MATCH")) != 0;   // A/B switch
+    // peer masks by MATCH.ANY cost ~ the number of distinct digits in the warp: a win only for the top digit, where
+    // the keys cluster (measured: 38 vs 45 us for that pass, 65 vs 56 us for the low digits); B200SEG_SORT_MATCH = 0 / 1
+    // forces ballots / match everywhere
+    static const int match_mode = getenv("B200SEG_SORT_MATCH") ? atoi(getenv("B200SEG_SORT_MATCH")) : 2;
     const int sms = b200seg_sm_count();
     const u32 cgrid = L.max_tiles < (u32)sms * 8 ? L.max_tiles : (u32)sms * 8;
     const u32 sgrid = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;
     for (int p = 0; p < SORT_PASSES; ++p) {
         sort_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_count_kernel");
+        const bool use_match = match_mode == 1 || (match_mode == 2 && p == SORT_PASSES - 1);
         if (use_match) sort_scatter_kernel<true><<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
         else sort_scatter_kernel<false><<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_scatter_kernel");
