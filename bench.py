@@ -35,8 +35,8 @@ import torch  # noqa: E402
 
 METRIC = "Mpixel/s Lovasz fwd+bwd + mIoU @540x960 C=25"
 UNIT = "Mpixel/s"
-STAGES = ["stats(+fused confmat)", "finalize", "emit", "sort_plan", "sort_pass0", "sort_pass1", "sort_pass2",
-          "jaccard+loss", None, "backward"]
+STAGES = ["stats(+fused confmat, records)", "finalize+decide", "emit", "sort_prepare", "sort_pass0", "sort_pass1",
+          "sort_pass2", "jaccard+loss", None, "backward"]
 N_EV = len(STAGES) + 1
 # stats, finalize+decide, emit (record path) + emit (streaming path, exits at once), sort prepare, 3 x (count, scatter),
 # fg_count, jaccard(+loss), backward, metrics
@@ -323,9 +323,10 @@ def main():
     p = px_rank
     # algorithmic bytes per launch of each kernel group (DESIGN.md "Kernels"): compulsory reads + writes of that stage
     alg = {
-        "stats(+fused confmat)": p * (4 * c + lab_bytes),
-        "emit": p * (4 * c + lab_bytes + 8),            # logits + labels + the 8 B/px softmax state
-        "backward": p * (2 * 4 * c + lab_bytes + 12),     # logits in, gradients out, labels, 12 B/px state
+        # logits + labels in; softmax state (8), compact label (1) and the 20-byte candidate record out
+        "stats(+fused confmat, records)": p * (4 * c + lab_bytes + 29),
+        # logits in, gradients out, 17 B/px of state (softmax max / denominator, own gradient, label8, candidate mask)
+        "backward": p * (2 * 4 * c + 17),
     }
     dom = max(stage_ms, key=stage_ms.get)
     traffic = None

@@ -137,6 +137,20 @@ int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_o
                           const uint32_t* counts, const uint32_t* key_bits, int32_t n_segments, int64_t capacity,
                           void* scratch, size_t scratch_bytes, int32_t* status, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Kernel-selection knobs (no reference counterpart; process-wide).  Every setting computes the same results;
+ * they exist so tests can exercise every code path and profiles can compare variants in one process.
+ *   "interleave"    1 (default) warps of the streaming kernels take interleaved tiles, 0 contiguous ranges
+ *   "stats_variant" 0 (default) pipelined stats kernel, 3 ring stages; 2 / 3: 2 / 4 stages; 1: register-tile
+ *                   kernel without per-pixel records (forces the streaming emission)
+ *   "emit_path"     0 (default) chosen on the device from the records; 1 record-driven; 2 streaming
+ *   "sort_match"    2 (default) MATCH.ANY peer masks in the top digit pass only; 0 ballots; 1 MATCH.ANY
+ *   "dbg"           timing experiments only (skips work: results become wrong)
+ * Initial values come from the environment variables B200SEG_INTERLEAVE, B200SEG_STATS_VARIANT,
+ * B200SEG_EMIT_PATH, B200SEG_SORT_MATCH, B200SEG_DBG.
+ * ------------------------------------------------------------------------------------------------ */
+int b200seg_set_tuning(const char* key, int32_t value);
+
 /* Test hook: byte offsets inside the Lovasz workspace of {pix_m, pix_s, label8, candidate mask, rec16, rec4,
  * seg_thr, grp_tmin} (see DESIGN.md "Data layout"), so tests can check the per-pixel candidate records that
  * b200seg_lovasz_forward leaves behind against a straightforward softmax / top-k. */

@@ -32,6 +32,7 @@ SIGNATURES = {
     "b200seg_confmat_accumulate": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp]),
     "b200seg_metrics_from_confmat": (_c.c_int, [_vp, _i32, _u32, _c.POINTER(_u32), _i32, _vp, _vp, _vp]),
     "b200seg_set_stage_events": (_c.c_int, [_c.POINTER(_vp), _i32]),
+    "b200seg_set_tuning": (_c.c_int, [_c.c_char_p, _i32]),
     "b200seg_debug_layout": (_c.c_int, [_i32, _i32, _i64, _i32, _c.POINTER(_sz), _i32]),
     "b200seg_sort_scratch_bytes": (_c.c_int, [_i32, _i64, _c.POINTER(_sz)]),
     "b200seg_sort_segments": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _sz, _vp, _vp]),
@@ -65,6 +66,13 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().b200seg_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def set_tuning(**knobs: int):
+    """Kernel-selection knobs of the library (see include/b200seg.h); every setting computes the same results."""
+    lib = load()
+    for k, v in knobs.items():
+        check(lib.b200seg_set_tuning(k.encode(), int(v)), f"b200seg_set_tuning({k})")
 
 
 def label_code(t: torch.Tensor) -> int:

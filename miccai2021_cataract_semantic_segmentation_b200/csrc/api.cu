@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 static thread_local char g_err[512] = "";
 
@@ -23,6 +25,27 @@ int b200seg_sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+B200segTuning& b200seg_tuning() {
+    static B200segTuning t = {env_int("B200SEG_INTERLEAVE", 1), env_int("B200SEG_STATS_VARIANT", 0),
+                              env_int("B200SEG_EMIT_PATH", 0), env_int("B200SEG_SORT_MATCH", 2), env_int("B200SEG_DBG", 0)};
+    return t;
+}
+extern "C" int b200seg_set_tuning(const char* key, int32_t value) {
+    B200segTuning& t = b200seg_tuning();
+    if (!key) { b200seg_set_error("b200seg_set_tuning: key is NULL"); return B200SEG_E_INVALID; }
+    if (!strcmp(key, "interleave")) t.interleave = value;
+    else if (!strcmp(key, "stats_variant")) t.stats_variant = value;
+    else if (!strcmp(key, "emit_path")) t.emit_path = value;
+    else if (!strcmp(key, "sort_match")) t.sort_match = value;
+    else if (!strcmp(key, "dbg")) t.dbg = value;
+    else { b200seg_set_error("b200seg_set_tuning: unknown key '%s'", key); return B200SEG_E_INVALID; }
+    return 0;
 }
 
 extern "C" int b200seg_version(void) { return B200SEG_VERSION; }

@@ -446,14 +446,14 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
 #pragma unroll
         for (int c = 1; c < CT; ++c) m = fmaxf(m, z[c]);
         // softmax denominator (ascending class order, like ATen) and the three largest exps among the other classes:
-        // exps are positive, so their bit patterns order like integers; the class index rides in the low 5 bits
+        // exps are positive, so their bit patterns order like integers; the class index rides in the low byte
         float s = 0.f;
         int b1 = -1, b2 = -1, b3 = -1;
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
             const float e = sm_exp(z[c], m);
             s = __fadd_rn(s, e);
-            int v = (int)((__float_as_uint(e) & ~31u) | (u32)c);
+            int v = (int)__byte_perm(__float_as_uint(e), (u32)c, 0x3214);   // low byte <- class (one PRMT)
             v = (c == lab) ? -1 : v;
             const int t1v = min(b1, v); b1 = max(b1, v);
             const int t2v = min(b2, t1v); b2 = max(b2, t1v);
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
         {
             const int c1 = b1 & 31, c2 = b2 & 31;          // CT >= 4: b1..b3 are real classes
             const float p1 = sm_prob(T[c1][lane], m, s), p2 = sm_prob(T[c2][lane], m, s);
-            const float p3 = __fdiv_ru(__uint_as_float((u32)b3 | 31u), s);   // >= p of every class not recorded
+            const float p3 = __fdiv_ru(__uint_as_float((u32)b3 | 255u), s);  // >= p of every class not recorded
             p.rec16[px] = make_uint4(kfg, __float_as_uint(p1), __float_as_uint(p2), __float_as_uint(p3));
             p.rec4[px] = l8 | ((u32)c1 << 8) | ((u32)c2 << 16);
         }
@@ -1682,8 +1682,7 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.cm = nullptr; p.has_drop = 0; p.drop = 0;
     p.status = (int*)(p.ctrl + CTRL_STATUS);
     p.loss_out = nullptr; p.need_grad = 1; p.dbg = 0;
-    static const int interleave = getenv("B200SEG_INTERLEAVE") ? atoi(getenv("B200SEG_INTERLEAVE")) : 1;
-    p.interleave = interleave;
+    p.interleave = b200seg_tuning().interleave;
     return true;
 }
 
@@ -1735,8 +1734,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     fill_params(p, L, ws, logits, labels, n, c, hw, per_image, filter_label, keep_absent, class_mask);
     p.loss_out = loss_out;
     p.need_grad = need_grad ? 1 : 0;
-    static const int dbg = getenv("B200SEG_DBG") ? atoi(getenv("B200SEG_DBG")) : 0;   // timing experiments only
-    p.dbg = dbg;
+    p.dbg = b200seg_tuning().dbg;
     p.cm = (unsigned long long*)cm;
     p.has_drop = (cm_drop_label != B200SEG_NO_LABEL && cm_drop_label >= INT_MIN && cm_drop_label <= INT_MAX) ? 1 : 0;
     p.drop = p.has_drop ? (int)cm_drop_label : 0;
@@ -1749,8 +1747,7 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
 
     // K1
     const bool known_c = (c == 8 || c == 17 || c == 25);
-    static const int stats_variant = getenv("B200SEG_STATS_VARIANT") ? atoi(getenv("B200SEG_STATS_VARIANT")) : 0;
-    static const int emit_force = getenv("B200SEG_EMIT_PATH") ? atoi(getenv("B200SEG_EMIT_PATH")) : 0;
+    const int stats_variant = b200seg_tuning().stats_variant, emit_force = b200seg_tuning().emit_path;
     const bool async_ok = v4 && known_c && hw % 16 == 0 && aligned16(labels);
     if (async_ok && stats_variant != 1) {
         p.have_records = 1;

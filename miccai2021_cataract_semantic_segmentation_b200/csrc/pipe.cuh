@@ -78,11 +78,16 @@ struct WarpTile {
         const int ch = lane % CHUNKS, r0 = lane / CHUNKS;
         const long long q = q0 + 4 * ch;
         if (q < HW) {
-            const float* src = logits + (size_t)n * CT * HW + q;
+            // one running source pointer and one running shared-memory address: two adds per copy
+            const float* src = logits + ((size_t)n * CT + r0) * HW + q;
+            const size_t step = (size_t)ROWS_PER_INSTR * HW;
+            u32 dst = smem_u32(&buf[r0][4 * ch]);
 #pragma unroll
             for (int i = 0; i < NINSTR; ++i) {
-                const int c = i * ROWS_PER_INSTR + r0;
-                if (c < CT) cp_async<16>(&buf[c][4 * ch], src + (size_t)c * HW);
+                if ((i + 1) * ROWS_PER_INSTR <= CT || i * ROWS_PER_INSTR + r0 < CT)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                src += step;
+                dst += ROWS_PER_INSTR * WT * 4;
             }
         }
     }

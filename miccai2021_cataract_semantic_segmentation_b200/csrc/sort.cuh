@@ -532,7 +532,7 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     // peer masks by MATCH.ANY cost ~ the number of distinct digits in the warp: a win only for the top digit, where
     // the keys cluster (measured: 38 vs 45 us for that pass, 65 vs 56 us for the low digits); B200SEG_SORT_MATCH = 0 / 1
     // forces ballots / match everywhere
-    static const int match_mode = getenv("B200SEG_SORT_MATCH") ? atoi(getenv("B200SEG_SORT_MATCH")) : 2;
+    const int match_mode = b200seg_tuning().sort_match;
     const int sms = b200seg_sm_count();
     const u32 cgrid = L.max_tiles < (u32)sms * 8 ? L.max_tiles : (u32)sms * 8;
     const u32 sgrid = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;
