@@ -617,9 +617,19 @@ __global__ void __launch_bounds__(DECIDE_TPB) finalize_decide_kernel(LovaszParam
             const long long stride = p.cap > target ? p.cap / target : 1;
             const long long i0 = flat ? (long long)blockIdx.x * DECIDE_TPB + tid : tid;
             const long long di = flat ? (long long)gridDim.x * DECIDE_TPB : DECIDE_TPB;
-            for (long long i = i0; i * stride < p.cap; i += di) {
-                slow += __uint_as_float(p.rec16[(size_t)g * p.cap + i * stride].w) >= tmin;
-                ++n;
+            const u32* guard = reinterpret_cast<const u32*>(p.rec16 + (size_t)g * p.cap) + 3;   // rec16[px].w
+            for (long long i = i0; i * stride < p.cap; i += 8 * di) {       // 8 independent loads in flight per thread
+                u32 w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const long long px = (i + k * di) * stride;
+                    w[k] = px < p.cap ? __ldg(guard + 4 * px) : 0xFFFFFFFFu;       // NaN pattern: compares false
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    slow += __uint_as_float(w[k]) >= tmin;
+                    n += (i + k * di) * stride < p.cap;
+                }
             }
         }
     }

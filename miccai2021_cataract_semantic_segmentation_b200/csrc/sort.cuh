@@ -104,6 +104,7 @@ __device__ __forceinline__ u32 upper_run(const u32* prefix, u32 lo, u32 hi, u32 
 //   3. one descriptor per tile {segment, first element, element count, digit width} (+ the source runs it intersects),
 //      so the per-tile prologue of every later kernel is a single 16-byte load instead of a chain of dependent ones
 #define SORT_PREP_TPB 1024
+#define SORT_PREP_WINDOW 1024                 // run-prefix entries a warp stages in shared memory (else it searches global)
 __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a, u32 max_tiles) {
     __shared__ u32 s_warp[32];
     __shared__ u32 s_carry;
@@ -163,15 +164,25 @@ __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a,
     for (int i = tid; i < a.n_seg * SORT_PASSES; i += SORT_PREP_TPB) a.seg_done[i] = 0;
     for (u32 i = tid; i < total && i < max_tiles; i += SORT_PREP_TPB) a.tile_fg[i] = 0;
     __syncthreads();
-    for (u32 t = tid; t < total && t < max_tiles; t += SORT_PREP_TPB) {
-        const int seg = sort_find_segment(a.tile_start, a.n_seg, t);
-        const u32 off = (t - a.tile_start[seg]) * SORT_TILE;
-        const u32 n = min((u32)SORT_TILE, a.seg_count[seg] - off);
-        a.tile_desc[t] = make_uint4((u32)seg, off, n, sort_digit_width(a.seg_bits[seg]));
-        if (a.run_prefix) {
-            const int n_runs = a.geo->n_runs;
-            const u32* prefix = a.run_prefix + (size_t)seg * (n_runs + 1);
-            a.tile_runs[t] = make_uint2(upper_run(prefix, 0, n_runs - 1, off), upper_run(prefix, 0, n_runs - 1, off + n - 1));
+    // descriptors: a warp per segment; the segment's run prefix is staged in shared memory so that the two binary
+    // searches per tile do not chase global memory
+    extern __shared__ u32 s_prefix_all[];
+    u32* s_prefix = s_prefix_all + (size_t)warp * SORT_PREP_WINDOW;
+    const int n_runs = a.run_prefix ? a.geo->n_runs : 0;
+    for (int seg = warp; seg < a.n_seg; seg += SORT_PREP_TPB / 32) {
+        const u32 t_first = a.tile_start[seg], nt = a.tile_start[seg + 1] - t_first;
+        if (nt == 0) continue;
+        const u32 cnt = a.seg_count[seg], w = sort_digit_width(a.seg_bits[seg]);
+        const u32* prefix = a.run_prefix ? a.run_prefix + (size_t)seg * (n_runs + 1) : nullptr;
+        const bool staged = prefix && n_runs + 1 <= SORT_PREP_WINDOW;
+        __syncwarp();
+        if (staged) for (int i = lane; i <= n_runs; i += 32) s_prefix[i] = prefix[i];
+        __syncwarp();
+        const u32* pf = staged ? s_prefix : prefix;
+        for (u32 i = lane; i < nt && t_first + i < max_tiles; i += 32) {
+            const u32 off = i * SORT_TILE, n = min((u32)SORT_TILE, cnt - off);
+            a.tile_desc[t_first + i] = make_uint4((u32)seg, off, n, w);
+            if (prefix) a.tile_runs[t_first + i] = make_uint2(upper_run(pf, 0, n_runs - 1, off), upper_run(pf, 0, n_runs - 1, off + n - 1));
         }
     }
 }
@@ -520,13 +531,15 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {          // opt in to > 48 KB of dynamic shared memory, once per device
+        CUDA_TRY(cudaFuncSetAttribute(sort_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(u32) * SORT_PREP_WINDOW * (SORT_PREP_TPB / 32))));
         CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(ScatterSmem)));
         CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(ScatterSmem)));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    sort_prepare_kernel<<<1, SORT_PREP_TPB, 0, st>>>(a, L.max_tiles);
+    sort_prepare_kernel<<<1, SORT_PREP_TPB, sizeof(u32) * SORT_PREP_WINDOW * (SORT_PREP_TPB / 32), st>>>(a, L.max_tiles);
     LAUNCH_CHECK("sort_prepare_kernel");
     b200seg_stage(4, st);
     // peer masks by MATCH.ANY cost ~ the number of distinct digits in the warp: a win only for the top digit, where
