@@ -26,6 +26,9 @@
 #define SORT_MAX_BINS 1024
 #define SORT_PASSES 3
 #define SORT_RUN_WINDOW 1024                 // run-prefix entries staged in shared memory per tile
+#ifndef SORT_SCATTER_MINB
+#define SORT_SCATTER_MINB 3                  // resident scatter CTAs per SM the register budget is cut for
+#endif
 
 struct SortArgs {
     u32* keys[2];
@@ -354,9 +357,8 @@ struct ScatterSmem {
     unsigned short cnt[SORT_WARPS][SORT_CNT_STRIDE];     // per-warp digit counters -> exclusive offsets across warps
     unsigned short binexcl[SORT_MAX_BINS];               // exclusive prefix of the tile's bin totals
     u32 binoff[SORT_MAX_BINS];                           // global position of local sorted index i in bin d: binoff[d] + i
-    u32 keys[SORT_TILE];
-    u32 vals[SORT_TILE];
-    u32 win[SORT_RUN_WINDOW + 1];
+    u32 keys[SORT_TILE];                                 // (the run-prefix window of a gathered pass-0 tile aliases keys:
+    u32 vals[SORT_TILE];                                 //  it is dead once the tile is in registers)
     u32 warp_sum[SORT_WARPS];
 };
 
@@ -389,7 +391,7 @@ __device__ __forceinline__ void rank_rows(ScatterSmem& S, const u32 (&key)[SORT_
 // lanes of a warp write consecutive addresses within each digit bin (a fully scattered 4-byte store costs the LSU
 // one wavefront per lane).
 template <bool USE_MATCH>
-__global__ void __launch_bounds__(SORT_TPB, 3) sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
+__global__ void __launch_bounds__(SORT_TPB, SORT_SCATTER_MINB) sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(SORT_TPB, 3) sort_scatter_kernel(SortArgs a, i
             uint2* z = reinterpret_cast<uint2*>(&S.cnt[0][0]);
             for (u32 i = tid; i < sizeof(S.cnt) / 8; i += SORT_TPB) z[i] = make_uint2(0, 0);
         }
-        const TileSrc T = tile_src_setup(a, pass, t, seg, off, S.win);
+        const TileSrc T = tile_src_setup(a, pass, t, seg, off, S.keys);
         __syncthreads();
 
         u32 key[SORT_KPT], val[SORT_KPT], rnk[SORT_KPT];
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(SORT_TPB, 3) sort_scatter_kernel(SortArgs a, i
 #pragma unroll
             for (int k = 0; k < SORT_KPT; ++k) {
                 const u32 idx = wbase + k * 32;
-                const size_t src = idx < n ? tile_src_index(T, S.win, idx, cur) : 0;
+                const size_t src = idx < n ? tile_src_index(T, S.keys, idx, cur) : 0;
                 key[k] = idx < n ? T.keys[src] : 0xFFFFFFFFu;
                 val[k] = idx < n ? T.vals[src] : 0u;
             }
@@ -548,7 +550,7 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     const int match_mode = b200seg_tuning().sort_match;
     const int sms = b200seg_sm_count();
     const u32 cgrid = L.max_tiles < (u32)sms * 8 ? L.max_tiles : (u32)sms * 8;
-    const u32 sgrid = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;
+    const u32 sgrid = L.max_tiles < (u32)sms * SORT_SCATTER_MINB ? L.max_tiles : (u32)sms * SORT_SCATTER_MINB;
     for (int p = 0; p < SORT_PASSES; ++p) {
         sort_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_count_kernel");
