@@ -118,15 +118,16 @@ __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a,
             const int g = seg / C, c = seg - g * C;
             u32* out = a.run_prefix_w + (size_t)seg * (n_runs + 1);
             u32 carry = 0;
-            for (int base = 0; base < n_runs; base += 1024) {             // 32 independent loads per lane, then the scans
-                u32 x[32];
+            for (int base = 0; base < n_runs; base += 256) {              // 8 independent loads per lane, then the scans
+                u32 x[8];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     const int r = base + i * 32 + lane;
                     x[i] = r < n_runs ? a.run_cnt[((size_t)g * n_runs + r) * C + c] : 0;
                 }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 8; ++i) {
+                    if (base + i * 32 >= n_runs) break;     // warp-uniform
                     const int r = base + i * 32 + lane;
                     u32 v = x[i];
 #pragma unroll
