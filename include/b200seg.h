@@ -39,6 +39,7 @@ extern "C" {
 /* negative return codes */
 #define B200SEG_E_INVALID (-1)   /* bad argument (null pointer, size out of range, unknown dtype) */
 #define B200SEG_E_WORKSPACE (-2) /* workspace too small or misaligned */
+#define B200SEG_E_UNSUPPORTED (-3) /* valid request that this entry point does not cover (see its comment) */
 
 /* bits of the device-side status word (`status`, int32, OR-ed into by kernels; caller zeroes it) */
 #define B200SEG_STATUS_LABEL_OOB 1 /* a label outside [0, C) other than drop_label reached the confusion matrix
@@ -84,6 +85,38 @@ int b200seg_lovasz_backward(const float* logits, const void* labels, int32_t lab
                             int32_t per_image, int64_t filter_label, int32_t keep_absent, uint32_t class_mask,
                             const void* workspace, size_t workspace_bytes,
                             const float* grad_out, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Lovasz-Softmax + cross entropy in one pass  --  replaces the pair LossWrapper evaluates on the same logits
+ *   reference: losses/LossWrapper.py:17-24 (nn.CrossEntropyLoss(ignore_index = 17 | 25 | -100)), :43-73
+ *              (loss = sum_k w_k * loss_k over {'CrossEntropyLoss', 'LovaszSoftmax'})
+ *
+ * Same arguments as b200seg_lovasz_forward / _backward plus:
+ *   ce_ignore_index   pixels with this label do not enter the cross entropy (B200SEG_NO_LABEL = none);
+ *                     any other label outside [0, C) sets B200SEG_STATUS_LABEL_OOB (torch raises there)
+ *   ce_out[0]         (device, fp32) <- mean over the non-ignored pixels of -log softmax(logits)[label]
+ *                     (NaN when every pixel is ignored, like torch)
+ *   grad_lovasz, grad_ce   DEVICE scalars: dlogits <- grad_lovasz * dLovasz/dlogits + grad_ce * dCE/dlogits
+ * The cross entropy shares the softmax max / denominator of the first kernel and its gradient rides in the backward
+ * kernel's single pass over the logits: no extra HBM traffic.  Only the pipelined kernels carry it
+ * (b200seg_lovasz_ce_supported: C in {8, 17, 25}, plane % 16 == 0, 16-byte aligned tensors, `status` required);
+ * otherwise B200SEG_E_UNSUPPORTED and the caller evaluates the cross entropy separately.  Also unsupported:
+ * filter_label naming a real class that the cross entropy keeps.
+ * ------------------------------------------------------------------------------------------------ */
+int b200seg_lovasz_ce_supported(const float* logits, const void* labels, int32_t label_dtype,
+                                int32_t n_images, int32_t n_classes, int64_t plane, const float* dlogits);
+int b200seg_lovasz_ce_forward(const float* logits, const void* labels, int32_t label_dtype,
+                              int32_t n_images, int32_t n_classes, int64_t plane,
+                              int32_t per_image, int64_t filter_label, int32_t keep_absent, uint32_t class_mask,
+                              int32_t need_grad, void* workspace, size_t workspace_bytes,
+                              float* loss_out, int64_t ce_ignore_index, float* ce_out,
+                              int64_t* cm, int64_t cm_drop_label, int32_t* status, void* stream);
+int b200seg_lovasz_ce_backward(const float* logits, const void* labels, int32_t label_dtype,
+                               int32_t n_images, int32_t n_classes, int64_t plane,
+                               int32_t per_image, int64_t filter_label, int32_t keep_absent, uint32_t class_mask,
+                               const void* workspace, size_t workspace_bytes,
+                               const float* grad_lovasz, int64_t ce_ignore_index, const float* grad_ce,
+                               float* dlogits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Confusion matrix  --  replaces t_get_confusion_matrix
@@ -156,6 +189,10 @@ int b200seg_set_tuning(const char* key, int32_t value);
  * b200seg_lovasz_forward leaves behind against a straightforward softmax / top-k. */
 int b200seg_debug_layout(int32_t n_images, int32_t n_classes, int64_t plane, int32_t per_image,
                          size_t* offsets, int32_t n_offsets);
+
+/* Test hook: *mismatches (device int32, caller-zeroed) += number of x[i] for which the exponential the stats kernel
+ * uses (expf()'s instruction sequence with two constants held in registers) differs from expf(x[i]) in any bit. */
+int b200seg_debug_exp_mismatches(const float* x, int32_t n, int32_t* mismatches, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,8 @@
 #define BWD_TPB 128
 #define JAC_TPB SORT_TPB
 
-enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_JTICKET = 27, CTRL_GEO = 32 };
+enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_JTICKET = 27, CTRL_GEO = 32,
+       CTRL_CE_SUM = 40 /* double */, CTRL_CE_CNT = 42, CTRL_CE_INV_N = 43 };
 enum { EMIT_PATH_STREAM = 0, EMIT_PATH_RECORDS = 1 };
 
 struct LovaszParams {
@@ -44,6 +45,12 @@ struct LovaszParams {
     float *seg_thr, *seg_logthr, *seg_w;
     float* grp_tmin;                    // [groups] smallest threshold among the group's summed classes
     unsigned char* seg_order;           // [groups][C] classes of the group by ascending threshold
+    // fused cross-entropy term (nn.CrossEntropyLoss(ignore_index), mean over the non-ignored pixels; LossWrapper.py:17-24)
+    int ce_enabled, has_ce_ignore, ce_ignore;
+    double* ce_sum;                     // sum over valid pixels of -log p_label
+    u32* ce_cnt;                        // valid pixels
+    float* ce_inv_n;                    // 1 / ce_cnt for the backward pass
+    float* ce_out;                      // caller's scalar
     int have_records;                   // stats_kernel_async ran: rec16 / rec4 are valid
     int emit_force;                     // 0 = decide on the device, 1 = record path, 2 = streaming path (B200SEG_EMIT_PATH)
     float *pix_m, *pix_s, *gown, *gbg;
@@ -415,7 +422,10 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
     };
 
     int cur_g = -1, stage = 0, pstage = STAGES - 1;
-    u32 nvalid = 0, oob = 0;
+    u32 nvalid = 0, oob = 0, ce_n = 0, ce_oob = 0;
+    float ce_acc = 0.f;
+    ExpConsts ek;
+    ek.load();
     for (u32 t = t0; t < t1; t += step) {
         __syncwarp();                                     // every lane is done reading the stage about to be refilled
         prefetch_next(pstage);
@@ -451,7 +461,7 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
         int b1 = -1, b2 = -1, b3 = -1;
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
-            const float e = sm_exp(z[c], m);
+            const float e = sm_exp_k(z[c], m, ek);
             s = __fadd_rn(s, e);
             int v = (int)__byte_perm(__float_as_uint(e), (u32)c, 0x3214);   // low byte <- class (one PRMT)
             v = (c == lab) ? -1 : v;
@@ -493,8 +503,19 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
                 atomicAdd(&s_cm[arg * CT + lab], 1u);
             } else oob = 1;
         }
+        if (p.ce_enabled && !(p.has_ce_ignore && lab == p.ce_ignore)) {
+            // -log softmax(z)[label] = max + log(sum) - z_label        (log_softmax + nll_loss of nn.CrossEntropyLoss)
+            if ((unsigned)lab < (unsigned)CT) { ce_acc += (m + logf(s)) - T[lab][lane]; ++ce_n; }
+            else ce_oob = 1;                               // torch raises on such a target
+        }
     }
     cp_async_wait<0>();
+    if (p.ce_enabled) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ce_acc += __shfl_xor_sync(FULL_MASK, ce_acc, o); ce_n += __shfl_xor_sync(FULL_MASK, ce_n, o); }
+        if (lane == 0 && ce_n) { atomicAdd(p.ce_sum, (double)ce_acc); atomicAdd(p.ce_cnt, ce_n); }
+        if (__any_sync(FULL_MASK, ce_oob) && lane == 0 && p.status) atomicOr(p.status, STATUS_LABEL_OOB);
+    }
     if (cur_g >= 0 && p.per_image) { flush_group(cur_g, nvalid); nvalid = 0; }
     // flat mode: combine the CTA's warps first (one global atomic per class and CTA)
     if (oob) s_oob = 1;
@@ -566,7 +587,14 @@ __global__ void __launch_bounds__(DECIDE_TPB) finalize_decide_kernel(LovaszParam
     __shared__ u32 s_slow, s_n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool flat = p.groups == 1;
-    if (blockIdx.x == 0 && tid == 0) *p.geo = p.geo_stream;       // default; the deciding block may override it
+    if (blockIdx.x == 0 && tid == 0) {
+        *p.geo = p.geo_stream;                                    // default; the deciding block may override it
+        if (p.ce_enabled) {                                       // mean over the non-ignored pixels (0 / 0 = NaN, like torch)
+            const u32 n = *p.ce_cnt;
+            *p.ce_out = (float)(*p.ce_sum / (double)n);
+            *p.ce_inv_n = n ? 1.0f / (float)n : 0.f;
+        }
+    }
     if (tid == 0) { s_slow = 0; s_n = 0; }
     u32 slow = 0, n = 0;
     for (int g = flat ? 0 : blockIdx.x; g < p.groups; g += gridDim.x) {
@@ -1456,6 +1484,7 @@ struct BwdStage {
 };
 template <int CT, int TPB>
 __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, const float* __restrict__ go,
+                                                             const float* __restrict__ go_ce,
                                                              float* __restrict__ dlogits) {
     using W = WarpTile<CT, 1>;
     using Stage = BwdStage<CT>;
@@ -1473,6 +1502,8 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
     const u32 t1 = p.interleave ? nwt : (u32)((u64)nwt * (gw + 1) / nwarps);
     if (t0 >= t1) return;
     const float gsc = __ldg(go);
+    // fused cross-entropy term: d/dz_k = go_ce * (p_k - [k == label]) / n_valid on the non-ignored pixels
+    const float gce = (p.ce_enabled && go_ce) ? __ldg(go_ce) * *p.ce_inv_n : 0.f;
     const size_t plane = (size_t)p.HW;
 
     // (image, tile-in-image) cursors advance by increments: no integer division per tile
@@ -1547,6 +1578,8 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
         float* dp = dlogits + off;
         const bool filt = l8 == LAB8_FILTERED;
         int lab = l8 < (u32)CT ? (int)l8 : -1;
+        const float gcp = (lab >= 0 && !(p.has_ce_ignore && lab == p.ce_ignore)) ? gce : 0.f;   // CE weight of this pixel
+        const int ce_lab = lab;
         if (lab >= 0 && !thr_active(s_thr[warp][lab])) lab = -1;   // class not summed: no own-class term
         // dot = sum_j g_j p_j over the pixel's candidates (background candidates ascending, then the own class)
         float d = 0.f, pk1 = 0.f, pk2 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -1568,9 +1601,10 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
         if (lab >= 0) {
             const float pown = sm_prob(T[lab][lane], m, s);
             d += gl * pown;
-            ownv = gsc * pown * (gl - d);                  // exact value of the own class
+            ownv = gsc * pown * (gl - d) + gcp * (pown - 1.0f);     // exact value of the own class
         }
-        const float nd = filt ? 0.f : -gsc * d * __fdiv_rn(1.0f, s);
+        const float inv_s = __fdiv_rn(1.0f, s);
+        const float nd = (filt ? 0.f : -gsc * d * inv_s) + gcp * inv_s;
         // every class gets -go * p_k * dot with the fast exponential, the own class takes its exact value ...
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
@@ -1587,10 +1621,12 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
                 float gk, pk;
                 if (i == 0) { gk = g1; pk = pk1; } else if (i == 1) { gk = g2; pk = pk2; }
                 else { gk = gb[(size_t)c * plane]; pk = sm_prob(T[c][lane], m, s); }
-                dp[(size_t)c * plane] = gsc * pk * (gk - d);
+                dp[(size_t)c * plane] = gsc * pk * (gk - d) + gcp * pk;
                 ++i;
             }
         }
+        // cross-entropy only: the label's class is not summed by the Lovasz term, its "- 1" was not applied above
+        if (gcp != 0.f && lab < 0) dp[(size_t)ce_lab * plane] = nd * __expf(T[ce_lab][lane] - m) - gcp;
     }
     cp_async_wait<0>();
 }
@@ -1690,6 +1726,9 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.rec16 = (uint4*)(ws + L.rec16); p.rec4 = (u32*)(ws + L.rec4);
     p.flags = p.ctrl + CTRL_FLAGS;
     p.geo = reinterpret_cast<EmitGeomDev*>(p.ctrl + CTRL_GEO);
+    p.ce_enabled = 0; p.has_ce_ignore = 0; p.ce_ignore = 0; p.ce_out = nullptr;
+    p.ce_sum = reinterpret_cast<double*>(p.ctrl + CTRL_CE_SUM); p.ce_cnt = p.ctrl + CTRL_CE_CNT;
+    p.ce_inv_n = reinterpret_cast<float*>(p.ctrl + CTRL_CE_INV_N);
     p.run_cnt = (u32*)(ws + L.run_cnt); p.run_prefix = (u32*)(ws + L.run_prefix);
     p.geo_stream = EmitGeomDev{0, 0, 0, 0}; p.geo_rec = EmitGeomDev{0, 0, 0, 0};
     p.keysA = (u32*)(ws + L.keysA); p.valsA = (u32*)(ws + L.valsA);
@@ -1724,16 +1763,42 @@ extern "C" int b200seg_lovasz_workspace_bytes(int32_t n, int32_t c, int64_t hw, 
     return 0;
 }
 
-extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
-                                      int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
-                                      int32_t keep_absent, uint32_t class_mask, int32_t need_grad, void* workspace,
-                                      size_t workspace_bytes, float* loss_out, int64_t* cm, int64_t cm_drop_label,
-                                      int32_t* status, void* stream) {
+// the pipelined kernels (the only ones that carry the fused cross-entropy term) cover this call
+static bool pipelined_ok(const float* logits, const void* labels, int label_dtype, int32_t c, int64_t hw) {
+    return vec4_ok(logits, labels, label_dtype, hw) && (c == 8 || c == 17 || c == 25) && hw % 16 == 0 && aligned16(labels) &&
+           b200seg_tuning().stats_variant != 1;
+}
+
+extern "C" int b200seg_lovasz_ce_supported(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
+                                           int32_t c, int64_t hw, const float* dlogits) {
+    if (check_shape(n, c, hw) != 0 || (long long)n * hw == 0) return 0;
+    return pipelined_ok(logits, labels, label_dtype, c, hw) && (!dlogits || aligned16(dlogits)) ? 1 : 0;
+}
+
+static int lovasz_forward_impl(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
+                               int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
+                               int32_t keep_absent, uint32_t class_mask, int32_t need_grad, void* workspace,
+                               size_t workspace_bytes, float* loss_out, int64_t* cm, int64_t cm_drop_label,
+                               int32_t* status, void* stream, bool ce_enabled, int64_t ce_ignore, float* ce_out) {
     if (int rc = check_shape(n, c, hw)) return rc;
     if (!loss_out) { b200seg_set_error("loss_out is NULL"); return B200SEG_E_INVALID; }
-    if ((long long)n * hw == 0) {      // empty batch: nothing to read, loss 0
+    if ((long long)n * hw == 0) {      // empty batch: nothing to read, loss 0 (cross entropy of nothing: NaN, like torch)
         CUDA_TRY(cudaMemsetAsync(loss_out, 0, sizeof(float), (cudaStream_t)stream));
+        if (ce_enabled) CUDA_TRY(cudaMemsetAsync(ce_out, 0xFF, sizeof(float), (cudaStream_t)stream));
         return 0;
+    }
+    if (ce_enabled) {
+        if (!ce_out || !status) { b200seg_set_error("ce_out / status is NULL"); return B200SEG_E_INVALID; }
+        if (!pipelined_ok(logits, labels, label_dtype, c, hw)) {
+            b200seg_set_error("the fused cross-entropy term needs the pipelined kernels (C in {8,17,25}, plane %% 16 == 0, "
+                              "16-byte aligned tensors): ask b200seg_lovasz_ce_supported first");
+            return B200SEG_E_UNSUPPORTED;
+        }
+        // with classes_to_ignore the compact label loses the class of the removed pixels: only the usual case is fused
+        if (filter_label != B200SEG_NO_LABEL && filter_label >= 0 && filter_label < c && filter_label != ce_ignore) {
+            b200seg_set_error("fused cross entropy: classes_to_ignore names a real class that the cross entropy keeps");
+            return B200SEG_E_UNSUPPORTED;
+        }
     }
     if (!logits || !labels || !workspace || (cm && !status)) {
         b200seg_set_error("null pointer argument");
@@ -1751,6 +1816,10 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     p.loss_out = loss_out;
     p.need_grad = need_grad ? 1 : 0;
     p.dbg = b200seg_tuning().dbg;
+    p.ce_enabled = ce_enabled ? 1 : 0;
+    p.has_ce_ignore = (ce_enabled && ce_ignore >= INT_MIN && ce_ignore <= INT_MAX) ? 1 : 0;
+    p.ce_ignore = p.has_ce_ignore ? (int)ce_ignore : 0;
+    p.ce_out = ce_out;
     p.cm = (unsigned long long*)cm;
     p.has_drop = (cm_drop_label != B200SEG_NO_LABEL && cm_drop_label >= INT_MIN && cm_drop_label <= INT_MAX) ? 1 : 0;
     p.drop = p.has_drop ? (int)cm_drop_label : 0;
@@ -1878,10 +1947,31 @@ extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, i
     return 0;
 }
 
-extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
-                                       int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
-                                       int32_t keep_absent, uint32_t class_mask, const void* workspace,
-                                       size_t workspace_bytes, const float* grad_out, float* dlogits, void* stream) {
+extern "C" int b200seg_lovasz_forward(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
+                                      int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
+                                      int32_t keep_absent, uint32_t class_mask, int32_t need_grad, void* workspace,
+                                      size_t workspace_bytes, float* loss_out, int64_t* cm, int64_t cm_drop_label,
+                                      int32_t* status, void* stream) {
+    return lovasz_forward_impl(logits, labels, label_dtype, n, c, hw, per_image, filter_label, keep_absent, class_mask,
+                               need_grad, workspace, workspace_bytes, loss_out, cm, cm_drop_label, status, stream,
+                               false, B200SEG_NO_LABEL, nullptr);
+}
+
+extern "C" int b200seg_lovasz_ce_forward(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
+                                         int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
+                                         int32_t keep_absent, uint32_t class_mask, int32_t need_grad, void* workspace,
+                                         size_t workspace_bytes, float* loss_out, int64_t ce_ignore_index, float* ce_out,
+                                         int64_t* cm, int64_t cm_drop_label, int32_t* status, void* stream) {
+    return lovasz_forward_impl(logits, labels, label_dtype, n, c, hw, per_image, filter_label, keep_absent, class_mask,
+                               need_grad, workspace, workspace_bytes, loss_out, cm, cm_drop_label, status, stream,
+                               true, ce_ignore_index, ce_out);
+}
+
+static int lovasz_backward_impl(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
+                                int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
+                                int32_t keep_absent, uint32_t class_mask, const void* workspace,
+                                size_t workspace_bytes, const float* grad_out, float* dlogits, void* stream,
+                                bool ce_enabled, int64_t ce_ignore, const float* grad_ce) {
     if (int rc = check_shape(n, c, hw)) return rc;
     if ((long long)n * hw == 0) return 0;
     if (!logits || !labels || !workspace || !grad_out || !dlogits) {
@@ -1898,9 +1988,16 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
     fill_params(p, L, (char*)const_cast<void*>(workspace), logits, labels, n, c, hw, per_image, filter_label,
                 keep_absent, class_mask);
     if (p.P == 0) return 0;
+    p.ce_enabled = ce_enabled ? 1 : 0;
+    p.has_ce_ignore = (ce_enabled && ce_ignore >= INT_MIN && ce_ignore <= INT_MAX) ? 1 : 0;
+    p.ce_ignore = p.has_ce_ignore ? (int)ce_ignore : 0;
     const int sms = b200seg_sm_count();
     const bool v4 = vec4_ok(logits, labels, label_dtype, hw) && aligned16(dlogits);
     const bool pipe_ok = v4 && hw % 16 == 0 && (c == 8 || c == 17 || c == 25);
+    if (ce_enabled && !pipe_ok) {
+        b200seg_set_error("the fused cross-entropy term needs the pipelined backward kernel (see b200seg_lovasz_ce_supported)");
+        return B200SEG_E_UNSUPPORTED;
+    }
     b200seg_stage(9, st);
     if (pipe_ok) {
 #define LAUNCH_BWD_ASYNC(CC, TT)                                                                                 \
@@ -1911,7 +2008,7 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
         int per_sm = (int)((224 * 1024) / (smem + 2048));                                                        \
         if (per_sm < 1) per_sm = 1;                                                                              \
         if (per_sm * TT > 2048) per_sm = 2048 / TT;                                                              \
-        backward_kernel_async<CC, TT><<<sms * per_sm, TT, smem, st>>>(p, grad_out, dlogits);                     \
+        backward_kernel_async<CC, TT><<<sms * per_sm, TT, smem, st>>>(p, grad_out, grad_ce, dlogits);                     \
     }
         if (c == 8) LAUNCH_BWD_ASYNC(8, 128)
         else if (c == 17) LAUNCH_BWD_ASYNC(17, 128)
@@ -1932,6 +2029,24 @@ extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, 
     return 0;
 }
 
+extern "C" int b200seg_lovasz_backward(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
+                                       int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
+                                       int32_t keep_absent, uint32_t class_mask, const void* workspace,
+                                       size_t workspace_bytes, const float* grad_out, float* dlogits, void* stream) {
+    return lovasz_backward_impl(logits, labels, label_dtype, n, c, hw, per_image, filter_label, keep_absent, class_mask,
+                                workspace, workspace_bytes, grad_out, dlogits, stream, false, B200SEG_NO_LABEL, nullptr);
+}
+
+extern "C" int b200seg_lovasz_ce_backward(const float* logits, const void* labels, int32_t label_dtype, int32_t n,
+                                          int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
+                                          int32_t keep_absent, uint32_t class_mask, const void* workspace,
+                                          size_t workspace_bytes, const float* grad_lovasz, int64_t ce_ignore_index,
+                                          const float* grad_ce, float* dlogits, void* stream) {
+    if (!grad_ce) { b200seg_set_error("grad_ce is NULL"); return B200SEG_E_INVALID; }
+    return lovasz_backward_impl(logits, labels, label_dtype, n, c, hw, per_image, filter_label, keep_absent, class_mask,
+                                workspace, workspace_bytes, grad_lovasz, dlogits, stream, true, ce_ignore_index, grad_ce);
+}
+
 // ---- test hook: byte offsets of a few workspace regions (tests inspect the per-pixel records) -----------------------
 extern "C" int b200seg_debug_layout(int32_t n, int32_t c, int64_t hw, int32_t per_image, size_t* offsets, int32_t n_offsets) {
     if (!offsets || n_offsets < 8) { b200seg_set_error("need room for 8 offsets"); return B200SEG_E_INVALID; }
@@ -1939,6 +2054,22 @@ extern "C" int b200seg_debug_layout(int32_t n, int32_t c, int64_t hw, int32_t pe
     const LovaszLayout L = lovasz_layout(n, c, hw, per_image);
     offsets[0] = L.pix_m; offsets[1] = L.pix_s; offsets[2] = L.lab8; offsets[3] = L.cmask;
     offsets[4] = L.rec16; offsets[5] = L.rec4; offsets[6] = L.seg_thr; offsets[7] = L.grp_tmin;
+    return 0;
+}
+
+// ---- test hook: the register-constant exponential against expf(), bit for bit -------------------------------------------
+__global__ void exp_check_kernel(const float* __restrict__ x, int n, int* __restrict__ mismatches) {
+    ExpConsts k;
+    k.load();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float a = sm_exp_k(x[i], 0.f, k), b = expf(__fsub_rn(x[i], 0.f));
+        if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) atomicAdd(mismatches, 1);
+    }
+}
+extern "C" int b200seg_debug_exp_mismatches(const float* x, int32_t n, int32_t* mismatches, void* stream) {
+    if (!x || !mismatches || n < 0) { b200seg_set_error("invalid argument"); return B200SEG_E_INVALID; }
+    exp_check_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(x, n, mismatches);
+    LAUNCH_CHECK("exp_check_kernel");
     return 0;
 }
 

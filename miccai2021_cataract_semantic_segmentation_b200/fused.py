@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from . import _native
 from .class_info import CLASS_INFO
-from .lovasz import _PRESENT, _resolve_classes, lovasz_softmax
+from .lovasz import LovaszSoftmax, _PRESENT, _resolve_classes, lovasz_softmax, lovasz_softmax_ce
 from .metrics import (accumulate_confusion_matrix, confusion_drop_label, metrics_summary,
                       raise_if_label_out_of_range)
 
@@ -73,3 +73,88 @@ class LovaszSoftmaxWithMetrics(nn.Module):
         return lovasz_softmax(prediction, target, self.per_image, self.classes_to_ignore, keep_absent, mask,
                               confusion=self.meter.cm, confusion_drop_label=self.meter.drop_label,
                               status=self.meter.status)
+
+
+def ce_ignore_index(experiment: int) -> int:
+    """ignore_index LossWrapper gives nn.CrossEntropyLoss (losses/LossWrapper.py:18-24)."""
+    return {2: 17, 3: 25}.get(experiment, -100)
+
+
+class LovaszSoftmaxCE(nn.Module):
+    """``forward(prediction, target) -> (lovasz, cross_entropy)``: the two losses the reference's ``LossWrapper``
+    evaluates on the same logits (losses/LossWrapper.py:43-73), from one pass over them.
+    Same config keys as ``LovaszSoftmax``; the cross entropy ignores label 17 / 25 for experiments 2 / 3.
+    With a ``SegmentationMeter`` the confusion matrix is accumulated in the same pass as well."""
+
+    def __init__(self, config, meter: SegmentationMeter | None = None):
+        super().__init__()
+        self.experiment = config['experiment']
+        self.per_image = config.get('per_image', False)
+        self.classes_to_ignore = config.get('classes_to_ignore', None)
+        self.classes_to_consider = config.get('classes_to_consider', _PRESENT)
+        self.ignore_index = ce_ignore_index(self.experiment)
+        self.meter = meter
+
+    def forward(self, prediction: torch.Tensor, target: torch.Tensor):
+        keep_absent, mask = _resolve_classes(self.classes_to_consider, prediction.shape[1])
+        kw = {}
+        if self.meter is not None:
+            kw = dict(confusion=self.meter.cm, confusion_drop_label=self.meter.drop_label, status=self.meter.status)
+        return lovasz_softmax_ce(prediction, target, self.ignore_index, self.per_image, self.classes_to_ignore,
+                                 keep_absent, mask, **kw)
+
+
+class LossWrapper(nn.Module):
+    """Stand-alone ``LossWrapper`` (losses/LossWrapper.py:8-74) for the loss pair on the hot path:
+    ``config['losses']`` may name ``'CrossEntropyLoss'`` and / or ``'LovaszSoftmax'`` with their weights; both are
+    evaluated by one fused pass.  Other loss classes belong to the reference: use ``install(fuse_ce=True)``, which
+    derives from the reference's own class and only takes over this pair.  Same constructor keys (``losses``,
+    ``device``, ``experiment``, optional ``dc_off_at_epoch``), same ``forward`` signature, ``loss_vals`` and
+    ``info_string`` attributes."""
+
+    def __init__(self, config: dict):
+        super().__init__()
+        self.config = config
+        self.loss_weightings = config['losses']
+        unknown = [k for k in self.loss_weightings if k not in ('CrossEntropyLoss', 'LovaszSoftmax')]
+        if unknown:
+            raise NotImplementedError(f"losses {unknown} are outside the accelerated path: use the reference's "
+                                      "LossWrapper with miccai2021_cataract_semantic_segmentation_b200.install(fuse_ce=True)")
+        self.device = config.get('device', 'cuda')
+        self.total_loss = None
+        self.loss_vals = {k: 0 for k in self.loss_weightings}
+        self.info_string = ', '.join(self.loss_weightings)
+        self.dc_off = 'dc_off_at_epoch' in config
+        self.pair = LovaszSoftmaxCE(config)
+        self.lovasz = LovaszSoftmax(config)
+        self.ignore_index = ce_ignore_index(config['experiment'])
+
+    def forward(self, deep_features, prediction, labels, loss_list=None, interm_prediction=None, epoch=None):
+        return fused_pair_forward(self, prediction, labels, loss_list, epoch)
+
+
+def fused_pair_forward(wrapper, prediction, labels, loss_list, epoch, base_total=None):
+    """total = sum of w_k * loss_k over {'CrossEntropyLoss', 'LovaszSoftmax'} in ``wrapper.loss_weightings`` order
+    (losses/LossWrapper.py:46-73), the pair coming from one fused pass when both are wanted."""
+    names = [k for k in wrapper.loss_weightings if k in ('CrossEntropyLoss', 'LovaszSoftmax')]
+    wanted = [k for k in names if loss_list is None or k in loss_list]
+    lov_on = 'LovaszSoftmax' in wanted and not (wrapper.dc_off and epoch is not None and
+                                                epoch < wrapper.config['dc_off_at_epoch'])
+    ce_on = 'CrossEntropyLoss' in wanted
+    zero = lambda: torch.tensor(0.0, dtype=torch.float, device=prediction.device)
+    lov = ce = None
+    if lov_on and ce_on:
+        lov, ce = wrapper.pair(prediction, labels)
+    elif lov_on:
+        lov = wrapper.lovasz(prediction, labels)
+    elif ce_on:
+        ce = torch.nn.functional.cross_entropy(prediction, labels.long(), ignore_index=wrapper.ignore_index)
+    total = zero() if base_total is None else base_total
+    for k in names:
+        val = (lov if k == 'LovaszSoftmax' else ce)
+        val = zero() if val is None else val
+        val = val * wrapper.loss_weightings[k]
+        wrapper.loss_vals[k] = val
+        total = total + val
+    wrapper.total_loss = total
+    return total

@@ -82,6 +82,85 @@ class _LovaszFunction(torch.autograd.Function):
         return dlogits, None, None, None, None, None, None, None, None
 
 
+class _LovaszCEFunction(torch.autograd.Function):
+    """Lovasz-Softmax and cross entropy of the same logits in one forward and one backward pass
+    (b200seg_lovasz_ce_forward / _backward); returns the two scalars."""
+
+    @staticmethod
+    def forward(ctx, logits, target, per_image, filter_label, keep_absent, class_mask, ce_ignore, cm, cm_drop, status):
+        lib = _native.load()
+        n, c, h, w = logits.shape
+        hw = h * w
+        need_grad = bool(ctx.needs_input_grad[0])
+        nbytes = _native._sz(0)
+        _native.check(lib.b200seg_lovasz_workspace_bytes(n, c, hw, int(per_image), nbytes), "workspace query")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
+        out = torch.empty(2, dtype=torch.float32, device=logits.device)
+        _native.check(lib.b200seg_lovasz_ce_forward(
+            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, hw, int(per_image),
+            filter_label, keep_absent, class_mask, int(need_grad), ws.data_ptr(), ws.numel(), out.data_ptr(),
+            ce_ignore, out.data_ptr() + 4, cm.data_ptr() if cm is not None else None, cm_drop,
+            status.data_ptr(), _native.stream_ptr(logits.device)), "b200seg_lovasz_ce_forward")
+        if need_grad:
+            ctx.save_for_backward(logits, target, ws)
+            ctx.opts = (int(per_image), filter_label, keep_absent, class_mask, ce_ignore)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, grad_lovasz, grad_ce):
+        logits, target, ws = ctx.saved_tensors
+        per_image, filter_label, keep_absent, class_mask, ce_ignore = ctx.opts
+        lib = _native.load()
+        n, c, h, w = logits.shape
+        zero = torch.zeros((), dtype=torch.float32, device=logits.device)
+        gl = (zero if grad_lovasz is None else grad_lovasz.detach().to(torch.float32)).contiguous()
+        gc = (zero if grad_ce is None else grad_ce.detach().to(torch.float32)).contiguous()
+        dlogits = torch.empty_like(logits)
+        _native.check(lib.b200seg_lovasz_ce_backward(
+            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, per_image, filter_label,
+            keep_absent, class_mask, ws.data_ptr(), ws.numel(), gl.data_ptr(), ce_ignore, gc.data_ptr(),
+            dlogits.data_ptr(), _native.stream_ptr(logits.device)), "b200seg_lovasz_ce_backward")
+        return dlogits, None, None, None, None, None, None, None, None, None
+
+
+def lovasz_softmax_ce(prediction: torch.Tensor, target: torch.Tensor, ce_ignore_index: int | None,
+                      per_image: bool = False, classes_to_ignore=None, keep_absent: int = 0,
+                      class_mask: int | None = None, confusion: torch.Tensor | None = None,
+                      confusion_drop_label: int | None = None, status: torch.Tensor | None = None):
+    """(Lovasz-Softmax, cross entropy) of the same logits, the cross entropy with nn.CrossEntropyLoss(ignore_index)
+    semantics (mean over the non-ignored pixels).  One pass over the logits forward, one backward, whenever the
+    library's pipelined kernels cover the call; otherwise the cross entropy is evaluated by torch on the side."""
+    if prediction.dim() != 4:
+        raise ValueError("prediction must be [N, C, H, W]")
+    _native.require_cuda(prediction, target)
+    n, c, h, w = prediction.shape
+    if tuple(target.shape) != (n, h, w):
+        raise ValueError(f"target shape {tuple(target.shape)} does not match prediction {tuple(prediction.shape)}")
+    logits = prediction if prediction.dtype == torch.float32 else prediction.float()
+    logits = logits.contiguous()
+    target = _native.as_label_tensor(target)
+    if class_mask is None:
+        class_mask = (1 << c) - 1
+    filt = _native.NO_LABEL if classes_to_ignore is None else int(classes_to_ignore)
+    drop = _native.NO_LABEL if confusion_drop_label is None else int(confusion_drop_label)
+    ce_ign = _native.NO_LABEL if ce_ignore_index is None else int(ce_ignore_index)
+    lib = _native.load()
+    fused = n * h * w > 0 and bool(lib.b200seg_lovasz_ce_supported(
+        logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, None))
+    if fused and classes_to_ignore is not None and 0 <= int(classes_to_ignore) < c and int(classes_to_ignore) != ce_ign:
+        fused = False
+    if not fused:
+        lov = lovasz_softmax(prediction, target, per_image, classes_to_ignore, keep_absent, class_mask, confusion,
+                             confusion_drop_label, status)
+        ce = torch.nn.functional.cross_entropy(prediction, target.long(),
+                                               ignore_index=-100 if ce_ignore_index is None else int(ce_ignore_index))
+        return lov, ce
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=logits.device)
+    return _LovaszCEFunction.apply(logits, target, bool(per_image), filt, int(keep_absent), int(class_mask), ce_ign,
+                                   confusion, drop, status)
+
+
 def lovasz_softmax(prediction: torch.Tensor, target: torch.Tensor, per_image: bool = False,
                    classes_to_ignore=None, keep_absent: int = 0, class_mask: int | None = None,
                    confusion: torch.Tensor | None = None, confusion_drop_label: int | None = None,

@@ -276,3 +276,18 @@ def soft_iou(x: torch.Tensor, t: torch.Tensor, epsilon=torch.finfo(torch.float32
     inter = x.mul(t).sum(dim=[-2, -1])
     union = (x.mul(1 - t) + t).sum(dim=[-2, -1])
     return inter / (union + epsilon)
+
+
+def cross_entropy(prediction: torch.Tensor, target: torch.Tensor, experiment: int) -> torch.Tensor:
+    """nn.CrossEntropyLoss(ignore_index = 17 | 25 | -100) as LossWrapper builds it (losses/LossWrapper.py:17-24,61-62)."""
+    ignore = {2: 17, 3: 25}.get(experiment, -100)
+    return torch.nn.functional.cross_entropy(prediction, target.long(), ignore_index=ignore)
+
+
+def loss_wrapper_pair(prediction: torch.Tensor, target: torch.Tensor, experiment: int, w_ce: float, w_lovasz: float,
+                      **lovasz_kw) -> torch.Tensor:
+    """total = w_ce * CrossEntropyLoss + w_lovasz * LovaszSoftmax (losses/LossWrapper.py:43-73, in that order)."""
+    total = torch.zeros((), dtype=torch.float32, device=prediction.device)
+    total = total + cross_entropy(prediction, target, experiment) * w_ce
+    total = total + lovasz_softmax(prediction, target, experiment, **lovasz_kw) * w_lovasz
+    return total

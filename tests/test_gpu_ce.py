@@ -1,0 +1,101 @@
+"""GPU tests (``-m gpu``) of the fused Lovasz-Softmax + cross-entropy pass (reference
+losses/LossWrapper.py:17-24,43-73): total loss and logit gradient against the oracle, the pair against the two
+separate evaluations, the fallback for shapes the pipelined kernels do not cover."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import grad_err, rel_err
+from test_gpu_parity import _blocky, _d1
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, builder, (n, c, h, w), experiment, lovasz config, (w_ce, w_lovasz)
+    ("d1_c25_flat", _d1, (2, 25, 128, 240), 3, {}, (1.0, 1.0)),
+    ("d1_c17_per_image", _d1, (3, 17, 128, 240), 2, {"per_image": True}, (0.7, 1.3)),
+    ("d1_c8_flat", _d1, (2, 8, 128, 240), 1, {}, (1.0, 0.5)),                     # ignore_index = -100: every pixel counts
+    ("d1_c25_filter_ignore", _d1, (2, 25, 96, 192), 3, {"classes_to_ignore": 25}, (1.0, 1.0)),
+    ("d2_c25_flat", _blocky, (2, 25, 128, 240), 3, {}, (2.0, 1.0)),
+    ("d2_c25_list", _blocky, (2, 25, 96, 160), 3, {"classes_to_consider": [0, 1, 2, 7]}, (1.0, 1.0)),   # CE-only classes
+    ("d1_c5_generic", _d1, (2, 5, 64, 96), 1, {}, (1.0, 1.0)),                    # no templated kernel: torch CE on the side
+    ("d1_c25_odd_plane", _d1, (1, 25, 61, 97), 3, {}, (1.0, 1.0)),                # plane % 16 != 0: same fallback
+]
+
+
+@pytest.fixture(scope="module")
+def b200():
+    assert torch.cuda.is_available()
+    import miccai2021_cataract_semantic_segmentation_b200 as pkg
+    from miccai2021_cataract_semantic_segmentation_b200 import _native
+    _native.load()
+    return pkg
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_loss_wrapper_pair_matches_oracle(b200, case):
+    from oracle import port
+    name, builder, (n, c, h, w), exp, extra, (w_ce, w_lov) = case
+    x, y = builder(n, c, h, w, seed=4321 + n * c, with_ignore=exp != 1)
+    cfg = {"losses": {"CrossEntropyLoss": w_ce, "LovaszSoftmax": w_lov}, "experiment": exp, "device": "cuda", **extra}
+    wrapper = b200.LossWrapper(cfg)
+    xd = x.cuda().requires_grad_(True)
+    total = wrapper(None, xd, y.cuda())
+    total.backward()
+    kw = dict(per_image=extra.get("per_image", False), classes_to_ignore=extra.get("classes_to_ignore"),
+              classes_to_consider=extra.get("classes_to_consider", "present"))
+    xr = x.cuda().requires_grad_(True)
+    ref = port.loss_wrapper_pair(xr, y.cuda(), exp, w_ce, w_lov, **kw)
+    ref.backward()
+    assert rel_err(float(total), float(ref)) <= 1e-5
+    assert grad_err(xd.grad.cpu().numpy(), xr.grad.cpu().numpy()) <= 1e-5
+    gmax = float(xr.grad.abs().max())
+    assert np.allclose(xd.grad.cpu().numpy(), xr.grad.cpu().numpy(), rtol=1e-5, atol=1e-5 * gmax)
+    # the weighted parts the reference keeps for logging (LossWrapper.py:71-72)
+    ce_ref = float(port.cross_entropy(x.cuda(), y.cuda(), exp)) * w_ce
+    assert rel_err(float(wrapper.loss_vals["CrossEntropyLoss"]), ce_ref) <= 1e-5
+    assert set(wrapper.loss_vals) == {"CrossEntropyLoss", "LovaszSoftmax"}
+
+
+def test_pair_equals_the_two_separate_evaluations(b200):
+    n, c, h, w, exp = 2, 25, 128, 240, 3
+    x, y = _d1(n, c, h, w, seed=99, with_ignore=True)
+    meter = b200.SegmentationMeter(exp, c)
+    pair = b200.LovaszSoftmaxCE({"experiment": exp}, meter)
+    xd = x.cuda().requires_grad_(True)
+    lov, ce = pair(xd, y.cuda())
+    # Lovasz part alone: same bits as the plain module, forward and backward
+    (g_lov,) = torch.autograd.grad(lov, xd, retain_graph=True)
+    x2 = x.cuda().requires_grad_(True)
+    lov2 = b200.LovaszSoftmax({"experiment": exp})(x2, y.cuda())
+    lov2.backward()
+    assert float(lov) == float(lov2) and torch.equal(g_lov, x2.grad)
+    # cross-entropy part alone against torch
+    (g_ce,) = torch.autograd.grad(ce, xd)
+    x3 = x.cuda().requires_grad_(True)
+    ce3 = torch.nn.functional.cross_entropy(x3, y.cuda(), ignore_index=25)
+    ce3.backward()
+    assert rel_err(float(ce), float(ce3)) <= 1e-6
+    assert float((g_ce - x3.grad).abs().max()) <= 1e-5 * float(x3.grad.abs().max())
+    # the confusion matrix rode along
+    assert torch.equal(meter.cm, b200.t_get_confusion_matrix(x.cuda(), y.cuda()))
+    meter.check()
+
+
+def test_cross_entropy_edge_cases(b200):
+    c, exp = 25, 3
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((1, c, 32, 64), generator=g)
+    pair = b200.LovaszSoftmaxCE({"experiment": exp})
+    # every pixel ignored: torch's mean over nothing is NaN; the Lovasz term has no class present and is 0
+    y = torch.full((1, 32, 64), 25)
+    lov, ce = pair(x.cuda(), y.cuda())
+    assert float(lov) == 0.0 and np.isnan(float(ce))
+    # a label that is neither a class nor the ignore index: torch raises, here the status word is set
+    y = torch.randint(0, c, (1, 32, 64), generator=g)
+    y[0, 3, 5] = 77
+    meter = b200.SegmentationMeter(exp, c)
+    pair_m = b200.LovaszSoftmaxCE({"experiment": exp}, meter)
+    pair_m(x.cuda(), y.cuda())
+    with pytest.raises(RuntimeError):
+        meter.check()

@@ -156,3 +156,20 @@ def test_candidate_records_match_softmax_topk(b200, c, exp):
     bits = torch.stack([(cmask >> k) & 1 for k in range(c)], 1)
     near = ((other - thr.view(1, c)).abs() <= 2e-7).any(1)          # one-ulp disagreements with ATen at the threshold
     assert torch.equal(bits[~near], expect[~near])
+
+
+def test_register_constant_exponential_is_expf_bit_for_bit(b200):
+    """stats_kernel_async forms exp(z - max) with expf()'s own instruction sequence but register-held constants."""
+    from miccai2021_cataract_semantic_segmentation_b200 import _native
+    lib = _native.load()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    parts = [-torch.rand(1 << 22, generator=g, device="cuda") * 110.0,            # the softmax range, past underflow
+             -torch.rand(1 << 20, generator=g, device="cuda") * 1e-3,               # just below zero
+             torch.randn(1 << 20, generator=g, device="cuda") * 50.0,               # both signs, overflow included
+             torch.tensor([0.0, -0.0, -87.3, -88.8, -103.9, -104.1, -1e30, 88.7, 89.0, float("-inf"), float("inf"),
+                           float("nan"), -1e-45, 1e-45], device="cuda")]
+    x = torch.cat(parts).contiguous()
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _native.check(lib.b200seg_debug_exp_mismatches(x.data_ptr(), x.numel(), bad.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream), "exp check")
+    assert int(bad.item()) == 0

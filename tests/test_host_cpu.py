@@ -150,3 +150,53 @@ def test_install_rebinds_names_bound_at_import_time():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_install_fuse_ce_replaces_loss_wrapper_with_a_subclass():
+    """install(fuse_ce=True): managers get a LossWrapper derived from the reference's class; the
+    defining module keeps the original; without the CE + Lovasz pair the subclass defers to the reference forward."""
+    import torch.nn as nn
+    import miccai2021_cataract_semantic_segmentation_b200 as b200
+
+    class RefLossWrapper(nn.Module):                       # the reference's constructor surface (LossWrapper.py:9-31)
+        def __init__(self, config):
+            super().__init__()
+            self.config, self.loss_weightings = config, config['losses']
+            self.loss_classes = {k: object() for k in self.loss_weightings}
+            self.loss_vals = {k: 0 for k in self.loss_weightings}
+            self.dc_off = 'dc_off_at_epoch' in config
+
+        def forward(self, deep_features, prediction, labels, loss_list=None, interm_prediction=None, epoch=None):
+            return ("reference forward", loss_list)
+
+    fake = {name: types.ModuleType(name) for name in ("losses", "losses.LossWrapper", "managers", "managers.EncDec_Manager")}
+    for name in ("losses", "losses.LossWrapper", "managers.EncDec_Manager"):
+        fake[name].LossWrapper = RefLossWrapper
+    saved = {k: sys.modules.get(k) for k in fake}
+    sys.modules.update(fake)
+    try:
+        b200.install(fuse_ce=True)
+        new = fake["managers.EncDec_Manager"].LossWrapper
+        assert new is not RefLossWrapper and issubclass(new, RefLossWrapper) and new.__name__ == "LossWrapper"
+        assert fake["losses"].LossWrapper is new
+        assert fake["losses.LossWrapper"].LossWrapper is RefLossWrapper                # defining module untouched
+        only_ce = new({'losses': {'CrossEntropyLoss': 1.0}, 'experiment': 3, 'device': 'cpu'})
+        assert only_ce(None, None, None) == ("reference forward", None)               # no pair: the reference path
+        both = new({'losses': {'CrossEntropyLoss': 1.0, 'LovaszSoftmax': 0.5}, 'experiment': 3, 'device': 'cpu'})
+        assert isinstance(both.pair, b200.LovaszSoftmaxCE) and both.ignore_index == 25
+        b200.install(fuse_ce=True)                                                     # idempotent
+        assert fake["managers.EncDec_Manager"].LossWrapper is new
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_standalone_loss_wrapper_rejects_losses_outside_the_path():
+    import miccai2021_cataract_semantic_segmentation_b200 as b200
+    with pytest.raises(NotImplementedError):
+        b200.LossWrapper({'losses': {'CrossEntropyLoss': 1.0, 'DenseContrastiveLoss': 0.1}, 'experiment': 3, 'device': 'cpu'})
+    lw = b200.LossWrapper({'losses': {'CrossEntropyLoss': 1.0, 'LovaszSoftmax': 1.0}, 'experiment': 2, 'device': 'cpu'})
+    assert lw.info_string == 'CrossEntropyLoss, LovaszSoftmax' and lw.ignore_index == 17
