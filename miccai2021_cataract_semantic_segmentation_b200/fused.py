@@ -141,7 +141,7 @@ def fused_pair_forward(wrapper, prediction, labels, loss_list, epoch, base_total
     lov_on = 'LovaszSoftmax' in wanted and not (wrapper.dc_off and epoch is not None and
                                                 epoch < wrapper.config['dc_off_at_epoch'])
     ce_on = 'CrossEntropyLoss' in wanted
-    zero = lambda: torch.tensor(0.0, dtype=torch.float, device=prediction.device)
+    zero = lambda: torch.zeros((), dtype=torch.float, device=prediction.device)     # (no host-to-device copy: stays async)
     lov = ce = None
     if lov_on and ce_on:
         lov, ce = wrapper.pair(prediction, labels)
@@ -149,12 +149,15 @@ def fused_pair_forward(wrapper, prediction, labels, loss_list, epoch, base_total
         lov = wrapper.lovasz(prediction, labels)
     elif ce_on:
         ce = torch.nn.functional.cross_entropy(prediction, labels.long(), ignore_index=wrapper.ignore_index)
-    total = zero() if base_total is None else base_total
+    total = base_total
     for k in names:
         val = (lov if k == 'LovaszSoftmax' else ce)
         val = zero() if val is None else val
-        val = val * wrapper.loss_weightings[k]
+        wgt = wrapper.loss_weightings[k]
+        val = val if wgt == 1 else val * wgt
         wrapper.loss_vals[k] = val
-        total = total + val
+        total = val if total is None else total + val
+    if total is None:
+        total = zero()
     wrapper.total_loss = total
     return total

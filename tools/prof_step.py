@@ -17,6 +17,7 @@ ap.add_argument("--per-image", action="store_true")
 ap.add_argument("--blocky", action="store_true")
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--confmat-only", action="store_true")
+ap.add_argument("--ce", action="store_true", help="fused cross entropy + Lovasz pair (LovaszSoftmaxCE)")
 a = ap.parse_args()
 c, exp = a.classes, {8: 1, 17: 2, 25: 3}[a.classes]
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -28,6 +29,7 @@ if a.blocky:
     x = x + 6.0 * torch.nn.functional.one_hot(y, c).permute(0, 3, 1, 2).float()
 meter = b200.SegmentationMeter(exp, c)
 mod = b200.LovaszSoftmaxWithMetrics({"experiment": exp, "per_image": a.per_image}, meter)
+pair = b200.LovaszSoftmaxCE({"experiment": exp, "per_image": a.per_image}, meter)
 xr = x.clone().requires_grad_(True)
 
 
@@ -37,7 +39,11 @@ def step():
         return
     meter.reset()
     xr.grad = None
-    loss = mod(xr, y)
+    if a.ce:
+        lov, ce = pair(xr, y)
+        loss = lov + ce
+    else:
+        loss = mod(xr, y)
     loss.backward()
     meter.summary()
 
