@@ -161,3 +161,62 @@ def fused_pair_forward(wrapper, prediction, labels, loss_list, epoch, base_total
         total = zero()
     wrapper.total_loss = total
     return total
+
+
+def two_heads_forward(loss_final, loss_interm, logits_interm, logits_final, target, w_final, w_interm, side_stream):
+    """loss_final(logits_final, target) * w_final + loss_interm(logits_interm, target) * w_interm
+    (losses/TwoScaleLoss.py:43-52) with the two heads on two CUDA streams: each head is a serial chain of
+    HBM-bound passes and latency-bound sort kernels, so the chains of two independent heads fill each other's gaps.
+    autograd replays each head's backward on the stream its forward ran on."""
+    ph, pw = logits_interm.size(2), logits_interm.size(3)
+    h, w = target.size(1), target.size(2)
+    if ph != h or pw != w:                                  # F.upsample(..., mode='bilinear') of the reference
+        logits_interm = torch.nn.functional.interpolate(logits_interm, size=(h, w), mode='bilinear')
+    if not logits_final.is_cuda or side_stream is None:
+        return loss_final(logits_final, target) * w_final + loss_interm(logits_interm, target) * w_interm
+    cur = torch.cuda.current_stream(logits_final.device)
+    side_stream.wait_stream(cur)
+    with torch.cuda.stream(side_stream):
+        li = loss_interm(logits_interm, target)
+    lf = loss_final(logits_final, target)
+    cur.wait_stream(side_stream)
+    for t in (logits_interm, target):
+        t.record_stream(side_stream)
+    li.record_stream(cur)
+    return lf * w_final + li * w_interm
+
+
+class TwoScaleLoss(nn.Module):
+    """Stand-alone ``TwoScaleLoss`` (losses/TwoScaleLoss.py:8-52) for the Lovasz-Lovasz pair of the published OCRNet
+    configuration (configs/OCRNet_rf_lvsz.json:24-28) and the CE-CE pair: same constructor dict (``interm`` / ``final``
+    with ``name``, ``args``, optional ``weight``; ``experiment``), same ``forward(logits_interm, logits_final, target)``.
+    The two heads run on two CUDA streams (see ``two_heads_forward``)."""
+
+    def __init__(self, config):
+        super().__init__()
+        names = (config['interm']['name'], config['final']['name'])
+        self.w_interm = config['interm'].get('weight', 0.4)
+        self.w_final = config['final'].get('weight', 1.0)
+        self.ignore_label = -100
+        if 'experiment' in config:
+            self.ignore_label = len(CLASS_INFO[config['experiment']][1]) - 1 if config['experiment'] in [2, 3] else -100
+        config['interm'].update({"experiment": config['experiment']})
+        config['final'].update({"experiment": config['experiment']})
+        if names == ('CrossEntropyLoss', 'CrossEntropyLoss'):
+            self.loss_interm = nn.CrossEntropyLoss(*config['interm'].get('args', []), ignore_index=self.ignore_label)
+            self.loss_final = nn.CrossEntropyLoss(*config['final'].get('args', []), ignore_index=self.ignore_label)
+        elif names == ('LovaszSoftmax', 'LovaszSoftmax'):
+            self.loss_interm = LovaszSoftmax(config['interm'])
+            self.loss_final = LovaszSoftmax(config['final'])
+        elif names[0] == names[1]:
+            raise NotImplementedError(f"{names[0]} is outside the accelerated path: use the reference's TwoScaleLoss "
+                                      "after miccai2021_cataract_semantic_segmentation_b200.install()")
+        else:
+            raise NotImplementedError('different losses for interm {} and final {}'.format(config['interm'], config['final']))
+        self._side = None
+
+    def forward(self, logits_interm, logits_final, target):
+        if logits_final.is_cuda and self._side is None:
+            self._side = torch.cuda.Stream(logits_final.device)
+        return two_heads_forward(self.loss_final, self.loss_interm, logits_interm, logits_final, target,
+                                 self.w_final, self.w_interm, self._side)

@@ -56,12 +56,40 @@ def _make_fused_loss_wrapper(ref_cls):
     return LossWrapper
 
 
-def install(packages=("losses", "utils", "managers"), verbose: bool = False, fuse_ce: bool = False):
+def _two_stream_two_scale(ref_cls):
+    """The reference's TwoScaleLoss with its two heads evaluated on two CUDA streams (fused.two_heads_forward)."""
+    if ref_cls in _FUSED_CACHE:
+        return _FUSED_CACHE[ref_cls]
+    import torch
+    from .fused import two_heads_forward
+
+    class TwoScaleLoss(ref_cls):
+        def forward(self, logits_interm, logits_final, target):
+            if not logits_final.is_cuda:
+                return super().forward(logits_interm, logits_final, target)
+            if getattr(self, "_b200_side", None) is None:
+                self._b200_side = torch.cuda.Stream(logits_final.device)
+            return two_heads_forward(self.loss_final, self.loss_interm, logits_interm, logits_final, target,
+                                     self.w_final, self.w_interm, self._b200_side)
+
+    TwoScaleLoss.__qualname__ = TwoScaleLoss.__name__ = "TwoScaleLoss"
+    TwoScaleLoss._b200_fused = True
+    _FUSED_CACHE[ref_cls] = TwoScaleLoss
+    return TwoScaleLoss
+
+
+def install(packages=("losses", "utils", "managers"), verbose: bool = False, fuse_ce: bool = False,
+            two_stream_heads: bool = False):
     """Returns {module_name: [rebound names]}.  ``fuse_ce=True`` additionally replaces ``LossWrapper`` wherever it is
-    bound by a subclass that evaluates its CrossEntropyLoss + LovaszSoftmax pair in one fused pass."""
+    bound by a subclass that evaluates its CrossEntropyLoss + LovaszSoftmax pair in one fused pass (SURVEY.md 8 F1);
+    ``two_stream_heads=True`` replaces ``TwoScaleLoss`` by a subclass that runs its two heads on two CUDA streams."""
     replaced = {}
     table = dict(_LOSS_NAMES)
     table.update(_METRIC_NAMES)
+    if two_stream_heads:
+        ref_ts = getattr(sys.modules.get("losses.TwoScaleLoss"), "TwoScaleLoss", None)
+        if ref_ts is not None and not getattr(ref_ts, "_b200_fused", False):
+            table["TwoScaleLoss"] = _two_stream_two_scale(ref_ts)
     if fuse_ce:
         ref_lw = getattr(sys.modules.get("losses.LossWrapper"), "LossWrapper", None)
         if ref_lw is not None and not getattr(ref_lw, "_b200_fused", False):
@@ -74,7 +102,7 @@ def install(packages=("losses", "utils", "managers"), verbose: bool = False, fus
             continue
         hits = []
         for name, obj in table.items():
-            if name == "LossWrapper" and mod_name == "losses.LossWrapper":
+            if (name, mod_name) in (("LossWrapper", "losses.LossWrapper"), ("TwoScaleLoss", "losses.TwoScaleLoss")):
                 continue                                   # the defining module keeps the reference class
             cur = mod.__dict__.get(name)
             if cur is not None and cur is not obj and callable(cur):

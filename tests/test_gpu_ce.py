@@ -99,3 +99,33 @@ def test_cross_entropy_edge_cases(b200):
     pair_m(x.cuda(), y.cuda())
     with pytest.raises(RuntimeError):
         meter.check()
+
+
+def test_two_scale_loss_two_streams_matches_oracle(b200):
+    """TwoScaleLoss (losses/TwoScaleLoss.py:43-52): the low-resolution intermediate head is upsampled bilinearly, both
+    heads get the same target; here they run on two CUDA streams."""
+    from oracle import port
+    n, c, exp = 2, 25, 3
+    g = torch.Generator().manual_seed(8)
+    x_final = torch.randn((n, c, 64, 128), generator=g)
+    x_interm = torch.randn((n, c, 32, 64), generator=g)                    # upsampled inside forward
+    y = torch.randint(0, c + 1, (n, 64, 128), generator=g)
+    cfg = {"interm": {"name": "LovaszSoftmax", "args": []}, "final": {"name": "LovaszSoftmax", "args": [], "weight": 1.0},
+           "experiment": exp}
+    mod = b200.TwoScaleLoss(cfg)
+    assert mod.w_interm == 0.4 and mod.w_final == 1.0 and mod.ignore_label == 25
+    xf, xi = x_final.cuda().requires_grad_(True), x_interm.cuda().requires_grad_(True)
+    for _ in range(2):                                                      # second round reuses the side stream
+        xf.grad = xi.grad = None
+        loss = mod(xi, xf, y.cuda())
+        loss.backward()
+    rf, ri = x_final.cuda().requires_grad_(True), x_interm.cuda().requires_grad_(True)
+    up = torch.nn.functional.interpolate(ri, size=(64, 128), mode="bilinear")
+    ref = port.lovasz_softmax(rf, y.cuda(), exp) * 1.0 + port.lovasz_softmax(up, y.cuda(), exp) * 0.4
+    ref.backward()
+    assert rel_err(float(loss), float(ref)) <= 1e-5
+    assert grad_err(xf.grad.cpu().numpy(), rf.grad.cpu().numpy()) <= 1e-5
+    assert grad_err(xi.grad.cpu().numpy(), ri.grad.cpu().numpy()) <= 1e-5
+    with pytest.raises(NotImplementedError):
+        b200.TwoScaleLoss({"interm": {"name": "LovaszSoftmax", "args": []}, "final": {"name": "CrossEntropyLoss", "args": []},
+                           "experiment": exp})

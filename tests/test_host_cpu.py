@@ -200,3 +200,31 @@ def test_standalone_loss_wrapper_rejects_losses_outside_the_path():
         b200.LossWrapper({'losses': {'CrossEntropyLoss': 1.0, 'DenseContrastiveLoss': 0.1}, 'experiment': 3, 'device': 'cpu'})
     lw = b200.LossWrapper({'losses': {'CrossEntropyLoss': 1.0, 'LovaszSoftmax': 1.0}, 'experiment': 2, 'device': 'cpu'})
     assert lw.info_string == 'CrossEntropyLoss, LovaszSoftmax' and lw.ignore_index == 17
+
+
+def test_install_two_stream_heads_replaces_two_scale_loss():
+    import torch.nn as nn
+    import miccai2021_cataract_semantic_segmentation_b200 as b200
+
+    class RefTwoScale(nn.Module):
+        def forward(self, logits_interm, logits_final, target):
+            return "reference forward"
+
+    fake = {name: types.ModuleType(name) for name in ("losses", "losses.TwoScaleLoss", "managers", "managers.OCRNet_Manager")}
+    for name in ("losses", "losses.TwoScaleLoss", "managers.OCRNet_Manager"):
+        fake[name].TwoScaleLoss = RefTwoScale
+    saved = {k: sys.modules.get(k) for k in fake}
+    sys.modules.update(fake)
+    try:
+        b200.install(two_stream_heads=True)
+        new = fake["managers.OCRNet_Manager"].TwoScaleLoss
+        assert new is not RefTwoScale and issubclass(new, RefTwoScale) and new.__name__ == "TwoScaleLoss"
+        assert fake["losses.TwoScaleLoss"].TwoScaleLoss is RefTwoScale             # defining module untouched
+        import torch
+        assert new()(torch.zeros(1), torch.zeros(1), torch.zeros(1)) == "reference forward"   # CPU tensors: reference path
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
