@@ -1937,6 +1937,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
     a.tile_desc = (uint4*)(ss + L.sort.tile_desc); a.tile_runs = (uint2*)(ss + L.sort.tile_runs);
     a.seg_done = (u32*)(ss + L.sort.seg_done);
     a.bin_base = (u32*)(ss + L.sort.bin_base); a.tile_fg = (u32*)(ss + L.sort.tile_fg);
+    a.big = (u32*)(ss + L.sort.big); a.chunksum = (u32*)(ss + L.sort.chunksum); a.gbar = (u32*)(ss + L.sort.gbar);
     a.status = p.status;
     if (int rc = sort_enqueue(a, L.sort, st)) return rc;
 
@@ -2108,6 +2109,7 @@ extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint3
     a.tile_desc = (uint4*)(ss + L.tile_desc); a.tile_runs = (uint2*)(ss + L.tile_runs);
     a.seg_done = (u32*)(ss + L.seg_done);
     a.bin_base = (u32*)(ss + L.bin_base); a.tile_fg = (u32*)(ss + L.tile_fg);
+    a.big = (u32*)(ss + L.big); a.chunksum = (u32*)(ss + L.chunksum); a.gbar = (u32*)(ss + L.gbar);
     a.status = status;
     return sort_enqueue(a, L, (cudaStream_t)stream);
 }

@@ -26,6 +26,8 @@
 #define SORT_MAX_BINS 1024
 #define SORT_PASSES 3
 #define SORT_RUN_WINDOW 1024                 // run-prefix entries staged in shared memory per tile
+#define SORT_SCAN_LOCAL_MAX 128               // segments with more tiles are scanned by the whole grid (see sort_big_scan)
+#define SORT_CHUNK 64                        // tiles per chunk of that scan
 #ifndef SORT_SCATTER_MINB
 #define SORT_SCATTER_MINB 3                  // resident scatter CTAs per SM the register budget is cut for
 #endif
@@ -55,11 +57,14 @@ struct SortArgs {
     u32* tilehist;          // [max_tiles][1024]
     u32* bin_base;          // [n_seg][1024]
     u32* tile_fg;           // [max_tiles] foreground flags per tile of the final order (sort_fg_count_kernel)
+    u32* big;               // [1 + n_seg] number of segments with > SORT_SCAN_LOCAL_MAX tiles, then their ids
+    u32* chunksum;          // [max_chunks][1024] per-chunk digit sums -> exclusive chunk offsets (big segments only)
+    u32* gbar;              // [2 * SORT_PASSES] grid-barrier counters of the scatter kernels
     int* status;
 };
 
 struct SortScratch {
-    size_t tile_start, tile_desc, tile_runs, seg_done, tilehist, bin_base, tile_fg, total;
+    size_t tile_start, tile_desc, tile_runs, seg_done, tilehist, bin_base, tile_fg, big, chunksum, gbar, total;
     u32 max_tiles;
 };
 
@@ -73,6 +78,9 @@ static inline SortScratch sort_scratch_layout(int n_seg, long long total_capacit
     L.seg_done = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_PASSES, 256);
     L.bin_base = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_MAX_BINS, 256);
     L.tile_fg = o;    o = align_up(o + sizeof(u32) * (size_t)L.max_tiles, 256);
+    L.big = o;        o = align_up(o + sizeof(u32) * (size_t)(n_seg + 1), 256);
+    L.gbar = o;       o = align_up(o + sizeof(u32) * 2 * SORT_PASSES, 256);
+    L.chunksum = o;   o = align_up(o + sizeof(u32) * ((size_t)L.max_tiles / SORT_CHUNK + n_seg + 2) * SORT_MAX_BINS, 256);
     L.tilehist = o;   o = align_up(o + sizeof(u32) * (size_t)L.max_tiles * SORT_MAX_BINS, 256);
     L.total = o;
     return L;
@@ -164,7 +172,11 @@ __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a,
         __syncthreads();
     }
     const u32 total = s_carry;
-    if (tid == 0) a.tile_start[a.n_seg] = total;
+    if (tid == 0) { a.tile_start[a.n_seg] = total; a.big[0] = 0; }
+    if (tid < 2 * SORT_PASSES) a.gbar[tid] = 0;
+    __syncthreads();
+    for (int sg = tid; sg < a.n_seg; sg += SORT_PREP_TPB)
+        if ((a.seg_count[sg] + SORT_TILE - 1) / SORT_TILE > SORT_SCAN_LOCAL_MAX) a.big[1 + atomicAdd(a.big, 1u)] = (u32)sg;
     for (int i = tid; i < a.n_seg * SORT_PASSES; i += SORT_PREP_TPB) a.seg_done[i] = 0;
     for (u32 i = tid; i < total && i < max_tiles; i += SORT_PREP_TPB) a.tile_fg[i] = 0;
     __syncthreads();
@@ -251,11 +263,11 @@ __device__ __forceinline__ u32 tile_src_cursor(const TileSrc& T) { return T.wind
 // ---- per-segment scan, run by the CTA that counted the segment's last tile ---------------------------------------------
 // column scan over the segment's tiles (tilehist[tile][bin] -> exclusive offset of the tile within the bin) and
 // exclusive scan over the bin totals (-> bin_base).  256 threads, thread b owns bins [4b, 4b+4).
-__device__ __forceinline__ void segment_scan(const SortArgs& a, int seg, u32 t0, u32 t1, u32 nbins, u32* s_warp) {
+__device__ __forceinline__ void segment_scan(const SortArgs& a, u32* rows, int seg, u32 t0, u32 t1, u32 nbins, u32* s_warp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     u32 tot[4] = {0, 0, 0, 0};
     if ((u32)(4 * tid) < nbins) {
-        uint4* col = reinterpret_cast<uint4*>(a.tilehist + (size_t)t0 * SORT_MAX_BINS + 4 * tid);
+        uint4* col = reinterpret_cast<uint4*>(rows + (size_t)t0 * SORT_MAX_BINS + 4 * tid);
         constexpr int STRIDE = SORT_MAX_BINS / 4;
         u32 t = t0;
         for (; t + 8 <= t1; t += 8, col += 8 * STRIDE) {                 // 8 independent 16-byte loads, then the sums
@@ -327,9 +339,9 @@ __global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pa
         const u32 ntiles_seg = (a.seg_count[seg] + SORT_TILE - 1) / SORT_TILE;
         if (tid == 0) s_last = (atomicAdd(a.seg_done + (size_t)pass * a.n_seg + seg, 1u) == ntiles_seg - 1);
         __syncthreads();
-        if (s_last) {
+        if (s_last && ntiles_seg <= SORT_SCAN_LOCAL_MAX) {   // (larger segments: sort_big_scan in the scatter kernel)
             __threadfence();
-            segment_scan(a, seg, tseg0, tseg0 + ntiles_seg, nbins, s_warp);
+            segment_scan(a, a.tilehist, seg, tseg0, tseg0 + ntiles_seg, nbins, s_warp);
         }
     }
 }
@@ -391,6 +403,69 @@ __device__ __forceinline__ void rank_rows(ScatterSmem& S, const u32 (&key)[SORT_
 // Elements are first placed at their tile-local sorted position in shared memory, then streamed out so that the
 // lanes of a warp write consecutive addresses within each digit bin (a fully scattered 4-byte store costs the LSU
 // one wavefront per lane).
+// ---- big segments: the histogram scan by the whole grid ------------------------------------------------------------------
+// A segment of T tiles needs, per digit, the exclusive prefix of its T tile histograms.  The count kernel's last-CTA scan
+// walks them 8 per L2 round trip: fine for tens of tiles, 200-600 us for the 500-2500 tiles of one class of confident
+// logits.  For segments above SORT_SCAN_LOCAL_MAX tiles the scatter kernel does it instead, with every CTA:
+//   phase 1  sum of each chunk of SORT_CHUNK tile histograms              (one CTA per chunk, round-robin)
+//   phase 2  exclusive scan of a segment's chunk sums + its bin bases     (one CTA per big segment)
+// and each scatter tile then adds the <= 63 raw histograms of its chunk that precede it.  Two grid barriers; all CTAs of
+// the scatter grid are co-resident (the launch clamps the grid to the occupancy).
+__device__ __forceinline__ void grid_barrier(u32* ctr, int* status) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        u32 spins = 0;
+        while (ld_relaxed(ctr) < gridDim.x) {
+            __nanosleep(64);
+            if (++spins >= SPIN_LIMIT) { atomicOr(status, STATUS_SPIN_TIMEOUT); break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ u32 sort_chunk_id(u32 tseg0, int seg, u32 lc) { return (tseg0 / SORT_CHUNK) + (u32)seg + lc; }
+
+__device__ __forceinline__ void sort_big_scan(const SortArgs& a, int pass, u32* s_warp) {
+    const int tid = threadIdx.x;
+    const u32 n_big = a.big[0];
+    u32 unit = 0;
+    for (u32 j = 0; j < n_big; ++j) {                      // phase 1
+        const int seg = (int)a.big[1 + j];
+        const u32 t0 = a.tile_start[seg], nt = a.tile_start[seg + 1] - t0;
+        const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]), nch = (nt + SORT_CHUNK - 1) / SORT_CHUNK;
+        for (u32 lc = 0; lc < nch; ++lc, ++unit) {
+            if (unit % gridDim.x != blockIdx.x || (u32)(4 * tid) >= nbins) continue;
+            const u32 ta = t0 + lc * SORT_CHUNK, tb = min(ta + SORT_CHUNK, t0 + nt);
+            const uint4* col = reinterpret_cast<const uint4*>(a.tilehist + (size_t)ta * SORT_MAX_BINS + 4 * tid);
+            constexpr int STRIDE = SORT_MAX_BINS / 4;
+            u32 tot[4] = {0, 0, 0, 0};
+            u32 t = ta;
+            for (; t + 16 <= tb; t += 16, col += 16 * STRIDE) {
+                uint4 x[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = __ldcg(col + i * STRIDE);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { tot[0] += x[i].x; tot[1] += x[i].y; tot[2] += x[i].z; tot[3] += x[i].w; }
+            }
+            for (; t < tb; ++t, col += STRIDE) { const uint4 x = __ldcg(col); tot[0] += x.x; tot[1] += x.y; tot[2] += x.z; tot[3] += x.w; }
+            __stcg(reinterpret_cast<uint4*>(a.chunksum + (size_t)sort_chunk_id(t0, seg, lc) * SORT_MAX_BINS + 4 * tid),
+                   make_uint4(tot[0], tot[1], tot[2], tot[3]));
+        }
+    }
+    grid_barrier(a.gbar + 2 * pass, a.status);
+    for (u32 j = blockIdx.x; j < n_big; j += gridDim.x) {  // phase 2
+        const int seg = (int)a.big[1 + j];
+        const u32 t0 = a.tile_start[seg], nt = a.tile_start[seg + 1] - t0;
+        const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]), nch = (nt + SORT_CHUNK - 1) / SORT_CHUNK;
+        const u32 c0 = sort_chunk_id(t0, seg, 0);
+        __syncthreads();
+        segment_scan(a, a.chunksum, seg, c0, c0 + nch, nbins, s_warp);
+    }
+    grid_barrier(a.gbar + 2 * pass + 1, a.status);
+}
+
 template <bool USE_MATCH>
 __global__ void __launch_bounds__(SORT_TPB, SORT_SCATTER_MINB) sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -401,6 +476,7 @@ __global__ void __launch_bounds__(SORT_TPB, SORT_SCATTER_MINB) sort_scatter_kern
     const bool odd = pass & 1;
     u32* __restrict__ kout = odd ? a.keys[0] : a.keys[1];
     u32* __restrict__ vout = odd ? a.vals[0] : a.vals[1];
+    if (a.big[0]) sort_big_scan(a, pass, S.warp_sum);     // grid-uniform
 
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const uint4 d4 = a.tile_desc[t];
@@ -470,7 +546,25 @@ __global__ void __launch_bounds__(SORT_TPB, SORT_SCATTER_MINB) sort_scatter_kern
         for (int w2 = 0; w2 < SORT_WARPS; ++w2) if (w2 < warp) excl += S.warp_sum[w2];
         if ((u32)(4 * tid) < nbins) {
             const uint4 bb = *reinterpret_cast<const uint4*>(a.bin_base + (size_t)seg * SORT_MAX_BINS + 4 * tid);
-            const uint4 th = *reinterpret_cast<const uint4*>(a.tilehist + (size_t)t * SORT_MAX_BINS + 4 * tid);
+            uint4 th;
+            const u32 tseg0 = t - off / SORT_TILE, nts = a.tile_start[seg + 1] - tseg0;
+            if (nts <= SORT_SCAN_LOCAL_MAX) {             // scanned by the count kernel: already the tile's offset in the bin
+                th = *reinterpret_cast<const uint4*>(a.tilehist + (size_t)t * SORT_MAX_BINS + 4 * tid);
+            } else {                                      // chunk offset + the raw histograms of the chunk's earlier tiles
+                const u32 lc = (t - tseg0) / SORT_CHUNK;
+                th = __ldcg(reinterpret_cast<const uint4*>(a.chunksum + (size_t)sort_chunk_id(tseg0, seg, lc) * SORT_MAX_BINS + 4 * tid));
+                const uint4* col = reinterpret_cast<const uint4*>(a.tilehist + (size_t)(tseg0 + lc * SORT_CHUNK) * SORT_MAX_BINS + 4 * tid);
+                constexpr int STRIDE = SORT_MAX_BINS / 4;
+                u32 tq = tseg0 + lc * SORT_CHUNK;
+                for (; tq + 8 <= t; tq += 8, col += 8 * STRIDE) {
+                    uint4 x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = __ldcg(col + i * STRIDE);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { th.x += x[i].x; th.y += x[i].y; th.z += x[i].z; th.w += x[i].w; }
+                }
+                for (; tq < t; ++tq, col += STRIDE) { const uint4 x = __ldcg(col); th.x += x.x; th.y += x.y; th.z += x.z; th.w += x.w; }
+            }
             const u32 e0 = excl, e1 = e0 + tot[0], e2 = e1 + tot[1], e3 = e2 + tot[2];
             *reinterpret_cast<uint2*>(&S.binexcl[4 * tid]) = make_uint2(e0 | (e1 << 16), e2 | (e3 << 16));
             *reinterpret_cast<uint4*>(&S.binoff[4 * tid]) =
@@ -551,7 +645,18 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     const int match_mode = b200seg_tuning().sort_match;
     const int sms = b200seg_sm_count();
     const u32 cgrid = L.max_tiles < (u32)sms * 8 ? L.max_tiles : (u32)sms * 8;
-    const u32 sgrid = L.max_tiles < (u32)sms * SORT_SCATTER_MINB ? L.max_tiles : (u32)sms * SORT_SCATTER_MINB;
+    // the scatter grid must be co-resident (grid barriers of sort_big_scan): clamp it to the measured occupancy
+    static int scatter_occ[64] = {0};
+    if (dev >= 0 && dev < 64 && scatter_occ[dev] == 0) {
+        int o0 = 0, o1 = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, sort_scatter_kernel<false>, SORT_TPB, sizeof(ScatterSmem)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, sort_scatter_kernel<true>, SORT_TPB, sizeof(ScatterSmem)));
+        scatter_occ[dev] = o0 < o1 ? o0 : o1;
+        if (scatter_occ[dev] < 1) scatter_occ[dev] = 1;
+        if (scatter_occ[dev] > SORT_SCATTER_MINB) scatter_occ[dev] = SORT_SCATTER_MINB;
+    }
+    const u32 per_sm = (dev >= 0 && dev < 64) ? (u32)scatter_occ[dev] : 1u;
+    const u32 sgrid = L.max_tiles < (u32)sms * per_sm ? L.max_tiles : (u32)sms * per_sm;
     for (int p = 0; p < SORT_PASSES; ++p) {
         sort_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_count_kernel");

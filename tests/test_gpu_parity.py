@@ -272,6 +272,33 @@ def test_segmented_sort_is_stable_and_exact(b200, seed):
         assert np.array_equal(vout[sl], vals[sl][order]), f"segment {s}: values / tie order"
 
 
+@pytest.mark.parametrize("bits", [24, 30])
+def test_segmented_sort_with_segments_above_the_local_scan_limit(b200, bits):
+    """Segments of more than 128 tiles (524 288 elements) have their tile histograms scanned by the whole scatter grid
+    (chunk sums, grid barrier, chunk offsets) instead of by the count kernel's last CTA; mixed here with small ones."""
+    rng = np.random.RandomState(7 + bits)
+    cap = 1_300_000
+    counts = np.array([1_300_000, 5000, 0, 700_001, 524_288, 524_289], dtype=np.int64)
+    nseg = len(counts)
+    kbits = np.array([bits, 17, 1, bits, 9, bits], dtype=np.int64)
+    keys = np.zeros(nseg * cap, dtype=np.int64)
+    vals = np.zeros(nseg * cap, dtype=np.int64)
+    for s in range(nseg):
+        n, hi = counts[s], 1 << kbits[s]
+        k = rng.randint(0, hi, size=n)
+        if s == 3:                                      # clustered with long tie runs
+            k = np.clip((rng.randn(n) * 50 + hi / 2).astype(np.int64), 0, hi - 1)
+        keys[s * cap:s * cap + n] = k
+        vals[s * cap:s * cap + n] = np.arange(n) * 2 + (rng.rand(n) < 0.3)
+    kout, vout = _sort_segments(keys, vals, counts, kbits, cap)
+    for s in range(nseg):
+        n = counts[s]
+        sl = slice(s * cap, s * cap + n)
+        order = np.argsort(keys[sl], kind="stable")
+        assert np.array_equal(kout[sl], keys[sl][order]), f"segment {s}: keys"
+        assert np.array_equal(vout[sl], vals[sl][order]), f"segment {s}: values / tie order"
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # edge cases and error behaviour
 # ---------------------------------------------------------------------------------------------------------------
