@@ -26,7 +26,7 @@
 #define BWD_TPB 128
 #define JAC_TPB SORT_TPB
 
-enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_JTICKET = 27, CTRL_GEO = 32,
+enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_JTICKET = 27, CTRL_PTICKET = 28, CTRL_GEO = 32,
        CTRL_CE_SUM = 40 /* double */, CTRL_CE_CNT = 42, CTRL_CE_INV_N = 43 };
 enum { EMIT_PATH_STREAM = 0, EMIT_PATH_RECORDS = 1 };
 
@@ -1933,6 +1933,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
     a.seg_count = p.seg_count; a.seg_bits = p.seg_bits; a.n_seg = p.n_seg; a.cap = p.cap;
     a.src_keys = p.keysA; a.src_vals = p.valsA; a.run_prefix = p.run_prefix; a.geo = p.geo;
     a.run_cnt = p.run_cnt; a.run_prefix_w = p.run_prefix; a.seg_count_w = p.seg_count; a.n_classes = c;
+    a.prep_ticket = p.ctrl + CTRL_PTICKET;
     a.tile_start = (u32*)(ss + L.sort.tile_start); a.tilehist = (u32*)(ss + L.sort.tilehist);
     a.tile_desc = (uint4*)(ss + L.sort.tile_desc); a.tile_runs = (uint2*)(ss + L.sort.tile_runs);
     a.seg_done = (u32*)(ss + L.sort.seg_done);
@@ -2104,7 +2105,7 @@ extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint3
     a.keys[0] = keys_in; a.vals[0] = vals_in; a.keys[1] = keys_out; a.vals[1] = vals_out;
     a.seg_count = counts; a.seg_bits = key_bits; a.n_seg = n_segments; a.cap = capacity;
     a.src_keys = nullptr; a.src_vals = nullptr; a.run_prefix = nullptr; a.geo = nullptr;
-    a.run_cnt = nullptr; a.run_prefix_w = nullptr; a.seg_count_w = nullptr; a.n_classes = 1;
+    a.run_cnt = nullptr; a.run_prefix_w = nullptr; a.seg_count_w = nullptr; a.n_classes = 1; a.prep_ticket = nullptr;
     a.tile_start = (u32*)(ss + L.tile_start); a.tilehist = (u32*)(ss + L.tilehist);
     a.tile_desc = (uint4*)(ss + L.tile_desc); a.tile_runs = (uint2*)(ss + L.tile_runs);
     a.seg_done = (u32*)(ss + L.seg_done);

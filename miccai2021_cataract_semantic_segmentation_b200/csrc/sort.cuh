@@ -48,6 +48,7 @@ struct SortArgs {
     const u32* run_cnt;     // [groups * n_runs][n_classes]
     u32* run_prefix_w;      // = run_prefix, writable: filled by sort_prepare_kernel
     u32* seg_count_w;       // = seg_count, writable: filled by sort_prepare_kernel
+    u32* prep_ticket;       // zeroed by the caller: CTAs of sort_prepare_kernel that finished part A
     int n_classes;
     // scratch
     u32* tile_start;        // [n_seg + 1] exclusive prefix of tiles per segment
@@ -74,7 +75,7 @@ static inline SortScratch sort_scratch_layout(int n_seg, long long total_capacit
     size_t o = 0;
     L.tile_start = o; o = align_up(o + sizeof(u32) * (size_t)(n_seg + 1), 256);
     L.tile_desc = o;  o = align_up(o + sizeof(uint4) * (size_t)L.max_tiles, 256);
-    L.tile_runs = o;  o = align_up(o + sizeof(uint2) * (size_t)L.max_tiles, 256);
+    L.tile_runs = o;  o = align_up(o + sizeof(uint2) * ((size_t)L.max_tiles + n_seg + 2), 256);
     L.seg_done = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_PASSES, 256);
     L.bin_base = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_MAX_BINS, 256);
     L.tile_fg = o;    o = align_up(o + sizeof(u32) * (size_t)L.max_tiles, 256);
@@ -101,58 +102,77 @@ __device__ __forceinline__ int sort_find_segment(const u32* tile_start, int n_se
     return lo;
 }
 
-__device__ __forceinline__ u32 upper_run(const u32* prefix, u32 lo, u32 hi, u32 v) {   // largest r in [lo,hi]: prefix[r] <= v
-    while (lo < hi) {
-        const u32 mid = (lo + hi + 1) >> 1;
-        if (prefix[mid] <= v) lo = mid; else hi = mid - 1;
-    }
-    return lo;
+// ---- prepare: everything between the emission and the first digit pass ----------------------------------------------
+//   A (holey source only; a CTA per segment, all CTAs): exclusive prefix of the segment's chunk counts (the run prefix),
+//     the segment's count, and for every tile the source runs it intersects -- written by the runs themselves (the run
+//     that holds a tile's first element says so), no searching
+//   B (the CTA that finishes last): tiles per segment -> exclusive prefix (tile_start); clears the per-pass counters;
+//     the list of big segments; one descriptor per tile {segment, first element, element count, digit width}, so the
+//     per-tile prologue of every later kernel is a single 16-byte load instead of a chain of dependent ones
+#define SORT_PREP_TPB 1024
+// tile_runs is indexed by capacity, not by the (not yet known) global tile number: slot of tile `tl` of segment `seg`
+__device__ __forceinline__ size_t sort_runs_slot(const SortArgs& a, int seg, u32 tl) {
+    return (size_t)(((long long)seg * a.cap) / SORT_TILE) + (size_t)seg + tl;
 }
 
-// ---- prepare (one CTA): everything between the emission and the first digit pass -------------------------------------
-//   1. holey source only: per segment, exclusive prefix of the chunk counts (the run prefix) and the segment's count
-//   2. tiles per segment -> exclusive prefix (tile_start); clears the per-pass and per-tile counters
-//   3. one descriptor per tile {segment, first element, element count, digit width} (+ the source runs it intersects),
-//      so the per-tile prologue of every later kernel is a single 16-byte load instead of a chain of dependent ones
-#define SORT_PREP_TPB 1024
-#define SORT_PREP_WINDOW 1024                 // run-prefix entries a warp stages in shared memory (else it searches global)
 __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a, u32 max_tiles) {
     __shared__ u32 s_warp[32];
-    __shared__ u32 s_carry;
+    __shared__ u32 s_carry, s_lastrun, s_islast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (a.run_prefix) {
         const int n_runs = a.geo->n_runs, C = a.n_classes;
-        for (int seg = warp; seg < a.n_seg; seg += SORT_PREP_TPB / 32) {
+        for (int seg = blockIdx.x; seg < a.n_seg; seg += gridDim.x) {
             const int g = seg / C, c = seg - g * C;
             u32* out = a.run_prefix_w + (size_t)seg * (n_runs + 1);
-            u32 carry = 0;
-            for (int base = 0; base < n_runs; base += 256) {              // 8 independent loads per lane, then the scans
-                u32 x[8];
+            uint2* truns = a.tile_runs + sort_runs_slot(a, seg, 0);
+            __syncthreads();
+            if (tid == 0) { s_carry = 0; s_lastrun = 0; }
+            __syncthreads();
+            for (int base = 0; base < n_runs; base += SORT_PREP_TPB) {
+                const int r = base + tid;
+                const u32 x = r < n_runs ? a.run_cnt[((size_t)g * n_runs + r) * C + c] : 0;
+                u32 v = x;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = base + i * 32 + lane;
-                    x[i] = r < n_runs ? a.run_cnt[((size_t)g * n_runs + r) * C + c] : 0;
+                for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
+                if (lane == 31) s_warp[warp] = v;
+                __syncthreads();
+                if (warp == 0) {
+                    u32 wv = s_warp[lane];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, wv, o); if (lane >= o) wv += y; }
+                    s_warp[lane] = wv;
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (base + i * 32 >= n_runs) break;     // warp-uniform
-                    const int r = base + i * 32 + lane;
-                    u32 v = x[i];
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
-                    if (r < n_runs) out[r] = carry + v - x[i];
-                    carry += __shfl_sync(FULL_MASK, v, 31);
+                __syncthreads();
+                const u32 p0 = s_carry + (warp ? s_warp[warp - 1] : 0) + v - x;      // elements before run r
+                if (r < n_runs) out[r] = p0;
+                if (x) {                                   // tiles whose first element lies in this run
+                    for (u32 tl = (p0 + SORT_TILE - 1) / SORT_TILE; tl * SORT_TILE < p0 + x; ++tl) truns[tl].x = (u32)r;
+                    atomicMax(&s_lastrun, (u32)r);
                 }
+                __syncthreads();
+                if (tid == SORT_PREP_TPB - 1) s_carry = p0 + x;
+                __syncthreads();
             }
-            if (lane == 0) { out[n_runs] = carry; a.seg_count_w[seg] = carry; }
+            const u32 cnt = s_carry, nt = (cnt + SORT_TILE - 1) / SORT_TILE;
+            if (tid == 0) { out[n_runs] = cnt; a.seg_count_w[seg] = cnt; }
+            // last run a tile touches: at most the first run of the next tile (a bound is enough: it sizes the window)
+            for (u32 tl = tid; tl < nt; tl += SORT_PREP_TPB) truns[tl].y = tl + 1 < nt ? truns[tl + 1].x : s_lastrun;
         }
-        __syncthreads();                                   // CTA-scope visibility of seg_count / run_prefix
+        if (gridDim.x > 1) {                               // only the CTA that finishes last goes on
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_islast = atomicAdd(a.prep_ticket, 1u) == gridDim.x - 1;
+            __syncthreads();
+            if (!s_islast) return;
+            __threadfence();
+        }
+        __syncthreads();
     }
     if (tid == 0) s_carry = 0;
     __syncthreads();
     for (int base = 0; base < a.n_seg; base += SORT_PREP_TPB) {
         const int s = base + tid;
-        const u32 nt = s < a.n_seg ? (a.seg_count[s] + SORT_TILE - 1) / SORT_TILE : 0;
+        const u32 nt = s < a.n_seg ? (__ldcg(a.seg_count + s) + SORT_TILE - 1) / SORT_TILE : 0;
         u32 v = nt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
@@ -176,29 +196,16 @@ __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a,
     if (tid < 2 * SORT_PASSES) a.gbar[tid] = 0;
     __syncthreads();
     for (int sg = tid; sg < a.n_seg; sg += SORT_PREP_TPB)
-        if ((a.seg_count[sg] + SORT_TILE - 1) / SORT_TILE > SORT_SCAN_LOCAL_MAX) a.big[1 + atomicAdd(a.big, 1u)] = (u32)sg;
+        if ((__ldcg(a.seg_count + sg) + SORT_TILE - 1) / SORT_TILE > SORT_SCAN_LOCAL_MAX) a.big[1 + atomicAdd(a.big, 1u)] = (u32)sg;
     for (int i = tid; i < a.n_seg * SORT_PASSES; i += SORT_PREP_TPB) a.seg_done[i] = 0;
     for (u32 i = tid; i < total && i < max_tiles; i += SORT_PREP_TPB) a.tile_fg[i] = 0;
     __syncthreads();
-    // descriptors: a warp per segment; the segment's run prefix is staged in shared memory so that the two binary
-    // searches per tile do not chase global memory
-    extern __shared__ u32 s_prefix_all[];
-    u32* s_prefix = s_prefix_all + (size_t)warp * SORT_PREP_WINDOW;
-    const int n_runs = a.run_prefix ? a.geo->n_runs : 0;
-    for (int seg = warp; seg < a.n_seg; seg += SORT_PREP_TPB / 32) {
+    for (int seg = warp; seg < a.n_seg; seg += SORT_PREP_TPB / 32) {      // descriptors: a warp per segment
         const u32 t_first = a.tile_start[seg], nt = a.tile_start[seg + 1] - t_first;
-        if (nt == 0) continue;
-        const u32 cnt = a.seg_count[seg], w = sort_digit_width(a.seg_bits[seg]);
-        const u32* prefix = a.run_prefix ? a.run_prefix + (size_t)seg * (n_runs + 1) : nullptr;
-        const bool staged = prefix && n_runs + 1 <= SORT_PREP_WINDOW;
-        __syncwarp();
-        if (staged) for (int i = lane; i <= n_runs; i += 32) s_prefix[i] = prefix[i];
-        __syncwarp();
-        const u32* pf = staged ? s_prefix : prefix;
+        const u32 cnt = __ldcg(a.seg_count + seg), w = sort_digit_width(a.seg_bits[seg]);
         for (u32 i = lane; i < nt && t_first + i < max_tiles; i += 32) {
-            const u32 off = i * SORT_TILE, n = min((u32)SORT_TILE, cnt - off);
-            a.tile_desc[t_first + i] = make_uint4((u32)seg, off, n, w);
-            if (prefix) a.tile_runs[t_first + i] = make_uint2(upper_run(pf, 0, n_runs - 1, off), upper_run(pf, 0, n_runs - 1, off + n - 1));
+            const u32 off = i * SORT_TILE;
+            a.tile_desc[t_first + i] = make_uint4((u32)seg, off, min((u32)SORT_TILE, cnt - off), w);
         }
     }
 }
@@ -236,7 +243,7 @@ __device__ __forceinline__ TileSrc tile_src_setup(const SortArgs& a, int pass, u
     T.voff = off;
     T.seg_base = (size_t)seg * G.src_cap;
     T.run_stride = G.run_stride;
-    const uint2 rr = a.tile_runs[t];
+    const uint2 rr = a.tile_runs[sort_runs_slot(a, seg, off / SORT_TILE)];
     T.r_lo = rr.x; T.r_hi = rr.y;
     T.window = (T.r_hi - T.r_lo + 2) <= SORT_RUN_WINDOW + 1;
     if (T.window)
@@ -628,15 +635,17 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {          // opt in to > 48 KB of dynamic shared memory, once per device
-        CUDA_TRY(cudaFuncSetAttribute(sort_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(u32) * SORT_PREP_WINDOW * (SORT_PREP_TPB / 32))));
         CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(ScatterSmem)));
         CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(ScatterSmem)));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    sort_prepare_kernel<<<1, SORT_PREP_TPB, sizeof(u32) * SORT_PREP_WINDOW * (SORT_PREP_TPB / 32), st>>>(a, L.max_tiles);
+    {
+        const int sms_p = b200seg_sm_count();
+        const int pgrid = a.run_prefix ? (a.n_seg < sms_p ? a.n_seg : sms_p) : 1;
+        sort_prepare_kernel<<<pgrid, SORT_PREP_TPB, 0, st>>>(a, L.max_tiles);
+    }
     LAUNCH_CHECK("sort_prepare_kernel");
     b200seg_stage(4, st);
     // peer masks by MATCH.ANY cost ~ the number of distinct digits in the warp: a win only for the top digit, where
