@@ -1308,7 +1308,17 @@ __global__ void __launch_bounds__(JAC_TPB, 4) jaccard_kernel(LovaszParams p, Sor
             run += __popc(b);
         }
         if (lane == 0) s_wfg[warp] = run;
+        {   // every load of the tile must have landed before its lines are dropped: consume the keys here
+            u32 kor = 0;
+#pragma unroll
+            for (int k = 0; k < SORT_KPT; ++k) kor |= key[k];
+            asm volatile("" ::"r"(kor) : "memory");
+        }
         __syncthreads();
+        {                                                  // the sorted tile is in registers: its lines in buffer B are dead
+            discard_dead_lines(keys + base, keys + base + SORT_TILE, keys + (size_t)seg * a.cap, keys + (size_t)(seg + 1) * a.cap);
+            discard_dead_lines(vals + base, vals + base + SORT_TILE, vals + (size_t)seg * a.cap, vals + (size_t)(seg + 1) * a.cap);
+        }
         u32 wexcl = 0, ttot = 0;
 #pragma unroll
         for (int w2 = 0; w2 < SORT_WARPS; ++w2) { const u32 x = s_wfg[w2]; if (w2 < warp) wexcl += x; ttot += x; }

@@ -609,6 +609,11 @@ __global__ void __launch_bounds__(SORT_TPB) sort_fg_count_kernel(SortArgs a, u32
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const uint4 d4 = a.tile_desc[t];
         const u32* v = a.vals[1] + (size_t)d4.x * a.cap + d4.y;
+        {   // buffer 0 (source of the last pass) is dead: drop this tile's share of its dirty lines from L2 unwritten
+            const size_t sb = (size_t)d4.x * a.cap;
+            discard_dead_lines(a.keys[0] + sb + d4.y, a.keys[0] + sb + d4.y + SORT_TILE, a.keys[0] + sb, a.keys[0] + sb + a.cap);
+            discard_dead_lines(a.vals[0] + sb + d4.y, a.vals[0] + sb + d4.y + SORT_TILE, a.vals[0] + sb, a.vals[0] + sb + a.cap);
+        }
         u32 c = 0;
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
