@@ -675,8 +675,15 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
         sort_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_count_kernel");
         const bool use_match = match_mode == 1 || (match_mode == 2 && p == SORT_PASSES - 1);
-        if (use_match) sort_scatter_kernel<true><<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
-        else sort_scatter_kernel<false><<<sgrid, SORT_TPB, sizeof(ScatterSmem), st>>>(a, p, L.max_tiles);
+        {   // cooperative launch: the grid is resident as a whole or not at all, so the grid barriers of sort_big_scan cannot
+            // dead-lock against another partially resident grid (two loss heads on two streams)
+            SortArgs a_copy = a;
+            int pass_copy = p;
+            u32 bound_copy = L.max_tiles;
+            void* args[] = {(void*)&a_copy, (void*)&pass_copy, (void*)&bound_copy};
+            const void* fn = use_match ? (const void*)sort_scatter_kernel<true> : (const void*)sort_scatter_kernel<false>;
+            CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(sgrid), dim3(SORT_TPB), args, sizeof(ScatterSmem), st));
+        }
         LAUNCH_CHECK("sort_scatter_kernel");
         if (p + 1 < SORT_PASSES) b200seg_stage(5 + p, st);
     }

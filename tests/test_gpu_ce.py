@@ -129,3 +129,27 @@ def test_two_scale_loss_two_streams_matches_oracle(b200):
     with pytest.raises(NotImplementedError):
         b200.TwoScaleLoss({"interm": {"name": "LovaszSoftmax", "args": []}, "final": {"name": "CrossEntropyLoss", "args": []},
                            "experiment": exp})
+
+
+def test_two_streams_with_big_sort_segments(b200):
+    """Two heads on two streams while both sorts have segments above the local-scan limit (confident logits: the grid
+    barriers of the scatter kernels run concurrently): results must equal the one-stream evaluation bit for bit."""
+    from test_gpu_parity import _blocky
+    n, c, h, w, exp = 2, 25, 540, 960, 3
+    xa, y = _blocky(n, c, h, w, seed=21, with_ignore=True)
+    xb, _ = _blocky(n, c, h, w, seed=22, with_ignore=True)
+    cfg = lambda: {"interm": {"name": "LovaszSoftmax", "args": [], "weight": 0.4},
+                   "final": {"name": "LovaszSoftmax", "args": [], "weight": 1.0}, "experiment": exp}
+    two = b200.TwoScaleLoss(cfg())
+    la, lb = b200.LovaszSoftmax({"experiment": exp}), b200.LovaszSoftmax({"experiment": exp})
+    a1, b1 = xa.cuda().requires_grad_(True), xb.cuda().requires_grad_(True)
+    yd = y.cuda()
+    ref = lb(b1, yd) * 1.0 + la(a1, yd) * 0.4
+    ref.backward()
+    for _ in range(3):
+        a2, b2 = xa.cuda().requires_grad_(True), xb.cuda().requires_grad_(True)
+        out = two(a2, b2, yd)
+        out.backward()
+        torch.cuda.synchronize()
+        assert float(out) == float(ref)
+        assert torch.equal(a2.grad, a1.grad) and torch.equal(b2.grad, b1.grad)
