@@ -44,7 +44,7 @@ extern "C" {
 /* bits of the device-side status word (`status`, int32, OR-ed into by kernels; caller zeroes it) */
 #define B200SEG_STATUS_LABEL_OOB 1 /* a label outside [0, C) other than drop_label reached the confusion matrix
                                        (the reference's one_hot raises RuntimeError there) */
-#define B200SEG_STATUS_SPIN_TIMEOUT 2 /* internal chained-scan watchdog fired (results invalid; a bug) */
+#define B200SEG_STATUS_SPIN_TIMEOUT 2 /* internal grid-barrier watchdog fired (results invalid; a bug) */
 
 int b200seg_version(void);
 const char* b200seg_last_error(void);

@@ -1,20 +1,22 @@
 // Lovasz-Softmax forward + backward for sm_100a.  Replaces losses/LovaszSoftmax.py:19-95 of the reference.
 //
 // Pipeline (all on one stream, no host sync, no allocation):
-//   K1 stats      read logits once: per-pixel softmax max/sum (kept, 8 B/px), per-segment foreground count and
-//                 max key (= min foreground error -> sort threshold), optional fused argmax + confusion matrix
+//   K1 stats      read logits once: per-pixel softmax max/sum (kept, 8 B/px), compact label, per-segment foreground count
+//                 and max key (= min foreground error -> sort threshold), a 20-byte candidate record per pixel (own-class key,
+//                 the two most probable other classes, a bound on the rest), optional fused argmax + confusion matrix and
+//                 cross-entropy sum
 //   K1c absent    (keep_absent only) max_i p_c(i) for considered classes without foreground
-//   K1b finalize  thresholds, log-thresholds, key widths, class weights 1/n_present(/n_images)
-//   K2 emit       re-read logits: every (pixel, class) with error >= threshold becomes a candidate
-//                 (key = 0x3F800000 - bits(error), value = pixel<<1 | fg), written in pixel order per segment
-//                 (smem bitmask ranks + chained scan across tiles) so a stable sort gives canonical tie order
+//   K1b finalize  thresholds, key widths, class weights 1/n_present(/n_images), class order; chooses the emission path
+//   K2 emit       every (pixel, class) with error >= threshold becomes a candidate (key = 0x3F800000 - bits(error),
+//                 value = pixel<<1 | fg), written in pixel order per (chunk, class) so a stable sort gives canonical tie order;
+//                 from the records (CTA kernel, no logits) or, for confident logits, from a second pass over the logits
 //   K3..K4 sort   segmented stable LSD radix sort (sort.cuh)
-//   K5 jaccard    scan of fg flags in sorted order -> Jaccard gradient, loss partials, per-candidate g
-//   K5b loss      mean over present classes (sequential fp32, class order) and over images
-//   K6 backward   re-read logits: dz_k = go * p_k (g_k - sum_j g_j p_j), sparse g gathered per pixel
+//   K5 jaccard    scan of fg flags in sorted order -> Jaccard gradient, loss partials, per-candidate g; the last CTA
+//                 takes the mean over present classes (sequential fp32, class order) and over images
+//   K6 backward   re-read logits: dz_k = go * p_k (g_k - sum_j g_j p_j) (+ the cross-entropy gradient), sparse g per pixel
 //
 // Exactness notes: candidates are a superset of every element with non-zero Jaccard gradient (SURVEY.md §7.3,
-// zero-tail), so pruning changes nothing; p_c is computed by the same inlined fp32 sequence in every pass.
+// zero-tail), so pruning changes nothing; p_c is computed by the same fp32 instruction sequence in every pass.
 #include "b200seg.h"
 #include "common.cuh"
 #include "sort.cuh"

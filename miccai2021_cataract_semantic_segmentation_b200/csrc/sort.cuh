@@ -9,12 +9,15 @@
 // same time, so a chained scan would serialise; each pass is two short kernels instead:
 //   count    per-tile digit histogram (shared-memory atomics) -> tilehist[tile][bin]; the CTA that finishes a segment's
 //            last tile scans it: column scan over its tiles + exclusive scan over bins -> tile offsets, bin_base
-//   scatter  re-read the tile (L2), stable ranks (ballot peer masks + per-warp counters), reorder in shared memory,
-//            write to the other buffer with warp-contiguous stores
+//            (segments above SORT_SCAN_LOCAL_MAX tiles: scanned by the whole scatter grid instead, sort_big_scan)
+//   scatter  re-read the tile (L2), stable ranks (ballot / MATCH.ANY peer masks + per-warp counters), reorder in shared
+//            memory, write to the other buffer with warp-contiguous stores; launched cooperatively (grid barriers)
 // The first pass can read a "holey" source: every segment is a concatenation of n_runs runs, run r starting at
-// s*src_cap + r*run_stride with run_prefix[s][r+1]-run_prefix[s][r] elements (what the emission kernel leaves
-// behind without any cross-CTA ordering); elements are gathered by binary search over the run prefix.
-// A last small kernel counts the foreground flags (value bit 0) per tile of the final order for the Jaccard scan.
+// s*src_cap + r*run_stride with run_prefix[s][r+1]-run_prefix[s][r] elements (what the emission kernels leave
+// behind without any cross-CTA ordering); sort_prepare_kernel turns the run counts into the prefix, notes for every
+// tile which runs it intersects, plans the tiles and writes their descriptors.
+// A last small kernel counts the foreground flags (value bit 0) per tile of the final order for the Jaccard scan and
+// drops the dead source buffer from L2.
 #pragma once
 #include "common.cuh"
 #include <cstdlib>
