@@ -1030,6 +1030,7 @@ struct EctaSmem {
     u32 carryK[B200SEG_MAX_CLASSES][8], carryV[B200SEG_MAX_CLASSES][8];
     float thr[B200SEG_MAX_CLASSES];
     unsigned char order[B200SEG_MAX_CLASSES];             // classes by ascending threshold
+    unsigned long long cls_slot[B200SEG_MAX_CLASSES];     // first slot of the chunk's run of every class
     u32 wcoff[ECTA_TPB / 32][B200SEG_MAX_CLASSES];        // per-warp copy of the stage offsets (single-pass tiles)
     u32 stageK[ECTA_CAP], stageV[ECTA_CAP];
 };
@@ -1063,14 +1064,19 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
             tmin = p.grp_tmin[g];
             cur_g = g;
         }
-        if (tid < B200SEG_MAX_CLASSES) { S.carry_cnt[tid] = 0; S.emitted[tid] = 0; }
+        const size_t chunk_slot0 = (size_t)g * CT * (size_t)G.src_cap + (size_t)r * G.run_stride;
+        if (tid < B200SEG_MAX_CLASSES) {
+            S.carry_cnt[tid] = 0; S.emitted[tid] = 0;
+            S.cls_slot[tid] = chunk_slot0 + (size_t)tid * (size_t)G.src_cap;
+        }
         for (int i = tid; i < B200SEG_MAX_CLASSES * ECTA_WORDS; i += ECTA_TPB) (&S.mask[0][0])[i] = 0;
         __syncthreads();
-        const size_t chunk_slot0 = (size_t)g * CT * (size_t)G.src_cap + (size_t)r * G.run_stride;
 
-        for (long long gt = gt0; gt < gt1; ++gt) {
-            const int n = p.per_image ? g : (int)(gt / tpi);
-            const long long ti = p.per_image ? gt : gt - (long long)n * tpi;
+        // (image, tile-in-image) of the chunk's first tile; advanced by increments (no 64-bit division per tile)
+        int n = p.per_image ? g : (int)(gt0 / tpi);
+        long long ti = p.per_image ? gt0 : gt0 - (long long)n * tpi;
+        for (long long gt = gt0; gt < gt1; ++gt, ++ti) {
+            if (!p.per_image && ti == tpi) { ti = 0; ++n; }
             const long long q0 = ti * ECTA_TILE + (long long)tid * 4;
             const bool inb = q0 < p.HW;                    // plane % 4 == 0: a thread's 4 pixels are in or out together
             const size_t px0 = (size_t)n * p.HW + q0;
@@ -1208,8 +1214,9 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
                 for (int c = lo + warp; c < hi; c += NW) {
                     const u32 cc = S.carry_cnt[c], nt = S.tot[c], total = cc + nt, w = total & ~7u;
                     const u32 co = coff[c] - base, done = S.emitted[c];
-                    u32* kd = p.keysA + chunk_slot0 + (size_t)c * G.src_cap + done;
-                    u32* vd = p.valsA + chunk_slot0 + (size_t)c * G.src_cap + done;
+                    const size_t cslot = S.cls_slot[c] + done;          // chunk_slot0 + c * src_cap, set per chunk
+                    u32* kd = p.keysA + cslot;
+                    u32* vd = p.valsA + cslot;
                     for (u32 e = lane; e < w; e += 32) {
                         const bool fromc = e < cc;
                         kd[e] = fromc ? S.carryK[c][e] : S.stageK[co + e - cc];
