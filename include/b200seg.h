@@ -174,8 +174,8 @@ int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_o
  * Kernel-selection knobs (no reference counterpart; process-wide).  Every setting computes the same results;
  * they exist so tests can exercise every code path and profiles can compare variants in one process.
  *   "interleave"    1 (default) warps of the streaming kernels take interleaved tiles, 0 contiguous ranges
- *   "stats_variant" 0 (default) pipelined stats kernel, 3 ring stages; 2 / 3: 2 / 4 stages; 1: register-tile
- *                   kernel without per-pixel records (forces the streaming emission)
+ *   "stats_variant" 0 (default) pipelined stats kernel, 384-thread CTAs, 2 ring stages; 2..6: other CTA sizes /
+ *                   stage counts; 1: register-tile kernel without per-pixel records (forces the streaming emission)
  *   "emit_path"     0 (default) chosen on the device from the records; 1 record-driven; 2 streaming
  *   "sort_match"    2 (default) MATCH.ANY peer masks in the top digit pass only; 0 ballots; 1 MATCH.ANY
  *   "dbg"           timing experiments only (skips work: results become wrong)

@@ -19,8 +19,10 @@ VARIANTS = [
     ("emit_records", dict(emit_path=1)),
     ("emit_stream", dict(emit_path=2)),
     ("stats_register_tile", dict(stats_variant=1)),
-    ("stats_2_stages", dict(stats_variant=2)),
-    ("stats_4_stages", dict(stats_variant=3)),
+    ("stats_128x2", dict(stats_variant=2)),
+    ("stats_128x4", dict(stats_variant=3)),
+    ("stats_128x3", dict(stats_variant=5)),
+    ("stats_512x2", dict(stats_variant=6)),
     ("contiguous_tiles", dict(interleave=0)),
     ("rank_ballots", dict(sort_match=0)),
     ("rank_match", dict(sort_match=1)),

@@ -22,4 +22,19 @@ for (n, c, h, w, exp, cfg) in [(2, 25, 64, 96, 3, {}), (2, 17, 64, 96, 2, {"per_
     cm = b200.t_get_confusion_matrix(x.detach(), y.int()) if c in (8, 17, 25) else None
     torch.cuda.synchronize()
     print(n, c, h, w, cfg, float(loss.detach()), float(x.grad.abs().max()))
+# the other emission path, the fused cross-entropy pair, confident logits (streaming emission) and a big sort segment
+from miccai2021_cataract_semantic_segmentation_b200 import _native
+x = torch.randn((2, 25, 64, 96), generator=g).cuda().requires_grad_(True)
+y = torch.randint(0, 26, (2, 64, 96), generator=g).cuda()
+for path in (1, 2):
+    _native.set_tuning(emit_path=path)
+    lov, ce = b200.LovaszSoftmaxCE({"experiment": 3})(x, y)
+    (lov + ce).backward()
+    torch.cuda.synchronize()
+    print("emit_path", path, float(lov.detach()), float(ce.detach()))
+_native.set_tuning(emit_path=0)
+xz = torch.zeros((1, 25, 160, 256)).cuda().requires_grad_(True)          # every pair is a candidate: 40 960 x 25, > 128 tiles
+yz = torch.zeros((1, 160, 256), dtype=torch.long).cuda()
+b200.LovaszSoftmax({"experiment": 3, "classes_to_consider": "all"})(xz, yz).backward()
+torch.cuda.synchronize()
 print("done")
