@@ -27,6 +27,13 @@
 #define EMIT_TPB 256
 #define BWD_TPB 128
 #define JAC_TPB SORT_TPB
+// record-driven CTA emission kernel: threads per CTA (4 pixels each), resident CTAs per SM, pixels / mask words per tile
+#ifndef ECTA_TPB
+#define ECTA_TPB 512
+#endif
+#define ECTA_MINB (1024 / ECTA_TPB)      // resident CTAs per SM at 64 registers per thread
+#define ECTA_TILE (ECTA_TPB * 4)
+#define ECTA_WORDS (ECTA_TILE / 32)
 
 enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_JTICKET = 27, CTRL_PTICKET = 28, CTRL_GEO = 32,
        CTRL_CE_SUM = 40 /* double */, CTRL_CE_CNT = 42, CTRL_CE_INV_N = 43 };
@@ -90,8 +97,8 @@ static EmitGeom emit_geom(int N, long long HW, int per_image, long long tile_px)
     G.tpg = per_image ? G.tpi : G.tpi * N;
     const long long total_tiles = G.tpi * N;
     // chunks over the whole batch: the pipelined kernel (32-pixel tiles) runs one chunk per resident warp
-    // and the record-driven CTA kernel (1024-pixel tiles) one chunk per resident CTA
-    const long long target_chunks = (long long)b200seg_sm_count() * (tile_px <= 64 ? 32 : (tile_px == 1024 ? 4 : 8));
+    // and the record-driven CTA kernel (ECTA_TILE-pixel tiles) one chunk per resident CTA
+    const long long target_chunks = (long long)b200seg_sm_count() * (tile_px <= 64 ? 32 : (tile_px == ECTA_TILE ? ECTA_MINB : 8));
     G.tpc = (total_tiles + target_chunks - 1) / target_chunks;
     if (G.tpc < 1) G.tpc = 1;
     G.n_runs = (G.tpg + G.tpc - 1) / G.tpc;
@@ -108,7 +115,7 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     const size_t S = (size_t)groups * C;
     const size_t CP = (size_t)C * P;
     size_t cap_max = 0, runs_max = 0;                      // every emission variant must fit
-    for (long long tile_px : {(long long)EMIT_TPB * 4, (long long)EMIT_TPB, (long long)EMIT_WARP_TILE}) {
+    for (long long tile_px : {(long long)ECTA_TPB * 4, (long long)EMIT_TPB * 4, (long long)EMIT_TPB, (long long)EMIT_WARP_TILE}) {
         const EmitGeom G = emit_geom(N, HW, per_image, tile_px);
         if ((size_t)G.src_cap > cap_max) cap_max = (size_t)G.src_cap;
         if ((size_t)G.n_runs > runs_max) runs_max = (size_t)G.n_runs;
@@ -994,7 +1001,7 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
 
 // Record-driven emission (the fast path after stats_kernel_async): candidates come from the 20-byte per-pixel records;
 // the logits are only touched by pixels whose guard says a class beyond the two recorded ones could qualify.
-// One CTA per chunk of consecutive 1024-pixel tiles.  Per tile: every thread decodes 4 pixels, sets one bit per
+// One CTA per chunk of consecutive ECTA_TILE-pixel tiles (512 threads x 4 pixels; 256 x 4 measured 1.5 us slower).  Per tile: every thread decodes 4 pixels, sets one bit per
 // (pixel, class) candidate in a shared bit matrix, a popcount prefix over the 32 words of each class gives the ranks in
 // pixel order, candidates are staged in shared memory grouped by class and written out by whole warps in multiples of 8
 // elements (full 32-byte sectors, each written exactly once: a partially written sector costs an L2 fill from DRAM and
@@ -1016,9 +1023,6 @@ __device__ __noinline__ u32 emit_scan_pixel(const float* lp, long long plane, in
     return more;
 }
 
-#define ECTA_TPB 256
-#define ECTA_TILE (ECTA_TPB * 4)
-#define ECTA_WORDS (ECTA_TILE / 32)
 #define ECTA_CAP 4096                                     // staged candidates per pass over the classes of a tile
 struct EctaSmem {
     u32 mask[B200SEG_MAX_CLASSES][ECTA_WORDS];            // bit (pixel in tile) set = candidate of the class
@@ -1036,7 +1040,7 @@ struct EctaSmem {
 };
 
 template <int CT>
-__global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
+__global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszParams p) {
     if (p.flags[0] != EMIT_PATH_RECORDS) return;
     extern __shared__ __align__(16) unsigned char ecta_smem_raw[];
     EctaSmem& S = *reinterpret_cast<EctaSmem*>(ecta_smem_raw);
@@ -1136,11 +1140,16 @@ __global__ void __launch_bounds__(ECTA_TPB, 4) emit_kernel_cta(LovaszParams p) {
             __syncthreads();
             // ---- ranks: exclusive popcount prefix over the 32 words of every class --------------------------------------
             for (int c = warp; c < CT; c += NW) {
-                const u32 cnt = __popc(S.mask[c][lane]);
-                u32 v = cnt;
+                constexpr int WPL = ECTA_WORDS / 32;      // words per lane (consecutive)
+                u32 cnt[WPL], sum = 0;
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) { cnt[k] = __popc(S.mask[c][lane * WPL + k]); sum += cnt[k]; }
+                u32 v = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
-                S.wpre[c][lane] = v - cnt;
+                u32 run = v - sum;
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) { S.wpre[c][lane * WPL + k] = run; run += cnt[k]; }
                 if (lane == 31) S.tot[c] = v;
             }
             __syncthreads();
@@ -1916,11 +1925,17 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
         const long long chunks = (long long)p.groups * Gs.n_runs;
         if (p.have_records) {                              // record path (no-op unless K1d selected it)
             const long long rchunks = (long long)p.groups * Gr.n_runs;
-            const int grid = (int)(rchunks < (long long)sms * 4 ? rchunks : (long long)sms * 4);
+            const int grid = (int)(rchunks < (long long)sms * ECTA_MINB ? rchunks : (long long)sms * ECTA_MINB);
             const size_t smem = sizeof(EctaSmem);
-            if (c == 8) emit_kernel_cta<8><<<grid, ECTA_TPB, smem, st>>>(p);
-            else if (c == 17) emit_kernel_cta<17><<<grid, ECTA_TPB, smem, st>>>(p);
-            else emit_kernel_cta<25><<<grid, ECTA_TPB, smem, st>>>(p);
+#define LAUNCH_EMIT_CTA(CC)                                                                                          \
+    {                                                                                                                \
+        CUDA_TRY(cudaFuncSetAttribute(emit_kernel_cta<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        emit_kernel_cta<CC><<<grid, ECTA_TPB, smem, st>>>(p);                                                        \
+    }
+            if (c == 8) LAUNCH_EMIT_CTA(8)
+            else if (c == 17) LAUNCH_EMIT_CTA(17)
+            else LAUNCH_EMIT_CTA(25)
+#undef LAUNCH_EMIT_CTA
             LAUNCH_CHECK("emit_kernel_cta");
         }
         if (pipe_ok) {
