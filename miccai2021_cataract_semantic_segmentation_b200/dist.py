@@ -38,16 +38,31 @@ def shard_range(n_items: int, rank: int, world: int):
     return start, start + base + (1 if rank < extra else 0)
 
 
+class _Pending:
+    """Handle of the asynchronous all-reduces of one meter: ``wait()`` makes the current stream wait for them."""
+
+    def __init__(self, works):
+        self.works = [w for w in works if w is not None]
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
 def all_reduce_confusion_matrix(cm: torch.Tensor, group=None, status: torch.Tensor | None = None, async_op=False):
     """In-place SUM of the int64 C x C matrix over ranks (<= 5 KB at C = 25: latency-bound, one call per step or
-    per sweep).  ``status`` (the sticky label-range flag) is MAX-reduced so every rank raises together."""
+    per sweep).  ``status`` (the sticky label-range flag) is MAX-reduced so every rank raises together.
+    ``async_op=True`` returns a handle at once: the collectives run on the backend's stream, ordered after the work
+    already queued on the current stream (the forward pass that fills the matrix), so they overlap whatever is queued
+    next (the backward pass); call ``.wait()`` before reading the matrix."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return None
+        return _Pending([]) if async_op else None
     assert cm.dtype == torch.int64
-    work = dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    works = [dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=group, async_op=async_op)]
     if status is not None:
-        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)
-    return work
+        works.append(dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group, async_op=async_op))
+    return _Pending(works) if async_op else None
 
 
 def all_reduce_mean(value: torch.Tensor, group=None):

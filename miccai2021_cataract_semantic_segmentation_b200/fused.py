@@ -38,10 +38,13 @@ class SegmentationMeter:
     def update(self, prediction: torch.Tensor, target: torch.Tensor):
         accumulate_confusion_matrix(prediction, target, self.cm, self.status, self.drop_label)
 
-    def all_reduce(self, group=None):
+    def all_reduce(self, group=None, async_op: bool = False):
+        """Sum the matrix over the data-parallel ranks.  ``async_op=True``: returns a handle whose ``wait()`` must be
+        called before the matrix is read; issue it right after the forward pass and wait after ``loss.backward()`` so the
+        5 KB collective hides under the backward kernel."""
         from .dist import all_reduce_confusion_matrix
-        all_reduce_confusion_matrix(self.cm, group=group, status=self.status)
-        return self.cm
+        pending = all_reduce_confusion_matrix(self.cm, group=group, status=self.status, async_op=async_op)
+        return pending if async_op else self.cm
 
     def summary(self):
         """(iou[C], [mIoU, PA, PAC, mIoU_instruments, mIoU_anatomies, mIoU_rare]) as device tensors."""

@@ -29,7 +29,11 @@ def _worker(rank, world, port, n_images, out_dir):
     # each rank accumulates the matrix of its own images (the CUDA kernel's role on the GPU box) ...
     cm = oracle.confusion_matrix(x[lo:hi], y[lo:hi]).to(torch.int64) if hi > lo else torch.zeros(17, 17, dtype=torch.int64)
     status = torch.tensor([1 if rank == 1 else 0], dtype=torch.int32)
-    bd.all_reduce_confusion_matrix(cm, status=status)
+    if n_images % 2:                                          # both forms of the call
+        bd.all_reduce_confusion_matrix(cm, status=status)
+    else:
+        pending = bd.all_reduce_confusion_matrix(cm, status=status, async_op=True)
+        pending.wait()
     # ... and the sum over ranks must be the single-process matrix of the concatenated data
     full = oracle.confusion_matrix(x, y).to(torch.int64)
     assert torch.equal(cm, full)
