@@ -241,7 +241,7 @@ def main():
     ms_step = float(ms) / args.steps
     value = px_rank * world / (ms_step * 1e-3) / 1e6
     meter.check()
-    loss_value = float(loss)
+    loss_value = float(loss.detach())
 
     # ---- end to end from pinned host buffers ------------------------------------------------------------------
     e2e = None
