@@ -476,8 +476,12 @@ __device__ __forceinline__ void sort_big_scan(const SortArgs& a, int pass, u32* 
     grid_barrier(a.gbar + 2 * pass + 1, a.status);
 }
 
-template <bool USE_MATCH>
-__global__ void __launch_bounds__(SORT_TPB, SORT_SCATTER_MINB) sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
+// GATHER = true: pass 0 over the holey source (values loaded with the keys: the source index is costly to form twice).
+// GATHER = false: compact source; the values are loaded only when they are placed, so key + rank are all that lives in
+// registers through the ranking and the kernel fits 4 CTAs per SM (1100 tiles: 2 rounds of 592 instead of 3 of 444).
+template <bool USE_MATCH, bool GATHER>
+__global__ void __launch_bounds__(SORT_TPB, GATHER ? SORT_SCATTER_MINB : SORT_SCATTER_MINB + 1)
+sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -503,16 +507,20 @@ __global__ void __launch_bounds__(SORT_TPB, SORT_SCATTER_MINB) sort_scatter_kern
         const TileSrc T = tile_src_setup(a, pass, t, seg, off, S.keys);
         __syncthreads();
 
-        u32 key[SORT_KPT], val[SORT_KPT], rnk[SORT_KPT];
+        u32 key[SORT_KPT], val[GATHER ? SORT_KPT : 1], rnk[SORT_KPT];
         const u32 wbase = warp * (32 * SORT_KPT) + lane;
-        if (!T.gather) {
+        if (!GATHER) {
+            const u32* __restrict__ kp = T.keys + T.base + wbase;
+#pragma unroll
+            for (int k = 0; k < SORT_KPT; ++k) key[k] = (wbase + k * 32 < n) ? kp[k * 32] : 0xFFFFFFFFu;
+        } else if (!T.gather) {
             const u32* __restrict__ kp = T.keys + T.base + wbase;
             const u32* __restrict__ vp = T.vals + T.base + wbase;
 #pragma unroll
             for (int k = 0; k < SORT_KPT; ++k) {
                 const bool valid = wbase + k * 32 < n;
                 key[k] = valid ? kp[k * 32] : 0xFFFFFFFFu;
-                val[k] = valid ? vp[k * 32] : 0u;
+                val[GATHER ? k : 0] = valid ? vp[k * 32] : 0u;
             }
         } else {
             u32 cur = tile_src_cursor(T);
@@ -521,7 +529,7 @@ __global__ void __launch_bounds__(SORT_TPB, SORT_SCATTER_MINB) sort_scatter_kern
                 const u32 idx = wbase + k * 32;
                 const size_t src = idx < n ? tile_src_index(T, S.keys, idx, cur) : 0;
                 key[k] = idx < n ? T.keys[src] : 0xFFFFFFFFu;
-                val[k] = idx < n ? T.vals[src] : 0u;
+                val[GATHER ? k : 0] = idx < n ? T.vals[src] : 0u;
             }
         }
         switch (w) {                                      // uniform per tile
@@ -581,14 +589,30 @@ __global__ void __launch_bounds__(SORT_TPB, SORT_SCATTER_MINB) sort_scatter_kern
                 make_uint4(bb.x + th.x - e0, bb.y + th.y - e1, bb.z + th.z - e2, bb.w + th.w - e3);
         }
         __syncthreads();
+        if (GATHER) {
 #pragma unroll
-        for (int k = 0; k < SORT_KPT; ++k) {
-            if (wbase + k * 32 < n) {
-                const u32 d = (key[k] >> shift) & dmask;
-                const u32 lpos = (u32)S.binexcl[d] + S.cnt[warp][d] + rnk[k];
-                S.keys[lpos] = key[k];
-                S.vals[lpos] = val[k];
+            for (int k = 0; k < SORT_KPT; ++k) {
+                if (wbase + k * 32 < n) {
+                    const u32 d = (key[k] >> shift) & dmask;
+                    const u32 lpos = (u32)S.binexcl[d] + S.cnt[warp][d] + rnk[k];
+                    S.keys[lpos] = key[k];
+                    S.vals[lpos] = val[GATHER ? k : 0];
+                }
             }
+        } else {                                           // values straight from the source tile (L2) to their place
+            const u32* __restrict__ vp = T.vals + T.base + wbase;
+#pragma unroll
+            for (int k = 0; k < SORT_KPT; ++k) {
+                const bool valid = wbase + k * 32 < n;
+                const u32 v = valid ? vp[k * 32] : 0u;
+                const u32 d = (key[k] >> shift) & dmask;
+                rnk[k] = valid ? (u32)S.binexcl[d] + S.cnt[warp][d] + rnk[k] : 0xFFFFFFFFu;
+                if (valid) S.keys[rnk[k]] = key[k];
+                key[k] = v;                                // the key register now carries the value
+            }
+#pragma unroll
+            for (int k = 0; k < SORT_KPT; ++k)
+                if (rnk[k] != 0xFFFFFFFFu) S.vals[rnk[k]] = key[k];
         }
         __syncthreads();
 #pragma unroll
@@ -643,10 +667,10 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {          // opt in to > 48 KB of dynamic shared memory, once per device
-        CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(ScatterSmem)));
-        CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(ScatterSmem)));
+        const void* fns[4] = {(const void*)sort_scatter_kernel<false, false>, (const void*)sort_scatter_kernel<false, true>,
+                              (const void*)sort_scatter_kernel<true, false>, (const void*)sort_scatter_kernel<true, true>};
+        for (const void* f : fns)
+            CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     {
@@ -662,32 +686,34 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     const int match_mode = b200seg_tuning().sort_match;
     const int sms = b200seg_sm_count();
     const u32 cgrid = L.max_tiles < (u32)sms * 8 ? L.max_tiles : (u32)sms * 8;
-    // the scatter grid must be co-resident (grid barriers of sort_big_scan): clamp it to the measured occupancy
-    static int scatter_occ[64] = {0};
-    if (dev >= 0 && dev < 64 && scatter_occ[dev] == 0) {
-        int o0 = 0, o1 = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, sort_scatter_kernel<false>, SORT_TPB, sizeof(ScatterSmem)));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, sort_scatter_kernel<true>, SORT_TPB, sizeof(ScatterSmem)));
-        scatter_occ[dev] = o0 < o1 ? o0 : o1;
-        if (scatter_occ[dev] < 1) scatter_occ[dev] = 1;
-        if (scatter_occ[dev] > SORT_SCATTER_MINB) scatter_occ[dev] = SORT_SCATTER_MINB;
+    // the scatter grids must be co-resident (grid barriers of sort_big_scan): clamp them to the measured occupancy
+    static int occ_gather[64] = {0}, occ_compact[64] = {0};
+    if (dev >= 0 && dev < 64 && occ_gather[dev] == 0) {
+        int o[4] = {0, 0, 0, 0};
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[0], sort_scatter_kernel<false, true>, SORT_TPB, sizeof(ScatterSmem)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[1], sort_scatter_kernel<true, true>, SORT_TPB, sizeof(ScatterSmem)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[2], sort_scatter_kernel<false, false>, SORT_TPB, sizeof(ScatterSmem)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[3], sort_scatter_kernel<true, false>, SORT_TPB, sizeof(ScatterSmem)));
+        occ_gather[dev] = max(1, min(min(o[0], o[1]), SORT_SCATTER_MINB));
+        occ_compact[dev] = max(1, min(min(o[2], o[3]), SORT_SCATTER_MINB + 1));
     }
-    const u32 per_sm = (dev >= 0 && dev < 64) ? (u32)scatter_occ[dev] : 1u;
-    const u32 sgrid = L.max_tiles < (u32)sms * per_sm ? L.max_tiles : (u32)sms * per_sm;
     for (int p = 0; p < SORT_PASSES; ++p) {
         sort_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_count_kernel");
         const bool use_match = match_mode == 1 || (match_mode == 2 && p == SORT_PASSES - 1);
+        const bool gather = p == 0 && a.run_prefix != nullptr;
         {   // cooperative launch: the grid is resident as a whole or not at all, so the grid barriers of sort_big_scan cannot
             // dead-lock against another partially resident grid (two loss heads on two streams)
+            const u32 per_sm = (dev >= 0 && dev < 64) ? (u32)(gather ? occ_gather[dev] : occ_compact[dev]) : 1u;
+            const u32 sgrid = L.max_tiles < (u32)sms * per_sm ? L.max_tiles : (u32)sms * per_sm;
             SortArgs a_copy = a;
             int pass_copy = p;
             u32 bound_copy = L.max_tiles;
             void* args[] = {(void*)&a_copy, (void*)&pass_copy, (void*)&bound_copy};
-            const void* fn = use_match ? (const void*)sort_scatter_kernel<true> : (const void*)sort_scatter_kernel<false>;
+            const void* fn = gather ? (use_match ? (const void*)sort_scatter_kernel<true, true> : (const void*)sort_scatter_kernel<false, true>)
+                                    : (use_match ? (const void*)sort_scatter_kernel<true, false> : (const void*)sort_scatter_kernel<false, false>);
             CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(sgrid), dim3(SORT_TPB), args, sizeof(ScatterSmem), st));
         }
-        LAUNCH_CHECK("sort_scatter_kernel");
         if (p + 1 < SORT_PASSES) b200seg_stage(5 + p, st);
     }
     sort_fg_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, L.max_tiles);
