@@ -434,3 +434,21 @@ def test_full_size_properties(b200, c, exp, per_image):
     ref1 = float(port.lovasz_softmax(x[:1].cpu(), y[:1].cpu(), exp, per_image=per_image))
     got1 = float(b200.LovaszSoftmax({"experiment": exp, "per_image": per_image})(x[:1], y[:1]))
     assert rel_err(got1, ref1) <= LOSS_RTOL
+
+
+@pytest.mark.parametrize("c,exp,per_image", [(25, 3, False), (17, 2, True)])
+def test_full_size_parity_with_the_oracle_on_device(b200, c, exp, per_image):
+    """The headline workload itself (8 x C x 540 x 960): loss and logit gradient against the oracle executed on the
+    device (the reference's algorithm with ATen's CUDA softmax and stable sorts), north-star gates."""
+    from oracle import port
+    n, h, w = 8, 540, 960
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((n, c, h, w), generator=g, device="cuda")
+    y = torch.randint(0, c + 1, (n, h, w), generator=g, device="cuda")
+    xr = x.clone().requires_grad_(True)
+    loss = b200.LovaszSoftmax({"experiment": exp, "per_image": per_image})(xr, y)
+    loss.backward()
+    ref_loss, ref_grad = port.lovasz_softmax_with_grad(x, y, exp, per_image=per_image)
+    assert rel_err(float(loss), float(ref_loss)) <= LOSS_RTOL
+    gmax = float(ref_grad.abs().max())
+    assert float((xr.grad - ref_grad).abs().max()) <= GRAD_RTOL * gmax
