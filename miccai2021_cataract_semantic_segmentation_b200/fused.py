@@ -223,3 +223,56 @@ class TwoScaleLoss(nn.Module):
             self._side = torch.cuda.Stream(logits_final.device)
         return two_heads_forward(self.loss_final, self.loss_interm, logits_interm, logits_final, target,
                                  self.w_final, self.w_interm, self._side)
+
+
+class IoUTracker:
+    """Running per-class IoU for the reference's adaptive batch sampler without a per-step host synchronisation
+    (SURVEY.md 8 F3).  The reference does, every training step (managers/OCRNet_Manager.py:114-117)::
+
+        iou_values = (1 - a) * self.metrics['iou_values'] + a * to_numpy(iou)     # blocks on the GPU
+        self.metrics['iou_values'][:] = iou_values                               # read by AdaptiveBatchSampler.get_prob
+
+    Here the exponential average lives on the device (``update(iou)`` takes the device vector ``meter.summary()`` or
+    ``t_get_mean_iou(..., calculate_mean=False)`` returns) and is mirrored into pinned host memory asynchronously, two
+    buffers in turn; ``host_values()`` hands the sampler the newest mirror whose copy has completed -- at most one step
+    behind, never blocking.  ``host_values(wait=True)`` gives the exact current value (epoch end)."""
+
+    def __init__(self, num_values: int, alpha: float, device=None, init=None):
+        device = torch.device("cpu") if device is None else torch.device(device)
+        self.alpha = float(alpha)
+        self.ema = torch.zeros(num_values, dtype=torch.float32, device=device)
+        if init is not None:
+            self.ema.copy_(torch.as_tensor(init, dtype=torch.float32))
+        pin = device.type == "cuda"
+        self._host = [torch.zeros(num_values, dtype=torch.float32, pin_memory=pin) for _ in range(2)]
+        for h in self._host:
+            h.copy_(self.ema)
+        self._events = [None, None]
+        self._next = 0                                         # buffer the next update writes
+        self._latest = 1                                       # newest buffer known complete
+
+    def update(self, iou: torch.Tensor):
+        self.ema.mul_(1.0 - self.alpha).add_(iou.to(self.ema.dtype), alpha=self.alpha)
+        b = self._next
+        self._host[b].copy_(self.ema, non_blocking=True)
+        if self.ema.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.ema.device))
+            self._events[b] = ev
+        else:
+            self._latest = b
+        self._next = 1 - b
+        return self.ema
+
+    def host_values(self, wait: bool = False):
+        """numpy view of the newest completed mirror (``wait=True``: of the current value)."""
+        newest = 1 - self._next                                # buffer written by the last update
+        ev = self._events[newest]
+        if ev is not None:
+            if wait:
+                ev.synchronize()
+            if ev.query():
+                self._latest = newest
+        elif not self.ema.is_cuda:
+            self._latest = newest
+        return self._host[self._latest].numpy()

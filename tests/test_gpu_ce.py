@@ -153,3 +153,23 @@ def test_two_streams_with_big_sort_segments(b200):
         torch.cuda.synchronize()
         assert float(out) == float(ref)
         assert torch.equal(a2.grad, a1.grad) and torch.equal(b2.grad, b1.grad)
+
+
+def test_iou_tracker_mirrors_without_blocking(b200):
+    """Device-side EMA of the per-class IoU with an asynchronous pinned mirror."""
+    c, exp = 25, 3
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    meter = b200.SegmentationMeter(exp, c)
+    tr = b200.IoUTracker(c, alpha=0.25, device="cuda")
+    ref = np.zeros(c, np.float32)
+    for _ in range(4):
+        x = torch.randn((1, c, 64, 96), generator=gen, device="cuda")
+        y = torch.randint(0, c + 1, (1, 64, 96), generator=gen, device="cuda")
+        meter.reset()
+        meter.update(x, y)
+        iou, _ = meter.summary()
+        tr.update(iou)
+        ref = 0.75 * ref + 0.25 * iou.cpu().numpy()
+        stale = tr.host_values()                               # never blocks: this or the previous step's value
+        assert stale.shape == (c,)
+    assert np.allclose(tr.host_values(wait=True), ref, rtol=1e-6, atol=1e-7)

@@ -228,3 +228,19 @@ def test_install_two_stream_heads_replaces_two_scale_loss():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_iou_tracker_matches_the_reference_update_rule():
+    """managers/OCRNet_Manager.py:114-117: iou_values <- (1 - a) * iou_values + a * iou, per step."""
+    import numpy as np
+    import torch
+    import miccai2021_cataract_semantic_segmentation_b200 as b200
+    rng = np.random.RandomState(0)
+    init = rng.rand(25).astype(np.float32)
+    tr = b200.IoUTracker(25, alpha=0.1, init=init)
+    ref = init.copy()
+    for _ in range(5):
+        iou = rng.rand(25).astype(np.float32)
+        tr.update(torch.from_numpy(iou))
+        ref = (1 - 0.1) * ref + 0.1 * iou
+        assert np.allclose(tr.host_values(), ref, rtol=1e-6, atol=1e-7)
