@@ -95,16 +95,18 @@ class _LovaszCEFunction(torch.autograd.Function):
         nbytes = _native._sz(0)
         _native.check(lib.b200seg_lovasz_workspace_bytes(n, c, hw, int(per_image), nbytes), "workspace query")
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
-        out = torch.empty(2, dtype=torch.float32, device=logits.device)
+        # two separate 0-dim tensors (not views of one buffer): callers mutate losses in place (LossWrapper.py:71)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        ce = torch.empty((), dtype=torch.float32, device=logits.device)
         _native.check(lib.b200seg_lovasz_ce_forward(
             logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, hw, int(per_image),
-            filter_label, keep_absent, class_mask, int(need_grad), ws.data_ptr(), ws.numel(), out.data_ptr(),
-            ce_ignore, out.data_ptr() + 4, cm.data_ptr() if cm is not None else None, cm_drop,
+            filter_label, keep_absent, class_mask, int(need_grad), ws.data_ptr(), ws.numel(), loss.data_ptr(),
+            ce_ignore, ce.data_ptr(), cm.data_ptr() if cm is not None else None, cm_drop,
             status.data_ptr(), _native.stream_ptr(logits.device)), "b200seg_lovasz_ce_forward")
         if need_grad:
             ctx.save_for_backward(logits, target, ws)
             ctx.opts = (int(per_image), filter_label, keep_absent, class_mask, ce_ignore)
-        return out[0], out[1]
+        return loss, ce
 
     @staticmethod
     def backward(ctx, grad_lovasz, grad_ce):

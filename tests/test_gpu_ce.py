@@ -173,3 +173,21 @@ def test_iou_tracker_mirrors_without_blocking(b200):
         stale = tr.host_values()                               # never blocks: this or the previous step's value
         assert stale.shape == (c,)
     assert np.allclose(tr.host_values(wait=True), ref, rtol=1e-6, atol=1e-7)
+
+
+def test_pair_outputs_survive_in_place_scaling_and_anomaly_mode(b200):
+    """The reference scales losses in place (`loss *= w`, LossWrapper.py:71) and runs under
+    torch.autograd.set_detect_anomaly(True) (main.py:8)."""
+    n, c, exp = 1, 25, 3
+    x, y = _d1(n, c, 64, 96, seed=3, with_ignore=True)
+    with torch.autograd.detect_anomaly():
+        xd = x.cuda().requires_grad_(True)
+        lov, ce = b200.LovaszSoftmaxCE({"experiment": exp})(xd, y.cuda())
+        lov *= 0.5
+        ce *= 2.0
+        total = lov + ce
+        total.backward()
+    xr = x.cuda().requires_grad_(True)
+    lov2, ce2 = b200.LovaszSoftmaxCE({"experiment": exp})(xr, y.cuda())
+    (lov2 * 0.5 + ce2 * 2.0).backward()
+    assert torch.equal(xd.grad, xr.grad) and torch.isfinite(xd.grad).all()
