@@ -349,6 +349,20 @@ def test_degenerate_inputs(b200):
     l3 = b200.LovaszSoftmax({"experiment": 2, "classes_to_ignore": 17})(x3, y3)
     p = torch.softmax(x3[0, :, 2, 1], 0)[4]
     assert abs(float(l3) - float(1 - p)) < 1e-6
+    # per-image mode with one fully filtered image (reference: empty-tensor loss, backward raises): that image
+    # contributes 0 to the mean over images and gets a zero gradient
+    from oracle import port
+    x6 = torch.randn(3, 17, 12, 20, device="cuda", requires_grad=True)
+    y6 = torch.randint(0, 18, (3, 12, 20), device="cuda")
+    y6[1] = 17
+    l6 = b200.LovaszSoftmax({"experiment": 2, "classes_to_ignore": 17, "per_image": True})(x6, y6)
+    l6.backward()
+    parts = [port.lovasz_softmax_with_grad(x6.detach()[i:i + 1], y6[i:i + 1], 2, classes_to_ignore=17) for i in (0, 2)]
+    ref6 = (float(parts[0][0]) + float(parts[1][0])) / 3
+    assert abs(float(l6.detach()) - ref6) <= 1e-5 * ref6
+    assert float(x6.grad[1].abs().max()) == 0.0
+    for i, (_, g) in zip((0, 2), parts):
+        assert float((x6.grad[i] - g[0] / 3).abs().max()) <= 1e-5 * float(g.abs().max() / 3)
     # empty batch
     l4 = b200.LovaszSoftmax({"experiment": 1})(torch.zeros(0, 8, 4, 4, device="cuda"),
                                                torch.zeros(0, 4, 4, dtype=torch.int64, device="cuda"))
