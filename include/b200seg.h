@@ -146,6 +146,23 @@ int b200seg_metrics_from_confmat(const int64_t* cm, int32_t n_classes, uint32_t 
                                  float* iou_out, float* summary_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Windowed mean IoU map  --  replaces sliding_miou (utils/torch_utils.py:189-218, called per image by
+ *   calculate_performance, :24-35, with kernel 7 / stride 4 from utils/defaults.py:335-336)
+ *
+ * out[n][i][j] (fp32, [N, (H-k)/s+1, (W-k)/s+1]) <- mean over the C classes of I_c / U_c inside the k x k window
+ * whose top-left corner is (i*s, j*s); I_c / U_c = pixels where argmax prediction AND / OR label equal c; a class
+ * absent from both counts as 1 (:203-204).  Counts are exact integers; the class mean is summed in class order.
+ * kernel_size must be odd (:191) and <= 255.  Labels outside [0, C) (the reference's scatter_ rejects them) set
+ * B200SEG_STATUS_LABEL_OOB in *status and match no class.  `scratch` holds the per-pixel class map.
+ * The `original_size` expansion (:208-214: repeat + pad) is index arithmetic left to the host side.
+ * ------------------------------------------------------------------------------------------------ */
+int b200seg_sliding_miou_scratch_bytes(int32_t n_images, int64_t height, int64_t width, size_t* bytes);
+int b200seg_sliding_miou(const float* prediction, const void* labels, int32_t label_dtype,
+                         int32_t n_images, int32_t n_classes, int32_t height, int32_t width,
+                         int32_t kernel_size, int32_t stride, void* scratch, size_t scratch_bytes,
+                         float* out, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Measurement hook (no reference counterpart): process-wide, hand the library up to B200SEG_N_STAGES
  * cudaEvent_t handles; while set, b200seg_lovasz_forward / _backward record events[i] on their stream at stage
  * boundary i, so a caller can time each kernel group with cudaEventElapsedTime without a profiler.

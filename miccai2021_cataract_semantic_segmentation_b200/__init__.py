@@ -8,13 +8,13 @@ from .install import install
 from .lovasz import LovaszSoftmax, lovasz_softmax, lovasz_softmax_ce
 from .metrics import (IoU, accumulate_confusion_matrix, get_confusion_matrix, get_mean_iou, get_pixel_accuracy,
                       get_single_class_iou, metrics_summary, normalise_confusion_matrix, set_confusion_dtype,
-                      t_get_confusion_matrix, t_get_mean_iou, t_get_miou, t_get_pixel_accuracy,
+                      sliding_miou, t_get_confusion_matrix, t_get_mean_iou, t_get_miou, t_get_pixel_accuracy,
                       t_get_single_class_iou, t_normalise_confusion_matrix)
 
 __all__ = [
     "CATEGORIES", "CLASS_INFO", "NUM_CLASSES", "LovaszSoftmax", "LovaszSoftmaxWithMetrics", "SegmentationMeter",
     "lovasz_softmax", "lovasz_softmax_ce", "LovaszSoftmaxCE", "LossWrapper", "TwoScaleLoss", "IoUTracker", "install", "IoU", "accumulate_confusion_matrix", "metrics_summary", "set_confusion_dtype",
-    "t_get_confusion_matrix", "t_get_mean_iou", "t_get_miou", "t_get_pixel_accuracy", "t_get_single_class_iou",
+    "sliding_miou", "t_get_confusion_matrix", "t_get_mean_iou", "t_get_miou", "t_get_pixel_accuracy", "t_get_single_class_iou",
     "t_normalise_confusion_matrix", "get_confusion_matrix", "get_mean_iou", "get_pixel_accuracy",
     "get_single_class_iou", "normalise_confusion_matrix",
 ]

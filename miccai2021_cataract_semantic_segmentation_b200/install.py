@@ -16,7 +16,7 @@ from . import metrics as _metrics
 _LOSS_NAMES = {"LovaszSoftmax": _lovasz.LovaszSoftmax}
 _METRIC_NAMES = {name: getattr(_metrics, name) for name in (
     "t_get_confusion_matrix", "t_normalise_confusion_matrix", "t_get_pixel_accuracy", "t_get_mean_iou",
-    "t_get_miou", "t_get_single_class_iou", "get_confusion_matrix", "normalise_confusion_matrix",
+    "t_get_miou", "t_get_single_class_iou", "sliding_miou", "get_confusion_matrix", "normalise_confusion_matrix",
     "get_pixel_accuracy", "get_mean_iou", "get_single_class_iou")}
 
 

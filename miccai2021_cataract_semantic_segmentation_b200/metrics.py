@@ -77,6 +77,45 @@ def t_get_confusion_matrix(prediction: torch.Tensor, target: torch.Tensor, exist
     return cm if dtype == torch.int64 else cm.to(dtype)
 
 
+def sliding_miou(prediction: torch.Tensor, target: torch.Tensor, kernel_size: int, stride: int,
+                 original_size: bool = True, validate: bool = True) -> torch.Tensor:
+    """Mean IoU inside every kernel_size x kernel_size window (reference: utils/torch_utils.py:189-218).
+    Returns [N, windows_v, windows_h], or, with ``original_size``, that map repeated ``stride`` times along both axes
+    and zero-padded to [N, H, W] exactly like :208-214.  One pass over the logits plus an L2-resident window pass
+    instead of the reference's two [N, C*k*k, windows] unfolds."""
+    assert (kernel_size % 2 == 1), "Kernel size needs to be odd"
+    _native.require_cuda(prediction, target)
+    if prediction.dim() != 4:
+        raise ValueError("prediction must be [N, C, H, W]")
+    n, c, h, w = prediction.shape
+    if target.numel() != n * h * w:
+        raise ValueError("target must hold N*H*W labels")
+    if kernel_size > h or kernel_size > w:
+        raise RuntimeError("sliding_miou: kernel size (%d) exceeds the input (%d x %d)" % (kernel_size, h, w))
+    pred = prediction.detach()
+    pred = (pred if pred.dtype == torch.float32 else pred.float()).contiguous()
+    tgt = _native.as_label_tensor(target.detach())
+    dev = pred.device
+    lib = _native.load()
+    need = _native._sz()
+    _native.check(lib.b200seg_sliding_miou_scratch_bytes(n, h, w, need), "b200seg_sliding_miou_scratch_bytes")
+    scratch = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)
+    ver_num_wins, hor_num_wins = (h - kernel_size) // stride + 1, (w - kernel_size) // stride + 1
+    out = torch.empty((n, ver_num_wins, hor_num_wins), dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _native.check(lib.b200seg_sliding_miou(
+        pred.data_ptr(), tgt.data_ptr(), _native.label_code(tgt), n, c, h, w, kernel_size, stride,
+        scratch.data_ptr(), scratch.numel(), out.data_ptr(), status.data_ptr(), _native.stream_ptr(dev)),
+        "b200seg_sliding_miou")
+    if validate:
+        raise_if_label_out_of_range(status)
+    if not original_size:
+        return out
+    out = torch.repeat_interleave(torch.repeat_interleave(out, stride, dim=-2), stride, dim=-1)
+    offset = kernel_size // 2
+    return torch.nn.functional.pad(out, (offset, w - out.shape[-1] - offset, offset, h - out.shape[-2] - offset))
+
+
 def t_normalise_confusion_matrix(matrix: torch.Tensor, mode: str):
     """reference: utils/torch_utils.py:244-256."""
     with torch.no_grad():

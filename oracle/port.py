@@ -150,6 +150,36 @@ def confusion_matrix(prediction: torch.Tensor, target: torch.Tensor, existing=No
     return cm
 
 
+def sliding_miou(prediction: torch.Tensor, target: torch.Tensor, kernel_size: int, stride: int,
+                 original_size: bool = True):
+    """utils/torch_utils.py:189-218 (sliding_miou), counted directly: per window and class, I = #(pred == c and
+    label == c), U = #(pred == c or label == c) as integers, IoU = I / U in fp32 with 0/0 -> 1, mean over the classes.
+    The reference gets the same integers through one-hot + unfold + int and/or sums.  Labels must be in [0, C)
+    (the reference's scatter_ rejects anything else)."""
+    assert kernel_size % 2 == 1, "Kernel size needs to be odd"
+    n, c, h, w = prediction.shape
+    t = target.reshape(n, h, w).to(torch.int64)
+    if t.numel() and (int(t.min()) < 0 or int(t.max()) >= c):
+        raise RuntimeError("Class values must be smaller than num_classes.")
+    p = prediction.argmax(1)
+    win_p = p.unfold(1, kernel_size, stride).unfold(2, kernel_size, stride)      # [N, vw, hw, k, k] views
+    win_t = t.unfold(1, kernel_size, stride).unfold(2, kernel_size, stride)
+    ious = []
+    for cls in range(c):
+        a, b = win_p == cls, win_t == cls
+        inter = (a & b).sum((-1, -2)).to(torch.float)
+        union = (a | b).sum((-1, -2)).to(torch.float)
+        iou = inter / union
+        iou[union == 0] = 1
+        ious.append(iou)
+    m = torch.mean(torch.stack(ious, 1), dim=1)                                  # :205
+    if not original_size:
+        return m
+    m = torch.repeat_interleave(torch.repeat_interleave(m, stride, dim=-2), stride, dim=-1)
+    off = kernel_size // 2
+    return torch.nn.functional.pad(m, (off, w - m.shape[-1] - off, off, h - m.shape[-2] - off))
+
+
 def normalise_confusion_matrix(cm: torch.Tensor, mode: str):
     """utils/torch_utils.py:244-256."""
     if mode not in ("row", "col"):
