@@ -5,7 +5,8 @@
 // the roofline of this path): first-maximum argmax like the confusion matrix, prediction and label packed into one u16
 // per pixel.  window_iou_kernel takes one window per thread: it counts, per class, predicted / labelled / agreeing
 // pixels of the window in 16-bit shared-memory counters private to the thread (the 8 MB class map is L2-resident, every
-// pixel is revisited ~(k/stride)^2 times), then averages I/U over the classes in class order (U == 0 counts as 1).
+// pixel is revisited ~(k/stride)^2 times), then averages I/U over the classes (U == 0 counts as 1); only the classes that
+// occur in the window are visited.
 #include "b200seg.h"
 #include "common.cuh"
 
@@ -83,32 +84,39 @@ __global__ void __launch_bounds__(SW_TPB) window_iou_kernel(const unsigned short
     const int tid = threadIdx.x;
     const long long total = (long long)N * VW * HWIN;
     const float inv_c = 1.0f / (float)C;
+    for (int r = 0; r < 3 * C; ++r) s_cnt[r * SW_TPB + tid] = 0;     // thread-private counters: no barrier needed
     for (long long base = (long long)blockIdx.x * SW_TPB; base < total; base += (long long)gridDim.x * SW_TPB) {
         const long long id = base + tid;
-        if (id >= total) continue;                                   // counters are thread-private: no barrier needed
-        for (int r = 0; r < 3 * C; ++r) s_cnt[r * SW_TPB + tid] = 0;
+        if (id >= total) continue;
         const int wx = (int)(id % HWIN);
         const long long rest = id / HWIN;
         const int wy = (int)(rest % VW), n = (int)(rest / VW);
         const unsigned short* src = map + ((size_t)n * H + (size_t)wy * S) * W + (size_t)wx * S;
+        u32 seen = 0;                                                // classes predicted or labelled in this window
         for (int dy = 0; dy < K; ++dy) {
             const unsigned short* row = src + (size_t)dy * W;
             for (int dx = 0; dx < K; ++dx) {
                 const u32 v = __ldg(row + dx);
                 const u32 pc = v & 255u, tc = v >> 8;
                 s_cnt[pc * SW_TPB + tid] += 1;
+                seen |= 1u << pc;
                 if (tc < (u32)C) {
                     s_cnt[(C + tc) * SW_TPB + tid] += 1;
+                    seen |= 1u << tc;
                     if (tc == pc) s_cnt[(2 * C + tc) * SW_TPB + tid] += 1;
                 }
             }
         }
-        float sum = 0.f;
-        for (int c = 0; c < C; ++c) {
+        // classes absent from the window score 1 each (0/0 -> 1); the others add I/U in class order and hand their
+        // counters back zeroed
+        float sum = (float)(C - __popc(seen));
+        while (seen) {
+            const int c = __ffs(seen) - 1;
+            seen &= seen - 1;
             const u32 np = s_cnt[c * SW_TPB + tid], nt = s_cnt[(C + c) * SW_TPB + tid];
             const u32 ni = s_cnt[(2 * C + c) * SW_TPB + tid];
-            const u32 nu = np + nt - ni;
-            sum += nu ? __fdiv_rn((float)ni, (float)nu) : 1.0f;
+            s_cnt[c * SW_TPB + tid] = 0; s_cnt[(C + c) * SW_TPB + tid] = 0; s_cnt[(2 * C + c) * SW_TPB + tid] = 0;
+            sum += __fdiv_rn((float)ni, (float)(np + nt - ni));
         }
         out[id] = sum * inv_c;
     }
