@@ -163,6 +163,30 @@ int b200seg_sliding_miou(const float* prediction, const void* labels, int32_t la
                          float* out, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Online hard example mining cross entropy  --  replaces OhemCrossEntropy.forward + its autograd backward
+ *   reference: losses/OhemCrossEntropy.py:22-40 (forward), :9-20 (thresh / min_kept / ignore_label)
+ *
+ * loss_out[0] (device, fp32) <- mean of -log p_label over the pixels with p_label < max(v, thresh), where v is the
+ * element of rank min(min_kept, n_valid - 1) (0-based) of the ascending label probabilities of the n_valid pixels
+ * whose label != ignore_label (:32-39).  The full-length sort of the reference only serves to read v: here it is a
+ * three-level radix select over the fp32 bit patterns.  No pixel below the threshold (or n_valid == 0, where the
+ * reference raises) gives 0/0 = NaN like torch's mean of an empty tensor.  Labels outside [0, C) other than
+ * ignore_label set B200SEG_STATUS_LABEL_OOB and are treated as ignored.  `min_kept` is the already clamped value
+ * (max(1, config) at :13).  The bilinear resize of :23-26 (score and target of different size) is left to the caller.
+ * The workspace must reach backward untouched.  dlogits <- grad_out[0] / n_kept * (softmax - onehot) on the kept
+ * pixels, 0 elsewhere.
+ * ------------------------------------------------------------------------------------------------ */
+int b200seg_ohem_workspace_bytes(int32_t n_images, int64_t plane, size_t* bytes);
+int b200seg_ohem_ce_forward(const float* logits, const void* labels, int32_t label_dtype,
+                            int32_t n_images, int32_t n_classes, int64_t plane, int64_t ignore_label,
+                            float thresh, int64_t min_kept, void* workspace, size_t workspace_bytes,
+                            float* loss_out, int32_t* status, void* stream);
+int b200seg_ohem_ce_backward(const float* logits, const void* labels, int32_t label_dtype,
+                             int32_t n_images, int32_t n_classes, int64_t plane, int64_t ignore_label,
+                             const void* workspace, size_t workspace_bytes, const float* grad_out,
+                             float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Measurement hook (no reference counterpart): process-wide, hand the library up to B200SEG_N_STAGES
  * cudaEvent_t handles; while set, b200seg_lovasz_forward / _backward record events[i] on their stream at stage
  * boundary i, so a caller can time each kernel group with cudaEventElapsedTime without a profiler.

@@ -38,6 +38,9 @@ SIGNATURES = {
     "b200seg_metrics_from_confmat": (_c.c_int, [_vp, _i32, _u32, _c.POINTER(_u32), _i32, _vp, _vp, _vp]),
     "b200seg_sliding_miou_scratch_bytes": (_c.c_int, [_i32, _i64, _i64, _c.POINTER(_sz)]),
     "b200seg_sliding_miou": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "b200seg_ohem_workspace_bytes": (_c.c_int, [_i32, _i64, _c.POINTER(_sz)]),
+    "b200seg_ohem_ce_forward": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _c.c_float, _i64, _vp, _sz, _vp, _vp, _vp]),
+    "b200seg_ohem_ce_backward": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
     "b200seg_set_stage_events": (_c.c_int, [_c.POINTER(_vp), _i32]),
     "b200seg_set_tuning": (_c.c_int, [_c.c_char_p, _i32]),
     "b200seg_debug_exp_mismatches": (_c.c_int, [_vp, _i32, _vp, _vp]),

@@ -12,8 +12,9 @@ import sys
 
 from . import lovasz as _lovasz
 from . import metrics as _metrics
+from . import ohem as _ohem
 
-_LOSS_NAMES = {"LovaszSoftmax": _lovasz.LovaszSoftmax}
+_LOSS_NAMES = {"LovaszSoftmax": _lovasz.LovaszSoftmax, "OhemCrossEntropy": _ohem.OhemCrossEntropy}
 _METRIC_NAMES = {name: getattr(_metrics, name) for name in (
     "t_get_confusion_matrix", "t_normalise_confusion_matrix", "t_get_pixel_accuracy", "t_get_mean_iou",
     "t_get_miou", "t_get_single_class_iou", "sliding_miou", "get_confusion_matrix", "normalise_confusion_matrix",
@@ -98,7 +99,7 @@ def install(packages=("losses", "utils", "managers"), verbose: bool = False, fus
         if mod is None or not any(mod_name == p or mod_name.startswith(p + ".") for p in packages):
             continue
         # the defining modules keep their originals so the reference stays inspectable next to the drop-in
-        if mod_name in ("losses.LovaszSoftmax", "utils.torch_utils", "utils.metrics"):
+        if mod_name in ("losses.LovaszSoftmax", "losses.OhemCrossEntropy", "utils.torch_utils", "utils.metrics"):
             continue
         hits = []
         for name, obj in table.items():

@@ -150,6 +150,31 @@ def confusion_matrix(prediction: torch.Tensor, target: torch.Tensor, existing=No
     return cm
 
 
+def ohem_cross_entropy(score: torch.Tensor, target: torch.Tensor, thresh: float = 0.7, min_kept: int = 100000,
+                       ignore_label: int = -100):
+    """losses/OhemCrossEntropy.py:22-40 (forward; score and target of equal size).  The reference sorts the label
+    probabilities of the non-ignored pixels and reads element min(min_kept, n - 1); kthvalue reads the same element.
+    Differentiable through the per-pixel losses exactly like the reference (the threshold is a constant)."""
+    logp = torch.log_softmax(score, dim=1)
+    t = target.to(torch.int64)
+    keep = t != ignore_label
+    safe = torch.where(keep, t, torch.zeros_like(t))
+    lab_logp = logp.gather(1, safe.unsqueeze(1)).squeeze(1)
+    losses = -lab_logp[keep]                                               # :28, :36
+    p_lab = torch.softmax(score, dim=1).gather(1, safe.unsqueeze(1)).squeeze(1)[keep].detach()   # :27-32
+    k = min(min_kept, p_lab.numel() - 1)
+    min_value = torch.kthvalue(p_lab, k + 1).values                        # 0-based index k of the ascending sort
+    threshold = max(float(min_value), thresh)                              # :34
+    return losses[p_lab < threshold].mean()                                # :37-39
+
+
+def ohem_with_grad(score: torch.Tensor, target: torch.Tensor, **kw):
+    x = score.detach().clone().requires_grad_(True)
+    loss = ohem_cross_entropy(x, target, **kw)
+    (g,) = torch.autograd.grad(loss, x)
+    return loss.detach(), g
+
+
 def sliding_miou(prediction: torch.Tensor, target: torch.Tensor, kernel_size: int, stride: int,
                  original_size: bool = True):
     """utils/torch_utils.py:189-218 (sliding_miou), counted directly: per window and class, I = #(pred == c and
