@@ -132,6 +132,8 @@ def test_install_rebinds_names_bound_at_import_time():
         fake[name].LovaszSoftmax = OldLoss
     for name in ("utils", "utils.torch_utils", "managers.OCRNet_Manager"):
         fake[name].t_get_confusion_matrix = old_cm
+    fake["losses"].OhemCrossEntropy = OldLoss
+    fake["utils"].sliding_miou = fake["utils.torch_utils"].sliding_miou = old_cm
     saved = {k: sys.modules.get(k) for k in fake}
     sys.modules.update(fake)
     try:
@@ -141,6 +143,9 @@ def test_install_rebinds_names_bound_at_import_time():
         assert fake["managers.OCRNet_Manager"].LovaszSoftmax is b200.LovaszSoftmax
         assert fake["managers.OCRNet_Manager"].t_get_confusion_matrix is b200.t_get_confusion_matrix
         assert fake["utils"].t_get_confusion_matrix is b200.t_get_confusion_matrix
+        assert fake["losses"].OhemCrossEntropy is b200.OhemCrossEntropy
+        assert fake["utils"].sliding_miou is b200.sliding_miou
+        assert fake["utils.torch_utils"].sliding_miou is old_cm
         assert fake["losses.LovaszSoftmax"].LovaszSoftmax is OldLoss                 # defining modules untouched
         assert fake["utils.torch_utils"].t_get_confusion_matrix is old_cm
         assert "losses.LossWrapper" in rep

@@ -37,4 +37,17 @@ xz = torch.zeros((1, 25, 160, 256)).cuda().requires_grad_(True)          # every
 yz = torch.zeros((1, 160, 256), dtype=torch.long).cuda()
 b200.LovaszSoftmax({"experiment": 3, "classes_to_consider": "all"})(xz, yz).backward()
 torch.cuda.synchronize()
+# windowed IoU map and OHEM cross entropy: pipelined and scalar kernels, ignored and rank-decided cases
+for (n, c, h, w) in [(2, 25, 32, 48), (1, 12, 21, 19)]:
+    xs = torch.randn((n, c, h, w), generator=g).cuda()
+    ys = torch.randint(0, c, (n, h, w), generator=g).cuda()
+    m = b200.sliding_miou(xs, ys, 7, 4)
+    xo = xs.clone().requires_grad_(True)
+    yo = ys.clone()
+    yo[:, :4] = c if c == 25 else 0
+    for cfg in ({"experiment": 3, "min_kept": 200, "thresh": 0.01}, {"experiment": 3}):
+        lo = b200.OhemCrossEntropy(cfg if c == 25 else {k: v for k, v in cfg.items() if k != "experiment"})(xo, yo)
+        lo.backward()
+    torch.cuda.synchronize()
+    print("sliding / ohem", n, c, h, w, float(m.mean()), float(lo.detach()))
 print("done")
