@@ -90,5 +90,66 @@ for case in range(n_cases):
         bad += 1
         print("ERROR", tag, repr(e)[:300])
 _native.set_tuning(emit_path=0, interleave=1, stats_variant=0)
-print(f"{n_cases} cases, {bad} bad")
+
+# ---- the widened rows: fused CE + Lovasz pair, OHEM cross entropy, windowed IoU map ------------------------------
+for case in range(n_cases):
+    c, exp = [(8, 1), (17, 2), (25, 3), (6, None)][rng.randint(4)]
+    n = int(rng.randint(1, 4))
+    h = int(rng.choice([16, 33, 48, 64, 100]))
+    w = int(rng.choice([16, 47, 64, 96, 160]))
+    g = torch.Generator().manual_seed(int(rng.randint(1 << 30)))
+    hi = c + 1 if exp in (2, 3) else c
+    y = torch.randint(0, hi, (n, h, w), generator=g)
+    x = torch.randn((n, c, h, w), generator=g) * float(rng.choice([0.5, 1.0, 2.0]))
+    if rng.rand() < 0.5:
+        x = x + 4.0 * torch.nn.functional.one_hot(y.clamp(max=c - 1), c).permute(0, 3, 1, 2).float() * \
+            (torch.rand((n, 1, h, w), generator=g) < 0.7).float()
+    ldt = [torch.int64, torch.int32, torch.uint8][rng.randint(3)]
+    xd, yd = x.cuda(), y.cuda().to(ldt)
+    tag = f"widened case {case}: C={c} exp={exp} n={n} {h}x{w} labels={ldt}"
+    try:
+        # OHEM
+        cfg = {"min_kept": int(rng.choice([1, 50, 500, 5000, 100000])), "thresh": float(rng.choice([0.05, 0.3, 0.7, 0.95]))}
+        if exp is not None:
+            cfg["experiment"] = exp
+        mod = b200.OhemCrossEntropy(cfg)
+        xo = xd.clone().requires_grad_(True)
+        lo = mod(xo, yd)
+        ref_l, ref_g = port.ohem_with_grad(xd, y.cuda(), thresh=mod.thresh, min_kept=mod.min_kept, ignore_label=mod.ignore_label)
+        if bool(torch.isnan(ref_l)):
+            ok = bool(torch.isnan(lo))
+        else:
+            lo.backward()
+            ok = abs(float(lo.detach()) - float(ref_l)) <= 1e-5 * abs(float(ref_l)) and \
+                float((xo.grad - ref_g).abs().max()) <= 1e-5 * float(ref_g.abs().max())
+        if not ok:
+            bad += 1
+            print("MISMATCH ohem", tag, cfg, float(lo.detach()), float(ref_l))
+        # windowed IoU (labels must be real classes)
+        k, s = int(rng.choice([1, 3, 5, 7, 9])), int(rng.choice([1, 2, 4, 5]))
+        yy = y.clamp(max=c - 1)
+        full = bool(rng.randint(2))
+        got = b200.sliding_miou(xd, yy.cuda().to(ldt), k, s, original_size=full)
+        ref = port.sliding_miou(x, yy, k, s, original_size=full)
+        if tuple(got.shape) != tuple(ref.shape) or float((got.cpu() - ref).abs().max()) > 1e-6:
+            bad += 1
+            print("MISMATCH sliding", tag, k, s, full)
+        # fused CE + Lovasz pair
+        if exp is not None:
+            xp = xd.clone().requires_grad_(True)
+            lov, ce = b200.LovaszSoftmaxCE({"experiment": exp})(xp, yd)
+            (lov + 0.5 * ce).backward()
+            xr = xd.clone().requires_grad_(True)
+            rt = port.loss_wrapper_pair(xr, y.cuda(), exp, 0.5, 1.0)
+            rt.backward()
+            got_t = float(lov.detach()) + 0.5 * float(ce.detach())
+            ok = abs(got_t - float(rt)) <= 1e-5 * abs(float(rt)) and \
+                float((xp.grad - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
+            if not ok:
+                bad += 1
+                print("MISMATCH pair", tag, got_t, float(rt))
+    except Exception as e:                                    # noqa: BLE001
+        bad += 1
+        print("ERROR", tag, repr(e)[:300])
+print(f"2 x {n_cases} cases, {bad} bad")
 sys.exit(1 if bad else 0)
