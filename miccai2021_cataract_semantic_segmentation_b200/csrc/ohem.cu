@@ -16,7 +16,7 @@
 
 #define OH_TPB 256
 #define OH_BINS 1024
-enum { OH_NVALID = 0, OH_PREFIX, OH_RANK, OH_THR, OH_TICKET, OH_KEPT, OH_INVKEPT, OH_CTRL_WORDS = 16 };
+enum { OH_NVALID = 0, OH_PREFIX, OH_RANK, OH_THR, OH_TICKET, OH_KEPT, OH_INVKEPT, OH_DONE, OH_CTRL_WORDS = 16 };
 #define OH_INVALID_BITS 0x7F800000u     // +inf marks ignored / out-of-range pixels in the p_label plane
 
 struct OhemParams {
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(OH_TPB) ohem_stats_generic(OhemParams p) {
 __global__ void __launch_bounds__(OH_BINS) ohem_pick_kernel(OhemParams p, int level) {
     __shared__ u32 s_warp[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (p.ctrl[OH_DONE]) return;                                  // an earlier level already settled the threshold
     const u32 n_valid = p.ctrl[OH_NVALID];
     const u32 prefix = level ? p.ctrl[OH_PREFIX] : 0u;
     u32 rank;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(OH_BINS) ohem_pick_kernel(OhemParams p, int le
     incl += s_warp[warp];
     const u32 excl = incl - cnt;
     if (n_valid == 0) {
-        if (t == 0 && level == 2) p.ctrl[OH_THR] = __float_as_uint(p.thresh);     // nothing to keep: the mean is 0/0
+        if (t == 0) { p.ctrl[OH_THR] = __float_as_uint(p.thresh); p.ctrl[OH_DONE] = 1; }   // nothing to keep: 0/0
         return;
     }
     if (excl <= rank && rank < incl) {
@@ -205,6 +206,13 @@ __global__ void __launch_bounds__(OH_BINS) ohem_pick_kernel(OhemParams p, int le
         p.ctrl[OH_PREFIX] = np;
         p.ctrl[OH_RANK] = rank - excl;
         if (level == 2) p.ctrl[OH_THR] = __float_as_uint(fmaxf(__uint_as_float(np), p.thresh));
+        // every value of this bin is below thresh's bin: the order statistic is below thresh, max() picks thresh
+        // (:34), and the two refinement passes have nothing left to decide
+        const float th = p.thresh;
+        if (level == 0 && th > 0.f && th == th && (u32)t < ohem_bin0(__float_as_uint(th))) {
+            p.ctrl[OH_THR] = __float_as_uint(th);
+            p.ctrl[OH_DONE] = 1;
+        }
     }
 }
 
@@ -212,6 +220,7 @@ __global__ void __launch_bounds__(OH_BINS) ohem_pick_kernel(OhemParams p, int le
 __global__ void __launch_bounds__(OH_TPB) ohem_hist_kernel(OhemParams p, int level) {
     __shared__ u32 s_hist[OH_BINS];
     const int tid = threadIdx.x;
+    if (p.ctrl[OH_DONE]) return;
     for (int i = tid; i < OH_BINS; i += OH_TPB) s_hist[i] = 0;
     __syncthreads();
     const u32 prefix = p.ctrl[OH_PREFIX];

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(SM_TPB) class_map_kernel_generic(ClassMapParam
     if (oob) atomicOr(p.status, STATUS_LABEL_OOB);
 }
 
-// counters: s_cnt[(kind * C + class) * SW_TPB + thread], kind 0 = predicted, 1 = labelled, 2 = both
+// counters: s_cnt[(kind * C + class) * SW_TPB + thread], kind 0 = predicted only, 1 = labelled only, 2 = both
 __global__ void __launch_bounds__(SW_TPB) window_iou_kernel(const unsigned short* __restrict__ map, int N, int C, int H,
                                                             int W, int K, int S, int VW, int HWIN,
                                                             float* __restrict__ out) {
@@ -98,12 +98,15 @@ __global__ void __launch_bounds__(SW_TPB) window_iou_kernel(const unsigned short
             for (int dx = 0; dx < K; ++dx) {
                 const u32 v = __ldg(row + dx);
                 const u32 pc = v & 255u, tc = v >> 8;
-                s_cnt[pc * SW_TPB + tid] += 1;
                 seen |= 1u << pc;
-                if (tc < (u32)C) {
-                    s_cnt[(C + tc) * SW_TPB + tid] += 1;
-                    seen |= 1u << tc;
-                    if (tc == pc) s_cnt[(2 * C + tc) * SW_TPB + tid] += 1;
+                if (tc == pc) {                                      // agreeing pixel: one counter instead of three
+                    s_cnt[(2 * C + pc) * SW_TPB + tid] += 1;
+                } else {
+                    s_cnt[pc * SW_TPB + tid] += 1;
+                    if (tc < (u32)C) {
+                        s_cnt[(C + tc) * SW_TPB + tid] += 1;
+                        seen |= 1u << tc;
+                    }
                 }
             }
         }
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(SW_TPB) window_iou_kernel(const unsigned short
             const u32 np = s_cnt[c * SW_TPB + tid], nt = s_cnt[(C + c) * SW_TPB + tid];
             const u32 ni = s_cnt[(2 * C + c) * SW_TPB + tid];
             s_cnt[c * SW_TPB + tid] = 0; s_cnt[(C + c) * SW_TPB + tid] = 0; s_cnt[(2 * C + c) * SW_TPB + tid] = 0;
-            sum += __fdiv_rn((float)ni, (float)(np + nt - ni));
+            sum += __fdiv_rn((float)ni, (float)(np + nt + ni));
         }
         out[id] = sum * inv_c;
     }
