@@ -67,13 +67,12 @@ def ohem_cross_entropy(score: torch.Tensor, target: torch.Tensor, thresh: float 
 class OhemCrossEntropy(nn.Module):
     def __init__(self, config):
         super().__init__()
-        # specify settings through config if they are made explicit else use default (OhemCrossEntropy.py:11-18)
-        self.thresh = config['thresh'] if 'thresh' in config else 0.7
+        # same keys and defaults as OhemCrossEntropy.py:11-18: thresh 0.7, min_kept 100000 (at least 1), and the ignore
+        # label is the last entry of the experiment's class table for experiments 2 / 3, otherwise nothing is ignored
+        self.thresh = config.get('thresh', 0.7)
         self.min_kept = max(1, config['min_kept']) if 'min_kept' in config else 100000
-        if 'experiment' in config:
-            self.ignore_label = len(CLASS_INFO[config['experiment']][1]) - 1 if config['experiment'] in [2, 3] else -100
-        else:
-            self.ignore_label = -100  # if experiment is not given assume nothing is ignored
+        experiment = config.get('experiment')
+        self.ignore_label = len(CLASS_INFO[experiment][1]) - 1 if experiment in (2, 3) else -100
         self.validate = bool(config.get('validate_labels', False))
 
     def forward(self, score, target, **kwargs):
