@@ -52,8 +52,22 @@ for style in ("iid", "confident"):
         port.ohem_cross_entropy(x, y, thresh=mod.thresh, min_kept=mod.min_kept, ignore_label=mod.ignore_label).backward()
 
     ms, ms_f, ms_ref = timed(step), timed(fwd), timed(ref_step, reps=5)
+    import time
+    xc, yc = x[:1].detach().cpu().requires_grad_(True), y[:1].cpu()
+
+    def cpu_step():
+        xc.grad = None
+        port.ohem_cross_entropy(xc, yc, thresh=mod.thresh, min_kept=mod.min_kept, ignore_label=mod.ignore_label).backward()
+
+    cpu_step()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cpu_step()
+    cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
     kept = int((x.grad.abs().sum(1) > 0).sum())
     alg = (8 * c + 8) * n * h * w                 # logits read twice... once per pass, dlogits written, labels
     print(json.dumps({"op": "ohem fwd+bwd", "logits": style, "ms": round(ms, 4), "fwd_ms": round(ms_f, 4),
                       "kept_fraction": round(kept / (n * h * w), 3), "Mpx_per_s": round(n * h * w / ms / 1e3, 1),
-                      "torch_restatement_ms": round(ms_ref, 3), "copy_peak_GBps": peak}))
+                      "torch_restatement_ms": round(ms_ref, 3), "copy_peak_GBps": peak,
+                      "cpu_oracle_1_image_ms": round(cpu_ms, 1), "cpu_threads": torch.get_num_threads(),
+                      "cpu_Mpx_per_s": round(h * w / cpu_ms / 1e3, 2)}))

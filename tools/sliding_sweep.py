@@ -43,6 +43,15 @@ for ldt, lb in ((torch.int64, 8), (torch.uint8, 1)):
                       "Mpx_per_s": round(n * h * w / ms / 1e3, 1)}))
 ms_ref = timed(lambda: port.sliding_miou(x[:1], y[:1], k, s, original_size=False), reps=5)
 print(json.dumps({"op": "torch restatement on the device, 1 frame", "ms": round(ms_ref, 3)}))
+import time
+xc, yc = x[:1].cpu(), y[:1].cpu()
+port.sliding_miou(xc, yc, k, s, original_size=False)
+t0 = time.perf_counter()
+for _ in range(3):
+    port.sliding_miou(xc, yc, k, s, original_size=False)
+cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+print(json.dumps({"op": "oracle on the host CPU, 1 frame", "ms": round(cpu_ms, 1), "threads": torch.get_num_threads(),
+                  "Mpx_per_s": round(h * w / cpu_ms / 1e3, 2)}))
 got = b200.sliding_miou(x, y, k, s, original_size=False)
 ref = torch.cat([port.sliding_miou(x[i:i + 1], y[i:i + 1], k, s, original_size=False) for i in range(n)])
 print("max abs diff vs oracle on the device:", float((got - ref).abs().max()))
