@@ -6,9 +6,10 @@
 // three-level radix select over the fp32 bit patterns (probabilities are non-negative: their bits order like the values):
 //   ohem_stats      one pass over the logits (4*C + label bytes read, 16 bytes written per pixel): softmax max / sum,
 //                   p_label, -log p_label, and the top-10-bit histogram of p_label
-//   ohem_pick x3    one CTA walks a 1024-bin histogram to the bin holding the wanted rank
-//   ohem_hist x2    refine inside that bin (the 16 MB p_label plane is L2-resident)
-//   ohem_reduce     sum / count of the losses with p_label < max(order statistic, thresh); the last CTA writes the mean
+//   ohem_select_reduce   one cooperative kernel: every CTA walks the 1024-bin histogram to the bin holding the wanted
+//                   rank; unless that already settles the threshold, two refinements inside the bin (grid-wide
+//                   histograms over the L2-resident 16 MB p_label plane, a grid barrier each); then sum / count of the
+//                   losses with p_label < max(order statistic, thresh), the last CTA writes the mean
 //   ohem_backward   one pass: dlogits = go / n_kept * (softmax - onehot) on kept pixels, 0 elsewhere (pixels that are
 //                   not kept never read their logits)
 #include "b200seg.h"
@@ -16,7 +17,7 @@
 
 #define OH_TPB 256
 #define OH_BINS 1024
-enum { OH_NVALID = 0, OH_PREFIX, OH_RANK, OH_THR, OH_TICKET, OH_KEPT, OH_INVKEPT, OH_DONE, OH_CTRL_WORDS = 16 };
+enum { OH_NVALID = 0, OH_THR, OH_TICKET, OH_KEPT, OH_INVKEPT, OH_BAR0, OH_BAR1, OH_CTRL_WORDS = 16 };
 #define OH_INVALID_BITS 0x7F800000u     // +inf marks ignored / out-of-range pixels in the p_label plane
 
 struct OhemParams {
@@ -161,69 +162,63 @@ __global__ void __launch_bounds__(OH_TPB) ohem_stats_generic(OhemParams p) {
     if (oob) atomicOr(p.status, STATUS_LABEL_OOB);
 }
 
-// One CTA of OH_BINS threads: find the bin of histogram `level` that holds the wanted rank, extend the bit prefix.
-// After level 2 the prefix is the order statistic itself; the threshold of :33-34 follows.
-__global__ void __launch_bounds__(OH_BINS) ohem_pick_kernel(OhemParams p, int level) {
-    __shared__ u32 s_warp[32];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (p.ctrl[OH_DONE]) return;                                  // an earlier level already settled the threshold
-    const u32 n_valid = p.ctrl[OH_NVALID];
-    const u32 prefix = level ? p.ctrl[OH_PREFIX] : 0u;
-    u32 rank;
-    if (level == 0) {
-        const long long last = (long long)n_valid - 1;
-        rank = (u32)(p.min_kept < last ? p.min_kept : (last < 0 ? 0 : last));     // min(min_kept, numel - 1)
-    } else {
-        rank = p.ctrl[OH_RANK];
+// ---- select + reduce: one cooperative kernel ---------------------------------------------------------------------
+// Every CTA walks the 1024-bin histogram of a level itself (4 KB from L2), so no CTA waits for a "picker"; the two
+// refinement histograms are built by the whole grid with a grid barrier each.  When the first level already shows that the
+// order statistic lies below thresh (the usual case: thresh = 0.7, min_kept a small fraction of the pixels) there is no
+// barrier at all and the kernel goes straight to the masked mean.
+__device__ __forceinline__ void ohem_grid_barrier(u32* ctr, int* status) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        u32 spins = 0;
+        while (ld_relaxed(ctr) < gridDim.x) {
+            if (++spins > SPIN_LIMIT) { atomicOr(status, STATUS_SPIN_TIMEOUT); break; }
+            __nanosleep(32);
+        }
+        __threadfence();
     }
-    const u32 cnt = p.hist[level * OH_BINS + t];
-    u32 incl = cnt;
+    __syncthreads();
+}
+
+// bin of `hist` (OH_BINS counters) that holds rank `rank`, and the rank inside that bin; all threads get the result
+__device__ __forceinline__ void ohem_pick(const u32* hist, u32 rank, u32& bin, u32& rank_in_bin, u32* s_tmp) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int PER = OH_BINS / OH_TPB;
+    u32 c[PER], tsum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { c[k] = __ldcg(hist + t * PER + k); tsum += c[k]; }
+    u32 incl = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const u32 up = __shfl_up_sync(FULL_MASK, incl, o);
         if (lane >= o) incl += up;
     }
-    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();                                   // s_tmp may still be read from the previous call
+    if (lane == 31) s_tmp[warp] = incl;
+    if (t == 0) { s_tmp[OH_TPB / 32] = OH_BINS - 1; s_tmp[OH_TPB / 32 + 1] = 0; }   // rank beyond the counts (NaNs): last bin
     __syncthreads();
-    if (warp == 0) {
-        u32 w = s_warp[lane], wi = w;
+    u32 base = 0;
+    for (int w2 = 0; w2 < warp; ++w2) base += s_tmp[w2];
+    u32 excl = base + incl - tsum;
+    if (excl <= rank && rank < excl + tsum) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 up = __shfl_up_sync(FULL_MASK, wi, o);
-            if (lane >= o) wi += up;
+        for (int k = 0; k < PER; ++k) {
+            if (rank >= excl && rank < excl + c[k]) { s_tmp[OH_TPB / 32] = (u32)(t * PER + k); s_tmp[OH_TPB / 32 + 1] = rank - excl; }
+            excl += c[k];
         }
-        s_warp[lane] = wi - w;
     }
     __syncthreads();
-    incl += s_warp[warp];
-    const u32 excl = incl - cnt;
-    if (n_valid == 0) {
-        if (t == 0) { p.ctrl[OH_THR] = __float_as_uint(p.thresh); p.ctrl[OH_DONE] = 1; }   // nothing to keep: 0/0
-        return;
-    }
-    if (excl <= rank && rank < incl) {
-        const u32 np = (prefix << 10) | (u32)t;
-        p.ctrl[OH_PREFIX] = np;
-        p.ctrl[OH_RANK] = rank - excl;
-        if (level == 2) p.ctrl[OH_THR] = __float_as_uint(fmaxf(__uint_as_float(np), p.thresh));
-        // every value of this bin is below thresh's bin: the order statistic is below thresh, max() picks thresh
-        // (:34), and the two refinement passes have nothing left to decide
-        const float th = p.thresh;
-        if (level == 0 && th > 0.f && th == th && (u32)t < ohem_bin0(__float_as_uint(th))) {
-            p.ctrl[OH_THR] = __float_as_uint(th);
-            p.ctrl[OH_DONE] = 1;
-        }
-    }
+    bin = s_tmp[OH_TPB / 32];
+    rank_in_bin = s_tmp[OH_TPB / 32 + 1];
 }
 
 // histogram of the next 10 bits among the elements that share the prefix chosen so far
-__global__ void __launch_bounds__(OH_TPB) ohem_hist_kernel(OhemParams p, int level) {
-    __shared__ u32 s_hist[OH_BINS];
+__device__ __forceinline__ void ohem_refine_hist(const OhemParams& p, int level, u32 prefix, u32* s_hist) {
     const int tid = threadIdx.x;
-    if (p.ctrl[OH_DONE]) return;
     for (int i = tid; i < OH_BINS; i += OH_TPB) s_hist[i] = 0;
     __syncthreads();
-    const u32 prefix = p.ctrl[OH_PREFIX];
     const int hi = 30 - 10 * level, lo = 20 - 10 * level;
     const u32* bits = reinterpret_cast<const u32*>(p.p_lab);
     for (long long i = (long long)blockIdx.x * OH_TPB + tid; i < p.P; i += (long long)gridDim.x * OH_TPB) {
@@ -235,11 +230,35 @@ __global__ void __launch_bounds__(OH_TPB) ohem_hist_kernel(OhemParams p, int lev
         if (s_hist[i]) atomicAdd(p.hist + level * OH_BINS + i, s_hist[i]);
 }
 
-__global__ void __launch_bounds__(OH_TPB) ohem_reduce_kernel(OhemParams p) {
+__global__ void __launch_bounds__(OH_TPB) ohem_select_reduce_kernel(OhemParams p) {
+    __shared__ u32 s_hist[OH_BINS];
+    __shared__ u32 s_tmp[OH_TPB / 32 + 2];
     __shared__ double s_sum[OH_TPB / 32];
     __shared__ u32 s_cnt[OH_TPB / 32];
     const int tid = threadIdx.x;
-    const float thr = __uint_as_float(p.ctrl[OH_THR]);
+    const u32 n_valid = p.ctrl[OH_NVALID];
+    float thr = p.thresh;                                           // n_valid == 0: nothing is kept, the mean is 0/0
+    if (n_valid) {
+        const long long last = (long long)n_valid - 1;
+        u32 rank = (u32)(p.min_kept < last ? p.min_kept : last);   // min(min_kept, numel - 1), :33
+        u32 prefix, bin;
+        ohem_pick(p.hist, rank, prefix, rank, s_tmp);
+        // every value of that bin is below thresh's bin: the order statistic is below thresh and max() picks thresh (:34)
+        const bool settled = p.thresh > 0.f && p.thresh == p.thresh && prefix < ohem_bin0(__float_as_uint(p.thresh));
+        if (!settled) {                                             // uniform over the grid: every CTA saw the same counts
+            ohem_refine_hist(p, 1, prefix, s_hist);
+            ohem_grid_barrier(p.ctrl + OH_BAR0, p.status);
+            ohem_pick(p.hist + OH_BINS, rank, bin, rank, s_tmp);
+            prefix = (prefix << 10) | bin;
+            ohem_refine_hist(p, 2, prefix, s_hist);
+            ohem_grid_barrier(p.ctrl + OH_BAR1, p.status);
+            ohem_pick(p.hist + 2 * OH_BINS, rank, bin, rank, s_tmp);
+            prefix = (prefix << 10) | bin;
+            thr = fmaxf(__uint_as_float(prefix), p.thresh);
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) p.ctrl[OH_THR] = __float_as_uint(thr);      // backward reads it
+
     double sum = 0.0;
     u32 cnt = 0;
     const long long quads = p.P / 4;                               // planes are 256-byte aligned: 128-bit loads
@@ -433,14 +452,22 @@ extern "C" int b200seg_ohem_ce_forward(const float* logits, const void* labels, 
         DISPATCH_LABEL(label_dtype, ohem_stats_generic<LT><<<grid, OH_TPB, 0, st>>>(p));
     }
     LAUNCH_CHECK("ohem_stats");
-    const long long blocks = (p.P + OH_TPB - 1) / OH_TPB;
-    const int rgrid = (int)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8);
-    ohem_pick_kernel<<<1, OH_BINS, 0, st>>>(p, 0);
-    ohem_hist_kernel<<<rgrid, OH_TPB, 0, st>>>(p, 1);
-    ohem_pick_kernel<<<1, OH_BINS, 0, st>>>(p, 1);
-    ohem_hist_kernel<<<rgrid, OH_TPB, 0, st>>>(p, 2);
-    ohem_pick_kernel<<<1, OH_BINS, 0, st>>>(p, 2);
-    ohem_reduce_kernel<<<rgrid, OH_TPB, 0, st>>>(p);
+    {   // cooperative launch: the grid barriers of the refinement need every CTA resident
+        static int occ[64] = {0};
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        int per_sm = (dev >= 0 && dev < 64) ? occ[dev] : 0;
+        if (per_sm == 0) {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ohem_select_reduce_kernel, OH_TPB, 0));
+            if (per_sm < 1) per_sm = 1;
+            if (dev >= 0 && dev < 64) occ[dev] = per_sm;
+        }
+        if (per_sm > 4) per_sm = 4;
+        const long long blocks = (p.P / 4 + OH_TPB - 1) / OH_TPB + 1;
+        const int rgrid = (int)(blocks < (long long)sms * per_sm ? blocks : (long long)sms * per_sm);
+        void* args[] = {(void*)&p};
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)ohem_select_reduce_kernel, dim3(rgrid), dim3(OH_TPB), args, 0, st));
+    }
     LAUNCH_CHECK("ohem select / reduce");
     return 0;
 }
