@@ -33,7 +33,8 @@ static int env_int(const char* name, int dflt) {
 }
 B200segTuning& b200seg_tuning() {
     static B200segTuning t = {env_int("B200SEG_INTERLEAVE", 1), env_int("B200SEG_STATS_VARIANT", 0),
-                              env_int("B200SEG_EMIT_PATH", 0), env_int("B200SEG_SORT_MATCH", 2), env_int("B200SEG_DBG", 0)};
+                              env_int("B200SEG_EMIT_PATH", 0), env_int("B200SEG_SORT_MATCH", 2), env_int("B200SEG_SORT_PATH", 0),
+                              env_int("B200SEG_DBG", 0)};
     return t;
 }
 extern "C" int b200seg_set_tuning(const char* key, int32_t value) {
@@ -43,6 +44,7 @@ extern "C" int b200seg_set_tuning(const char* key, int32_t value) {
     else if (!strcmp(key, "stats_variant")) t.stats_variant = value;
     else if (!strcmp(key, "emit_path")) t.emit_path = value;
     else if (!strcmp(key, "sort_match")) t.sort_match = value;
+    else if (!strcmp(key, "sort_path")) t.sort_path = value;
     else if (!strcmp(key, "dbg")) t.dbg = value;
     else { b200seg_set_error("b200seg_set_tuning: unknown key '%s'", key); return B200SEG_E_INVALID; }
     return 0;

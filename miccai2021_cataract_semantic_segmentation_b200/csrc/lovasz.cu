@@ -20,6 +20,7 @@
 #include "b200seg.h"
 #include "common.cuh"
 #include "sort.cuh"
+#include "hybrid.cuh"
 #include "pipe.cuh"
 #include <cstdlib>
 
@@ -35,7 +36,8 @@
 #define ECTA_TILE (ECTA_TPB * 4)
 #define ECTA_WORDS (ECTA_TILE / 32)
 
-enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_JTICKET = 27, CTRL_PTICKET = 28, CTRL_GEO = 32,
+enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL_TICKET = 26, CTRL_JTICKET = 27, CTRL_PTICKET = 28,
+       CTRL_OVF_ANY = 29, CTRL_HTICKET = 30 /* 2 words */, CTRL_GEO = 32,
        CTRL_CE_SUM = 40 /* double */, CTRL_CE_CNT = 42, CTRL_CE_INV_N = 43 };
 enum { EMIT_PATH_STREAM = 0, EMIT_PATH_RECORDS = 1 };
 
@@ -44,6 +46,7 @@ struct LovaszParams {
     const void* labels;
     int N, C;
     long long HW, P, cap;
+    u32 inv_hw;                         // floor(2^32 / HW) (HW >= 2), for the pixel -> (image, offset) split
     int per_image, has_filter, filter, keep_absent, need_grad, dbg, interleave;
     u32 class_mask;
     int groups, n_seg;
@@ -80,9 +83,10 @@ struct LovaszParams {
 };
 
 struct LovaszLayout {
-    size_t ctrl, seg_fg, seg_maxkey, seg_maxp, seg_count, grp_valid, seg_loss, zero_end;
+    size_t ctrl, seg_fg, seg_maxkey, seg_maxp, seg_count, grp_valid, seg_loss, seg_loss_h, seg_ovf, zero_end;
     size_t seg_thr, seg_logthr, seg_w, seg_bits, grp_tmin, seg_order, run_cnt, run_prefix;
-    size_t pix_m, pix_s, gown, lab8, cmask, rec16, rec4, keysA, valsA, keysB, valsB, sort_scratch, total;
+    size_t pix_m, pix_s, gown, lab8, cmask, rec16, rec4, keysA, valsA, keysB, valsB, gbg, sort_scratch, total;
+    size_t hyb_hist, hyb_fgpre, hyb_done;
     SortScratch sort;
 };
 
@@ -130,6 +134,8 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     L.seg_count = o;  o = align_up(o + 4 * S, 256);
     L.grp_valid = o;  o = align_up(o + 4 * (size_t)groups, 256);
     L.seg_loss = o;   o = align_up(o + 8 * S, 256);
+    L.seg_loss_h = o; o = align_up(o + 8 * S, 256);
+    L.seg_ovf = o;    o = align_up(o + 4 * S, 256);
     L.zero_end = o;
     L.seg_thr = o;    o = align_up(o + 4 * S, 256);
     L.seg_logthr = o; o = align_up(o + 4 * S, 256);
@@ -150,8 +156,14 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     L.valsA = o;      o = align_up(o + 4 * holey, 256);
     L.keysB = o;      o = align_up(o + 4 * CP, 256);
     L.valsB = o;      o = align_up(o + 4 * CP, 256);
+    // background-candidate gradients, indexed like the logits.  (Not aliased onto the dead sort buffer A any more: the
+    // hybrid path's fallback re-reads the emission output in A after gradients have been written.)
+    L.gbg = o;        o = align_up(o + 4 * CP, 256);
     L.sort = sort_scratch_layout((int)S, (long long)CP);
     L.sort_scratch = o; o = align_up(o + L.sort.total, 256);
+    L.hyb_hist = o;   o = align_up(o + 4 * S * (size_t)HYB_MAX_BINS, 256);
+    L.hyb_done = o;   o = align_up(o + 4 * S, 256);
+    L.hyb_fgpre = o;  o = align_up(o + 4 * S * (size_t)HYB_MAX_BINS, 256);
     L.total = o;
     return L;
 }
@@ -1262,7 +1274,9 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
 }
 
 // K5b: loss = mean over groups of (mean over kept classes)      reference: mean(), losses/LovaszSoftmax.py:102-120
-__device__ void loss_finalize(const LovaszParams& p) {       // one thread
+// `hyb_loss` / `hyb_ovf` (hybrid path): a segment's sum comes from the local kernel unless the segment overflowed and went
+// through the LSD fallback
+__device__ void loss_finalize(const LovaszParams& p, const double* hyb_loss = nullptr, const u32* hyb_ovf = nullptr) {       // one thread
     float total = 0.f;
     for (int g = 0; g < p.groups; ++g) {
         float acc = 0.f;
@@ -1270,7 +1284,8 @@ __device__ void loss_finalize(const LovaszParams& p) {       // one thread
         for (int c = 0; c < p.C; ++c) {
             const size_t seg = (size_t)g * p.C + c;
             if (!thr_active(p.seg_thr[seg])) continue;
-            const float l = (float)__ldcg(p.seg_loss + seg);
+            const bool from_hyb = hyb_loss && !__ldcg(hyb_ovf + seg);
+            const float l = (float)__ldcg((from_hyb ? hyb_loss : p.seg_loss) + seg);
             acc = n ? acc + l : l;
             ++n;
         }
@@ -1284,7 +1299,34 @@ __device__ void loss_finalize(const LovaszParams& p) {       // one thread
 // --------------------------------------------------------------------------------------------------------------
 // K5: Jaccard gradient over the sorted candidates      reference: lovasz_grad, losses/LovaszSoftmax.py:83-95
 // --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(JAC_TPB, 4) jaccard_kernel(LovaszParams p, SortArgs a) {
+// One sorted candidate: position i in its segment, F foreground flags among positions 0..i.  Returns err * grad (the loss
+// term) and scatters the candidate's gradient g = +-grad * w to the pixel (lovasz_grad: J = 1 - I/U, first difference).
+__device__ __forceinline__ double jaccard_element(const LovaszParams& p, u32 key, u32 val, u32 i, u32 F, float gts, float w, int c) {
+    const u32 fgi = val & 1u;
+    const u32 B = i + 1 - F;                               // background among positions 0..i
+    const float J = 1.0f - __fdiv_rn(gts - (float)F, gts + (float)B);
+    float grad = J;
+    if (i > 0) {
+        const float Jp = 1.0f - __fdiv_rn(gts - (float)(F - fgi), gts + (float)(B - (1u - fgi)));
+        grad = __fsub_rn(J, Jp);
+    }
+    const float err = key_err(key);
+    if (p.need_grad) {
+        // d|fg - p|/dp = -sgn(fg - p): fg -> -1, bg -> +1, exactly 0 when the error is 0
+        const float gv = err > 0.f ? (fgi ? -grad : grad) * w : 0.f;
+        const u32 px = val >> 1;
+        if (fgi) p.gown[px] = gv;
+        else {
+            u32 ni = __umulhi(px, p.inv_hw);               // floor(px / HW) or one less (inv_hw = floor(2^32 / HW))
+            u32 q = px - ni * (u32)p.HW;
+            if (q >= (u32)p.HW) { ++ni; q -= (u32)p.HW; }
+            p.gbg[((size_t)ni * p.C + c) * (size_t)p.HW + q] = gv;
+        }
+    }
+    return (double)err * (double)grad;
+}
+
+__device__ __forceinline__ void jaccard_body(const LovaszParams& p, const SortArgs& a) {
     __shared__ u32 s_wfg[SORT_WARPS];
     __shared__ double s_red[SORT_WARPS];
     __shared__ u32 s_excl;
@@ -1294,9 +1336,10 @@ __global__ void __launch_bounds__(JAC_TPB, 4) jaccard_kernel(LovaszParams p, Sor
     const u32* keys = a.keys[1];
     const u32* vals = a.vals[1];
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        __syncthreads();
         const uint4 d4 = a.tile_desc[t];
         const int seg = (int)d4.x;
+        if (a.seg_sel && !a.seg_sel[seg]) continue;        // (CTA-uniform; before any barrier of the iteration)
+        __syncthreads();
         const u32 off = d4.y, n = d4.z;
         const u32 tis = off / SORT_TILE;
         const u32 tseg0 = t - tis;
@@ -1355,28 +1398,7 @@ __global__ void __launch_bounds__(JAC_TPB, 4) jaccard_kernel(LovaszParams p, Sor
             const u32 idx = wbase + k * 32;
             if (idx < n) {
                 const u32 i = off + idx;                  // position in the segment's sorted order
-                const u32 fgi = val[k] & 1u;
-                const u32 F = fbase + floc[k];            // foreground among positions 0..i
-                const u32 B = i + 1 - F;                  // background among positions 0..i
-                const float J = 1.0f - __fdiv_rn(gts - (float)F, gts + (float)B);
-                float grad = J;
-                if (i > 0) {
-                    const float Jp = 1.0f - __fdiv_rn(gts - (float)(F - fgi), gts + (float)(B - (1u - fgi)));
-                    grad = __fsub_rn(J, Jp);
-                }
-                const float err = key_err(key[k]);
-                acc += (double)err * (double)grad;
-                if (p.need_grad) {
-                    // d|fg - p|/dp = -sgn(fg - p): fg -> -1, bg -> +1, exactly 0 when the error is 0
-                    const float gv = err > 0.f ? (fgi ? -grad : grad) * w : 0.f;
-                    const u32 px = val[k] >> 1;
-                    if (fgi) p.gown[px] = gv;
-                    else {
-                        const u32 ni = px / (u32)p.HW;
-                        const u32 q = px - ni * (u32)p.HW;
-                        p.gbg[((size_t)ni * p.C + c) * (size_t)p.HW + q] = gv;
-                    }
-                }
+                acc += jaccard_element(p, key[k], val[k], i, fbase + floc[k], gts, w, c);
             }
         }
 #pragma unroll
@@ -1390,14 +1412,339 @@ __global__ void __launch_bounds__(JAC_TPB, 4) jaccard_kernel(LovaszParams p, Sor
             atomicAdd(p.seg_loss + seg, tot);
         }
     }
+}
+__global__ void __launch_bounds__(JAC_TPB, 4) jaccard_kernel(LovaszParams p, SortArgs a) {
+    jaccard_body(p, a);
     // the CTA that finishes last turns the per-segment sums into the loss (K5b)
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(p.ctrl + CTRL_JTICKET, 1u) == gridDim.x - 1) {
             __threadfence();
             loss_finalize(p);
         }
     }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K4h: hybrid path, local half.  After hyb_partition every segment is grouped into buckets of equal top-w key bits, in
+//      bucket order.  A work unit starts every LOC_T0 elements of a segment and owns the buckets that START inside its
+//      window [j*T0, (j+1)*T0): it finds them by comparing the digits of neighbouring keys (no bucket table), ranks their
+//      elements in shared memory, reads the number of foreground flags in front of its first bucket from the table
+//      hyb_count left (fgpre), and goes straight to the Jaccard gradient: units are independent of each other and the
+//      sorted order is never materialised, not even in shared memory.
+//      Ranking = ONE counting pass: the unit's keys span 2^kbits values (low L bits + the span of its bucket digits);
+//      LOC_BINS bins of 2^(kbits-13) values each hold (elements | foreground flags << 16), one exclusive scan gives
+//      every bin its first rank and the foreground flags before it, the elements are grouped by bin through an index
+//      array, and every element finds its rank inside its bin group (canonical order: key, then pixel index =
+//      torch.sort(stable=True)) by looking at the group's other members -- bins hold ~0.3 elements on average.  A unit
+//      with a bin group above LOC_TIE_MAX (heavy ties, a dense cluster next to a sparse tail) is sorted by stable LSD
+//      passes over value and key bits instead (loc_heavy_unit).
+//      reference: torch.sort + lovasz_grad + dot, losses/LovaszSoftmax.py:57-60,83-95
+// --------------------------------------------------------------------------------------------------------------
+#define LOC_NONE 0xFFFFFFFFu
+#define LOC_TIE_MAX 32                                     // longer bin groups take the LSD passes
+#define LOC_BIN_BITS 13
+#define LOC_BINS (1u << LOC_BIN_BITS)
+#define LOC_CNT_STRIDE 260                                 // u16 row stride of the LSD passes: 256 bins + dummy bin, rows 8-byte aligned
+
+struct LocSmem {
+    u32 keys[LOC_CAP];                                     // as loaded (partition order)
+    u32 vals[LOC_CAP];
+    unsigned short order[LOC_CAP];                         // element indices grouped by bin
+    u32 bins[LOC_BINS];                                    // (count | fg count << 16) -> exclusive starts -> cursors (LSD passes: u16 counters)
+    u32 warp_sum[LOC_WARPS];
+    double red[LOC_WARPS];
+    u32 s_first, s_end, heavy, skip;
+};
+
+// One stable counting pass over the unit's n elements by digit ((A - sub) >> shift) & 255; B is moved along.
+// Element m lives in row m / 32; warp w owns rows [w * rpw, (w + 1) * rpw), so the order (warp, row, lane) is the
+// element order and the per-warp counters + a scan across warps give stable positions.  (Rare path: not inlined.)
+__device__ __noinline__ void loc_pass(LocSmem& S, u32* A, u32* Bv, u32 n, u32 rpw, u32 sub, u32 shift) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lt_mask = (1u << lane) - 1;
+    unsigned short (*cnt)[LOC_CNT_STRIDE] = reinterpret_cast<unsigned short (*)[LOC_CNT_STRIDE]>(S.bins);
+    unsigned short* binexcl = reinterpret_cast<unsigned short*>(S.bins) + LOC_WARPS * LOC_CNT_STRIDE;
+    for (u32 i = tid; i < LOC_WARPS * LOC_CNT_STRIDE / 2; i += LOC_TPB) S.bins[i] = 0;
+    u32 a[LOC_KPT], rnk[LOC_KPT];
+    const u32 wb = warp * rpw * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < LOC_KPT; ++k) a[k] = ((u32)k < rpw && wb + k * 32 < n) ? A[wb + k * 32] : 0u;
+    __syncthreads();                                       // counters cleared; every element of A is in a register
+#pragma unroll
+    for (int k = 0; k < LOC_KPT; ++k) {
+        if ((u32)k < rpw) {                                // (warp-uniform)
+            const u32 d = (wb + k * 32 < n) ? (((a[k] - sub) >> shift) & 255u) : 256u;
+            const u32 m = peer_mask<9>(d);
+            const int leader = __ffs(m) - 1;
+            u32 old = 0;
+            if (lane == leader) { old = cnt[warp][d]; cnt[warp][d] = (unsigned short)(old + __popc(m)); }
+            rnk[k] = __shfl_sync(FULL_MASK, old, leader) + __popc(m & lt_mask);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // thread b < 64 owns bins [4b, 4b+4): four u16 counters travel as one 64-bit word (no carries: totals <= LOC_CAP)
+    u64 run = 0;
+    if (tid < 64) {
+        for (int w2 = 0; w2 < LOC_WARPS; ++w2) {
+            u64* c4 = reinterpret_cast<u64*>(&cnt[w2][4 * tid]);
+            const u64 c = *c4;
+            *c4 = run;
+            run += c;
+        }
+    }
+    u32 tot[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tot[j] = (u32)((run >> (16 * j)) & 0xFFFFu);
+    const u32 tsum = tot[0] + tot[1] + tot[2] + tot[3];
+    u32 v = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
+    if (lane == 31 && warp < 2) S.warp_sum[warp] = v;
+    __syncthreads();
+    if (tid < 64) {
+        const u32 e0 = v - tsum + (warp ? S.warp_sum[0] : 0u);
+        const u32 e1 = e0 + tot[0], e2 = e1 + tot[1], e3 = e2 + tot[2];
+        *reinterpret_cast<uint2*>(&binexcl[4 * tid]) = make_uint2(e0 | (e1 << 16), e2 | (e3 << 16));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LOC_KPT; ++k) {
+        if ((u32)k < rpw && wb + k * 32 < n) {
+            const u32 d = ((a[k] - sub) >> shift) & 255u;
+            rnk[k] = (u32)binexcl[d] + cnt[warp][d] + rnk[k];
+            A[rnk[k]] = a[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LOC_KPT; ++k) a[k] = ((u32)k < rpw && wb + k * 32 < n) ? Bv[wb + k * 32] : 0u;
+    __syncthreads();                                       // every element of B is in a register
+#pragma unroll
+    for (int k = 0; k < LOC_KPT; ++k)
+        if ((u32)k < rpw && wb + k * 32 < n) Bv[rnk[k]] = a[k];
+    __syncthreads();
+}
+
+// The rare unit with a long bin group: full stable sort of (K, V) in place (LSD over the value bits, then the key bits),
+// then foreground prefix by ballots in sorted order and the gradient.  `fexcl` = foreground flags in front of the unit.
+__device__ __noinline__ double loc_heavy_unit(const LovaszParams& p, LocSmem& S, u32* K, u32* V, u32 n, u32 sub, u32 kbits,
+                                              u32 valbits, u32 pos0, u32 fexcl, float gts, float w, int c) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 le_mask = lane == 31 ? FULL_MASK : ((2u << lane) - 1u);
+    const u32 rpw = ((n + 31) / 32 + LOC_WARPS - 1) / LOC_WARPS;
+    for (u32 sh = 0; sh < valbits; sh += 8) loc_pass(S, V, K, n, rpw, 0u, sh);
+    for (u32 sh = 0; sh < kbits; sh += 8) loc_pass(S, K, V, n, rpw, sub, sh);
+    const u32 wb = warp * rpw * 32 + lane;
+    u32 run = 0;
+    for (u32 k = 0; k < rpw; ++k) {
+        const u32 idx = wb + k * 32;
+        run += __popc(__ballot_sync(FULL_MASK, idx < n && (V[idx] & 1u)));
+    }
+    if (lane == 0) S.warp_sum[warp] = run;
+    __syncthreads();
+    u32 frun = fexcl;
+    for (int w2 = 0; w2 < warp; ++w2) frun += S.warp_sum[w2];
+    double acc = 0.0;
+    for (u32 k = 0; k < rpw; ++k) {
+        const u32 idx = wb + k * 32;
+        const u32 v = idx < n ? V[idx] : 0u;
+        const u32 bal = __ballot_sync(FULL_MASK, idx < n && (v & 1u));
+        if (idx < n) acc += jaccard_element(p, K[idx], v, pos0 + idx, frun + __popc(bal & le_mask), gts, w, c);
+        frun += __popc(bal);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, SortArgs a, HybArgs h, u32 max_tiles) {
+    extern __shared__ __align__(16) unsigned char loc_smem_raw[];
+    LocSmem& S = *reinterpret_cast<LocSmem*>(loc_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 total_tiles = min(a.tile_start[a.n_seg], max_tiles);
+    const u32 n_work = total_tiles * LOC_PER_SORT_TILE;
+    const u32* __restrict__ gkeys = a.keys[1];
+    const u32* __restrict__ gvals = a.vals[1];
+    const u32 valbits = 32u - (u32)__clz((int)(2u * (u32)p.P - 1u));     // bits of the largest value (pixel << 1 | fg)
+    uint4 d4_next = blockIdx.x < n_work ? a.tile_desc[blockIdx.x / LOC_PER_SORT_TILE] : make_uint4(0, 0, 0, 0);
+    for (u32 lt = blockIdx.x; lt < n_work; lt += gridDim.x) {
+        const uint4 d4 = d4_next;
+        if (lt + gridDim.x < n_work) d4_next = a.tile_desc[(lt + gridDim.x) / LOC_PER_SORT_TILE];   // one unit ahead
+        const int seg = (int)d4.x;
+        const u32 p0 = d4.y + (lt % LOC_PER_SORT_TILE) * LOC_T0;
+        const u32 ns = a.seg_count[seg];
+        if (p0 >= ns) continue;                            // (CTA-uniform) no such unit
+        const float gts = (float)p.seg_fg[seg];
+        const float w = p.seg_w[seg];
+        __syncthreads();                                   // previous unit done with the shared state
+        // (the give-up flag of the segment can be raised by another CTA at any time: one thread reads it, all follow that reading)
+        if (tid == 0) { S.s_first = LOC_NONE; S.s_end = LOC_NONE; S.heavy = 0; S.skip = ld_relaxed(h.seg_ovf + seg); }
+        const u32 L = hyb_plan(a.seg_bits[seg], ns).L;
+        const size_t sbase = (size_t)seg * a.cap + p0;
+        const u32 avail = min(ns - p0, (u32)LOC_CAP);
+
+        // ---- the unit's buckets: first digit change at or after p0, first digit change at or after p0 + T0 ----------
+        // (keys and values travel global -> shared as 16-byte cp.async copies: no load -> store round trip per element)
+        const bool al16 = ((sbase & 3) == 0) && ((a.cap & 3) == 0) && ((((uintptr_t)gkeys | (uintptr_t)gvals) & 15) == 0);
+        u32 prevkey = 0;
+        if (tid == 0 && p0 > 0) prevkey = gkeys[sbase - 1];
+        u32 loaded = 0, checked = 0, target = min(avail, (u32)(LOC_T0 + 1024));
+        for (;;) {
+            if (al16) {                                    // (whole 16-byte chunks: may read up to 3 elements past `target`, inside the segment)
+                for (u32 ch = loaded / 4 + tid; ch < (target + 3) / 4; ch += LOC_TPB) {
+                    cp_async<16>(&S.keys[4 * ch], gkeys + sbase + 4 * ch);
+                    cp_async<16>(&S.vals[4 * ch], gvals + sbase + 4 * ch);
+                }
+            } else {
+                for (u32 i = loaded + tid; i < target; i += LOC_TPB) {
+                    cp_async<4>(&S.keys[i], gkeys + sbase + i);
+                    cp_async<4>(&S.vals[i], gvals + sbase + i);
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            if (S.skip) break;                             // (CTA-uniform) segment already given up
+            for (u32 i = checked + tid; i < target; i += LOC_TPB) {
+                bool bnd = p0 + i == 0;
+                if (!bnd) {
+                    const u32 prev = i > 0 ? S.keys[i - 1] : prevkey;      // (i == 0: thread 0, which holds the predecessor)
+                    bnd = (S.keys[i] >> L) != (prev >> L);
+                }
+                if (bnd) atomicMin(i < LOC_T0 ? &S.s_first : &S.s_end, i);
+            }
+            __syncthreads();
+            checked = target;
+            loaded = al16 ? ((target + 3) & ~3u) : target;
+            if (S.s_end != LOC_NONE || S.s_first == LOC_NONE || checked == avail) break;
+            target = avail;
+        }
+        const u32 s_rel = S.s_first;
+        if (S.skip || s_rel == LOC_NONE) continue;         // segment given up / the window lies inside a bucket of an earlier unit
+        u32 e_rel = S.s_end;
+        if (e_rel == LOC_NONE) {
+            if (p0 + avail == ns) e_rel = avail;           // the segment ends here
+            else {                                         // a bucket too long for shared memory: LSD fallback for the segment
+                if (tid == 0) { atomicExch(h.seg_ovf + seg, 1u); atomicExch(h.ovf_any, 1u); }
+                continue;
+            }
+        }
+        const u32 n = e_rel - s_rel;
+        u32* K = S.keys + s_rel;
+        u32* V = S.vals + s_rel;
+        if (p.dbg & 32) continue;
+        // ---- counting pass over the span of the unit's keys ---------------------------------------------------------------------
+        const u32 dmin = K[0] >> L, dmax = K[n - 1] >> L;                   // buckets lie in digit order
+        const u32 sub = dmin << L;
+        const u32 kbits = L + (dmax > dmin ? 32u - (u32)__clz((int)(dmax - dmin)) : 0u);
+        const u32 bsh = kbits > LOC_BIN_BITS ? kbits - LOC_BIN_BITS : 0u;
+        const u32 fexcl = __ldcg(h.fgpre + (size_t)seg * HYB_MAX_BINS + dmin);      // foreground flags in front of the unit
+        {
+            uint4* z = reinterpret_cast<uint4*>(S.bins);
+            for (u32 i = tid; i < LOC_BINS / 4; i += LOC_TPB) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        for (u32 i = tid; i < n; i += LOC_TPB) atomicAdd(&S.bins[(K[i] - sub) >> bsh], 1u + ((V[i] & 1u) << 16));
+        __syncthreads();
+        {   // exclusive scan of both halves at once (totals <= LOC_CAP: no carry); thread t owns bins [16t, 16t + 16)
+            uint4* b4 = reinterpret_cast<uint4*>(S.bins) + 4 * tid;
+            uint4 c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = b4[j];
+            u32 sum = 0, big = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sum += c[j].x + c[j].y + c[j].z + c[j].w;
+                big |= ((c[j].x & 0xFFFFu) > LOC_TIE_MAX) | ((c[j].y & 0xFFFFu) > LOC_TIE_MAX) | ((c[j].z & 0xFFFFu) > LOC_TIE_MAX) |
+                       ((c[j].w & 0xFFFFu) > LOC_TIE_MAX);
+            }
+            if (big) S.heavy = 1;
+            u32 v = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
+            if (lane == 31) S.warp_sum[warp] = v;
+            __syncthreads();
+            u32 run = v - sum;
+#pragma unroll
+            for (int w2 = 0; w2 < LOC_WARPS; ++w2) if (w2 < warp) run += S.warp_sum[w2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 o4;
+                o4.x = run; run += c[j].x;
+                o4.y = run; run += c[j].y;
+                o4.z = run; run += c[j].z;
+                o4.w = run; run += c[j].w;
+                b4[j] = o4;
+            }
+        }
+        __syncthreads();
+        const bool heavy = S.heavy != 0;
+        if (p.dbg & 16) continue;
+        if (!heavy) {                                      // group the elements by bin (arrival order inside a bin)
+            for (u32 i = tid; i < n; i += LOC_TPB) S.order[atomicAdd(&S.bins[(K[i] - sub) >> bsh], 1u) & 0xFFFFu] = (unsigned short)i;
+            __syncthreads();
+        }
+        const int c = seg % p.C;
+        const u32 pos0 = p0 + s_rel;                       // position of the unit's first element in its segment
+        double acc = 0.0;
+        if (heavy) acc = loc_heavy_unit(p, S, K, V, n, sub, kbits, valbits, pos0, fexcl, gts, w, c);     // (CTA-uniform)
+        else {
+            // ---- rank inside the bin group, Jaccard gradient ------------------------------------------------------------------
+            for (u32 i = tid; i < n; i += LOC_TPB) {
+                const u32 k = K[i], v = V[i];
+                const u32 b = (k - sub) >> bsh;
+                const u32 lo = b ? S.bins[b - 1] : 0u;     // bins[b - 1]: (end of bin b-1 = start of b) | fg flags before bin b-1 ...
+                const u32 hi = S.bins[b];                  // ... and bins[b]: end of b | fg flags before bin b
+                const u32 start = lo & 0xFFFFu, stop = hi & 0xFFFFu;
+                u32 rank = start, F = fexcl + (hi >> 16) + (v & 1u);
+                for (u32 j = start; j < stop; ++j) {
+                    const u32 o = S.order[j];
+                    const u32 k2 = K[o], v2 = V[o];
+                    const bool less = k2 < k || (k2 == k && v2 < v);
+                    rank += less;
+                    F += less & (v2 & 1u);
+                }
+                if (p.dbg & 8) acc += (double)(rank + F); else
+                acc += jaccard_element(p, k, v, pos0 + rank, F, gts, w, c);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+        if (lane == 0) S.red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < LOC_WARPS; ++w2) tot += S.red[w2];
+            atomicAdd(h.seg_loss + seg, tot);
+        }
+    }
+    // the CTA that finishes last turns the per-segment sums into the loss, unless a segment needs the fallback
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(h.ticket + 1, 1u) == gridDim.x - 1) {
+            __threadfence();
+            if (!ld_relaxed(h.ovf_any)) loss_finalize(p, h.seg_loss, h.seg_ovf);
+        }
+    }
+}
+
+// Fallback of the hybrid path: the segments the local kernel gave up on go through the three-pass LSD sort and the
+// Jaccard kernel of the plain path, fused into one cooperative launch (phases separated by grid barriers) that returns
+// at once when no segment overflowed -- the usual case.
+__global__ void __launch_bounds__(SORT_TPB, 2) sort_fallback_kernel(LovaszParams p, SortArgs a, HybArgs h, u32 max_tiles) {
+    if (!ld_relaxed(h.ovf_any)) return;                    // (grid-uniform: written by an earlier launch)
+    for (int pass = 0; pass < SORT_PASSES; ++pass) {
+        sort_count_body(a, pass, max_tiles);
+        grid_barrier(a.gbar + 2 * SORT_PASSES + 2 * pass, a.status);
+        if (pass == 0) sort_scatter_body<false, true>(a, pass, max_tiles);
+        else sort_scatter_body<false, false>(a, pass, max_tiles);
+        grid_barrier(a.gbar + 2 * SORT_PASSES + 2 * pass + 1, a.status);
+    }
+    sort_fg_count_body(a, max_tiles);
+    grid_barrier(a.gbar + 4 * SORT_PASSES, a.status);
+    jaccard_body(p, a);
+    grid_barrier(a.gbar + 4 * SORT_PASSES + 1, a.status);
+    if (blockIdx.x == 0 && threadIdx.x == 0) loss_finalize(p, h.seg_loss, h.seg_ovf);
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -1713,6 +2060,59 @@ __global__ void __launch_bounds__(BWD_TPB) backward_kernel_generic(LovaszParams 
     }
 }
 
+// Enqueue the hybrid path: prepare, bucket histogram, partition, local sort + Jaccard, fallback (a no-op unless a
+// segment overflowed).  All decisions are taken on the device.
+static int hybrid_enqueue(const LovaszParams& p, const SortArgs& a, const HybArgs& h, const SortScratch& L, cudaStream_t st) {
+    static bool attr_set[64] = {false};
+    static int fb_occ[64] = {0};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    const bool cached = dev >= 0 && dev < 64;
+    if (!cached || !attr_set[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(hyb_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * HYB_MAX_BINS * sizeof(u32))));
+        CUDA_TRY(cudaFuncSetAttribute(hyb_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(hyb_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LocSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(sort_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_fallback_kernel, SORT_TPB, sizeof(ScatterSmem)));
+        if (cached) { fb_occ[dev] = occ < 1 ? 1 : occ; attr_set[dev] = true; }
+    }
+    const int sms = b200seg_sm_count();
+    {
+        const int pgrid = a.n_seg < sms ? a.n_seg : sms;
+        sort_prepare_kernel<<<pgrid, SORT_PREP_TPB, 0, st>>>(a, h, L.max_tiles);
+        LAUNCH_CHECK("sort_prepare_kernel");
+    }
+    b200seg_stage(4, st);
+    const u32 cgrid = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;
+    hyb_count_kernel<<<cgrid, SORT_TPB, 2 * HYB_MAX_BINS * sizeof(u32), st>>>(a, h, L.max_tiles);
+    LAUNCH_CHECK("hyb_count_kernel");
+    b200seg_stage(5, st);
+    const u32 pgrid2 = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;
+    hyb_partition_kernel<<<pgrid2, SORT_TPB, sizeof(PartSmem), st>>>(a, h, L.max_tiles);
+    LAUNCH_CHECK("hyb_partition_kernel");
+    b200seg_stage(6, st);
+    if (p.dbg & 128) return 0;                             // (debugging: stop after the partition)
+    const u32 units = L.max_tiles * LOC_PER_SORT_TILE;
+    const u32 lgrid = units < (u32)sms * 2 ? units : (u32)sms * 2;
+    hyb_local_kernel<<<lgrid, LOC_TPB, sizeof(LocSmem), st>>>(p, a, h, L.max_tiles);
+    LAUNCH_CHECK("hyb_local_kernel");
+    b200seg_stage(7, st);
+    {   // cooperative: the grid barriers between its phases need the whole grid resident
+        SortArgs a_fb = a;
+        a_fb.seg_sel = h.seg_ovf;
+        LovaszParams p_copy = p;
+        HybArgs h_copy = h;
+        u32 bound = L.max_tiles;
+        const u32 per_sm = cached ? (u32)fb_occ[dev] : 1u;
+        const u32 fgrid = L.max_tiles < (u32)sms * per_sm ? L.max_tiles : (u32)sms * per_sm;
+        void* args[] = {(void*)&p_copy, (void*)&a_fb, (void*)&h_copy, (void*)&bound};
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)sort_fallback_kernel, dim3(fgrid), dim3(SORT_TPB), args,
+                                             sizeof(ScatterSmem), st));
+    }
+    return 0;
+}
+
 // --------------------------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------------------------
@@ -1735,6 +2135,7 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
                         int32_t keep_absent, uint32_t class_mask) {
     p.logits = logits; p.labels = labels;
     p.N = n; p.C = c; p.HW = hw; p.P = (long long)n * hw;
+    p.inv_hw = hw >= 2 ? (u32)((1ull << 32) / (unsigned long long)hw) : 0xFFFFFFFFu;
     p.per_image = per_image ? 1 : 0;
     p.groups = per_image ? n : 1;
     p.n_seg = p.groups * c;
@@ -1761,7 +2162,7 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.geo_stream = EmitGeomDev{0, 0, 0, 0}; p.geo_rec = EmitGeomDev{0, 0, 0, 0};
     p.keysA = (u32*)(ws + L.keysA); p.valsA = (u32*)(ws + L.valsA);
     p.keysB = (u32*)(ws + L.keysB); p.valsB = (u32*)(ws + L.valsB);
-    p.gbg = (float*)(ws + L.keysA);      // free again once the sort result sits in buffer B
+    p.gbg = (float*)(ws + L.gbg);
     p.cm = nullptr; p.has_drop = 0; p.drop = 0;
     p.status = (int*)(p.ctrl + CTRL_STATUS);
     p.loss_out = nullptr; p.need_grad = 1; p.dbg = 0;
@@ -1978,11 +2379,18 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
     a.bin_base = (u32*)(ss + L.sort.bin_base); a.tile_fg = (u32*)(ss + L.sort.tile_fg);
     a.big = (u32*)(ss + L.sort.big); a.chunksum = (u32*)(ss + L.sort.chunksum); a.gbar = (u32*)(ss + L.sort.gbar);
     a.status = p.status;
-    if (int rc = sort_enqueue(a, L.sort, st)) return rc;
-
-    // K5
-    jaccard_kernel<<<sms * 4, JAC_TPB, 0, st>>>(p, a);
-    LAUNCH_CHECK("jaccard_kernel");
+    a.seg_sel = nullptr;
+    if (b200seg_tuning().sort_path == 1) {                 // plain path: three LSD passes, then the Jaccard kernel
+        if (int rc = sort_enqueue(a, L.sort, st)) return rc;
+        jaccard_kernel<<<sms * 4, JAC_TPB, 0, st>>>(p, a);
+        LAUNCH_CHECK("jaccard_kernel");
+    } else {                                               // hybrid path: one MSD partition pass + the fused local kernel
+        HybArgs h;
+        h.hist = (u32*)(ws + L.hyb_hist); h.fgpre = (u32*)(ws + L.hyb_fgpre); h.seg_done = (u32*)(ws + L.hyb_done);
+        h.ticket = p.ctrl + CTRL_HTICKET; h.seg_ovf = (u32*)(ws + L.seg_ovf); h.ovf_any = p.ctrl + CTRL_OVF_ANY;
+        h.seg_loss = (double*)(ws + L.seg_loss_h);
+        if (int rc = hybrid_enqueue(p, a, h, L.sort, st)) return rc;
+    }
     b200seg_stage(8, st);
     return 0;
 }
@@ -2094,6 +2502,10 @@ extern "C" int b200seg_debug_layout(int32_t n, int32_t c, int64_t hw, int32_t pe
     const LovaszLayout L = lovasz_layout(n, c, hw, per_image);
     offsets[0] = L.pix_m; offsets[1] = L.pix_s; offsets[2] = L.lab8; offsets[3] = L.cmask;
     offsets[4] = L.rec16; offsets[5] = L.rec4; offsets[6] = L.seg_thr; offsets[7] = L.grp_tmin;
+    if (n_offsets >= 14) {
+        offsets[8] = L.keysB; offsets[9] = L.valsB; offsets[10] = L.seg_count; offsets[11] = L.seg_bits;
+        offsets[12] = L.hyb_hist; offsets[13] = L.hyb_fgpre;
+    }
     return 0;
 }
 
@@ -2149,6 +2561,6 @@ extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint3
     a.seg_done = (u32*)(ss + L.seg_done);
     a.bin_base = (u32*)(ss + L.bin_base); a.tile_fg = (u32*)(ss + L.tile_fg);
     a.big = (u32*)(ss + L.big); a.chunksum = (u32*)(ss + L.chunksum); a.gbar = (u32*)(ss + L.gbar);
-    a.status = status;
+    a.status = status; a.seg_sel = nullptr;
     return sort_enqueue(a, L, (cudaStream_t)stream);
 }

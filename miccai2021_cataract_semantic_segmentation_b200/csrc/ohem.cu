@@ -174,7 +174,7 @@ __device__ __forceinline__ void ohem_grid_barrier(u32* ctr, int* status) {
         atomicAdd(ctr, 1u);
         u32 spins = 0;
         while (ld_relaxed(ctr) < gridDim.x) {
-            if (++spins > SPIN_LIMIT) { atomicOr(status, STATUS_SPIN_TIMEOUT); break; }
+            if (++spins > SPIN_LIMIT) { atomicOr(status, STATUS_SPIN_TIMEOUT); __threadfence_system(); __trap(); }
             __nanosleep(32);
         }
         __threadfence();

@@ -63,9 +63,11 @@ struct SortArgs {
     u32* tile_fg;           // [max_tiles] foreground flags per tile of the final order (sort_fg_count_kernel)
     u32* big;               // [1 + n_seg] number of segments with > SORT_SCAN_LOCAL_MAX tiles, then their ids
     u32* chunksum;          // [max_chunks][1024] per-chunk digit sums -> exclusive chunk offsets (big segments only)
-    u32* gbar;              // [2 * SORT_PASSES] grid-barrier counters of the scatter kernels
+    u32* gbar;              // [SORT_GBAR] grid-barrier counters: 2 per pass (sort_big_scan), the rest for the fused fallback
     int* status;
+    const u32* seg_sel;     // nullptr: every segment; else only segments with seg_sel[seg] != 0 are processed
 };
+#define SORT_GBAR 24
 
 struct SortScratch {
     size_t tile_start, tile_desc, tile_runs, seg_done, tilehist, bin_base, tile_fg, big, chunksum, gbar, total;
@@ -83,12 +85,55 @@ static inline SortScratch sort_scratch_layout(int n_seg, long long total_capacit
     L.bin_base = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_MAX_BINS, 256);
     L.tile_fg = o;    o = align_up(o + sizeof(u32) * (size_t)L.max_tiles, 256);
     L.big = o;        o = align_up(o + sizeof(u32) * (size_t)(n_seg + 1), 256);
-    L.gbar = o;       o = align_up(o + sizeof(u32) * 2 * SORT_PASSES, 256);
+    L.gbar = o;       o = align_up(o + sizeof(u32) * SORT_GBAR, 256);
     L.chunksum = o;   o = align_up(o + sizeof(u32) * ((size_t)L.max_tiles / SORT_CHUNK + n_seg + 2) * SORT_MAX_BINS, 256);
     L.tilehist = o;   o = align_up(o + sizeof(u32) * (size_t)L.max_tiles * SORT_MAX_BINS, 256);
     L.total = o;
     return L;
 }
+
+// ---- hybrid path (hybrid.cuh, hyb_local_kernel): shared definitions -------------------------------------------------
+// local tiles: the local kernel's work unit starts every LOC_T0 elements of a segment and owns the buckets that START in
+// its window; LOC_CAP bounds what it can hold in shared memory (a bucket longer than LOC_CAP - LOC_T0 may overflow it)
+#define LOC_TPB 512
+#define LOC_WARPS (LOC_TPB / 32)
+#define LOC_KPT 16
+#define LOC_CAP (LOC_TPB * LOC_KPT)
+#ifndef LOC_T0
+#define LOC_T0 4096
+#endif
+#define LOC_PER_SORT_TILE (SORT_TILE / LOC_T0)
+#define HYB_MAX_W 13
+#define HYB_MAX_BINS (1u << HYB_MAX_W)
+
+struct HybArgs {
+    u32* hist;          // [n_seg][HYB_MAX_BINS] bucket counts -> exclusive bucket offsets -> running cursors
+    u32* fgpre;         // [n_seg][HYB_MAX_BINS] foreground flags per bucket -> foreground flags in front of the bucket
+    u32* seg_done;      // [n_seg] tiles of the segment counted so far
+    u32* ticket;        // [2] work ticket of the local kernel, CTAs of it that have finished
+    u32* seg_ovf;       // [n_seg] 1 = a bucket of the segment did not fit: the segment goes through the LSD fallback
+    u32* ovf_any;       // [1]
+    double* seg_loss;   // [n_seg] loss sums of the local kernel (the fallback sums into LovaszParams::seg_loss)
+};
+
+struct HybPlan { u32 w, L; };   // partition digit = key >> L, w bits wide
+__host__ __device__ __forceinline__ HybPlan hyb_plan(u32 bits, u32 n) {
+#ifdef __CUDA_ARCH__
+    const u32 lg = n <= 1 ? 0u : 32u - (u32)__clz((int)(n - 1));   // ceil(log2 n)
+#else
+    u32 lg = 0;
+    while (lg < 31 && (1u << lg) < n) ++lg;
+#endif
+    int w = (int)lg - 6;
+    if (w < 0) w = 0;
+    if (w > HYB_MAX_W) w = HYB_MAX_W;
+    if (w > (int)bits) w = (int)bits;
+    HybPlan p;
+    p.w = (u32)w;
+    p.L = bits - (u32)w;
+    return p;
+}
+
 
 __device__ __forceinline__ u32 sort_digit_width(u32 bits) {
     u32 w = (bits + SORT_PASSES - 1) / SORT_PASSES;
@@ -118,7 +163,7 @@ __device__ __forceinline__ size_t sort_runs_slot(const SortArgs& a, int seg, u32
     return (size_t)(((long long)seg * a.cap) / SORT_TILE) + (size_t)seg + tl;
 }
 
-__global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a, u32 max_tiles) {
+__global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a, HybArgs h, u32 max_tiles) {
     __shared__ u32 s_warp[32];
     __shared__ u32 s_carry, s_lastrun, s_islast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -158,6 +203,13 @@ __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a,
             }
             const u32 cnt = s_carry, nt = (cnt + SORT_TILE - 1) / SORT_TILE;
             if (tid == 0) { out[n_runs] = cnt; a.seg_count_w[seg] = cnt; }
+            if (h.hist) {                                  // hybrid path: clear the segment's bucket histogram
+                const u32 nb = 1u << hyb_plan(a.seg_bits[seg], cnt).w;
+                u32* gh = h.hist + (size_t)seg * HYB_MAX_BINS;
+                u32* gf = h.fgpre + (size_t)seg * HYB_MAX_BINS;
+                for (u32 b = tid; b < nb; b += SORT_PREP_TPB) { gh[b] = 0; gf[b] = 0; }
+                if (tid == 0) h.seg_done[seg] = 0;
+            }
             // last run a tile touches: at most the first run of the next tile (a bound is enough: it sizes the window)
             for (u32 tl = tid; tl < nt; tl += SORT_PREP_TPB) truns[tl].y = tl + 1 < nt ? truns[tl + 1].x : s_lastrun;
         }
@@ -196,12 +248,15 @@ __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a,
     }
     const u32 total = s_carry;
     if (tid == 0) { a.tile_start[a.n_seg] = total; a.big[0] = 0; }
-    if (tid < 2 * SORT_PASSES) a.gbar[tid] = 0;
+    if (tid < SORT_GBAR) a.gbar[tid] = 0;
     __syncthreads();
     for (int sg = tid; sg < a.n_seg; sg += SORT_PREP_TPB)
         if ((__ldcg(a.seg_count + sg) + SORT_TILE - 1) / SORT_TILE > SORT_SCAN_LOCAL_MAX) a.big[1 + atomicAdd(a.big, 1u)] = (u32)sg;
     for (int i = tid; i < a.n_seg * SORT_PASSES; i += SORT_PREP_TPB) a.seg_done[i] = 0;
     for (u32 i = tid; i < total && i < max_tiles; i += SORT_PREP_TPB) a.tile_fg[i] = 0;
+    if (h.hist) {
+        if (tid < 2) h.ticket[tid] = 0;
+    }
     __syncthreads();
     for (int seg = warp; seg < a.n_seg; seg += SORT_PREP_TPB / 32) {      // descriptors: a warp per segment
         const u32 t_first = a.tile_start[seg], nt = a.tile_start[seg + 1] - t_first;
@@ -313,7 +368,7 @@ __device__ __forceinline__ void segment_scan(const SortArgs& a, u32* rows, int s
 }
 
 // ---- count: per-tile digit histogram (+ the segment's scan once its last tile is in) ---------------------------------
-__global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pass, u32 total_bound) {
+__device__ __forceinline__ void sort_count_body(const SortArgs& a, int pass, u32 total_bound) {
     __shared__ __align__(16) u32 s_hist[SORT_MAX_BINS];
     __shared__ u32 s_win[SORT_RUN_WINDOW + 1];
     __shared__ u32 s_warp[SORT_WARPS];
@@ -325,6 +380,7 @@ __global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pa
         const int seg = (int)d4.x;
         const u32 off = d4.y, n = d4.z, w = d4.w;
         const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
+        if (a.seg_sel && !a.seg_sel[seg]) continue;        // (CTA-uniform)
         __syncthreads();                                   // previous iteration done with s_hist / s_win
         for (u32 b = tid; b < SORT_MAX_BINS; b += SORT_TPB) s_hist[b] = 0;
         const TileSrc T = tile_src_setup(a, pass, t, seg, off, s_win);
@@ -354,6 +410,9 @@ __global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pa
             segment_scan(a, a.tilehist, seg, tseg0, tseg0 + ntiles_seg, nbins, s_warp);
         }
     }
+}
+__global__ void __launch_bounds__(SORT_TPB) sort_count_kernel(SortArgs a, int pass, u32 total_bound) {
+    sort_count_body(a, pass, total_bound);
 }
 
 // ---- scatter ----------------------------------------------------------------------------------------------------------------
@@ -429,7 +488,11 @@ __device__ __forceinline__ void grid_barrier(u32* ctr, int* status) {
         u32 spins = 0;
         while (ld_relaxed(ctr) < gridDim.x) {
             __nanosleep(64);
-            if (++spins >= SPIN_LIMIT) { atomicOr(status, STATUS_SPIN_TIMEOUT); break; }
+            if (++spins >= SPIN_LIMIT) {                     // never compute on incomplete data: flag it and kill the stream
+                atomicOr(status, STATUS_SPIN_TIMEOUT);
+                __threadfence_system();
+                __trap();
+            }
         }
         __threadfence();
     }
@@ -443,6 +506,7 @@ __device__ __forceinline__ void sort_big_scan(const SortArgs& a, int pass, u32* 
     u32 unit = 0;
     for (u32 j = 0; j < n_big; ++j) {                      // phase 1
         const int seg = (int)a.big[1 + j];
+        if (a.seg_sel && !a.seg_sel[seg]) continue;
         const u32 t0 = a.tile_start[seg], nt = a.tile_start[seg + 1] - t0;
         const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]), nch = (nt + SORT_CHUNK - 1) / SORT_CHUNK;
         for (u32 lc = 0; lc < nch; ++lc, ++unit) {
@@ -467,6 +531,7 @@ __device__ __forceinline__ void sort_big_scan(const SortArgs& a, int pass, u32* 
     grid_barrier(a.gbar + 2 * pass, a.status);
     for (u32 j = blockIdx.x; j < n_big; j += gridDim.x) {  // phase 2
         const int seg = (int)a.big[1 + j];
+        if (a.seg_sel && !a.seg_sel[seg]) continue;
         const u32 t0 = a.tile_start[seg], nt = a.tile_start[seg + 1] - t0;
         const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]), nch = (nt + SORT_CHUNK - 1) / SORT_CHUNK;
         const u32 c0 = sort_chunk_id(t0, seg, 0);
@@ -480,8 +545,7 @@ __device__ __forceinline__ void sort_big_scan(const SortArgs& a, int pass, u32* 
 // GATHER = false: compact source; the values are loaded only when they are placed, so key + rank are all that lives in
 // registers through the ranking and the kernel fits 4 CTAs per SM (1100 tiles: 2 rounds of 592 instead of 3 of 444).
 template <bool USE_MATCH, bool GATHER>
-__global__ void __launch_bounds__(SORT_TPB, GATHER ? SORT_SCATTER_MINB : SORT_SCATTER_MINB + 1)
-sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
+__device__ __forceinline__ void sort_scatter_body(const SortArgs& a, int pass, u32 total_bound) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -499,6 +563,7 @@ sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
         const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
         u32* __restrict__ ko = kout + (size_t)seg * a.cap;
         u32* __restrict__ vo = vout + (size_t)seg * a.cap;
+        if (a.seg_sel && !a.seg_sel[seg]) continue;        // (CTA-uniform)
         __syncthreads();
         {
             uint2* z = reinterpret_cast<uint2*>(&S.cnt[0][0]);
@@ -627,14 +692,20 @@ sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
         }
     }
 }
+template <bool USE_MATCH, bool GATHER>
+__global__ void __launch_bounds__(SORT_TPB, GATHER ? SORT_SCATTER_MINB : SORT_SCATTER_MINB + 1)
+sort_scatter_kernel(SortArgs a, int pass, u32 total_bound) {
+    sort_scatter_body<USE_MATCH, GATHER>(a, pass, total_bound);
+}
 
 // foreground flags (value bit 0) per tile of the final order, for the Jaccard scan
-__global__ void __launch_bounds__(SORT_TPB) sort_fg_count_kernel(SortArgs a, u32 total_bound) {
+__device__ __forceinline__ void sort_fg_count_body(const SortArgs& a, u32 total_bound) {
     __shared__ u32 s_w[SORT_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 total_tiles = min(a.tile_start[a.n_seg], total_bound);
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const uint4 d4 = a.tile_desc[t];
+        if (a.seg_sel && !a.seg_sel[d4.x]) continue;       // (CTA-uniform)
         const u32* v = a.vals[1] + (size_t)d4.x * a.cap + d4.y;
         {   // buffer 0 (source of the last pass) is dead: drop this tile's share of its dirty lines from L2 unwritten
             const size_t sb = (size_t)d4.x * a.cap;
@@ -660,9 +731,13 @@ __global__ void __launch_bounds__(SORT_TPB) sort_fg_count_kernel(SortArgs a, u32
         }
     }
 }
+__global__ void __launch_bounds__(SORT_TPB) sort_fg_count_kernel(SortArgs a, u32 total_bound) {
+    sort_fg_count_body(a, total_bound);
+}
 
 // Enqueue plan + descriptors + three (count+scan, scatter) passes.  Result in keys/vals[1].
 static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStream_t st) {
+    HybArgs h = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // (hist == nullptr: plain path)
     static bool attr_set[64] = {false};
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -676,7 +751,7 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     {
         const int sms_p = b200seg_sm_count();
         const int pgrid = a.run_prefix ? (a.n_seg < sms_p ? a.n_seg : sms_p) : 1;
-        sort_prepare_kernel<<<pgrid, SORT_PREP_TPB, 0, st>>>(a, L.max_tiles);
+        sort_prepare_kernel<<<pgrid, SORT_PREP_TPB, 0, st>>>(a, h, L.max_tiles);
     }
     LAUNCH_CHECK("sort_prepare_kernel");
     b200seg_stage(4, st);

@@ -14,7 +14,7 @@ from test_gpu_parity import CASES, _blocky, _d1
 
 pytestmark = pytest.mark.gpu
 
-DEFAULTS = dict(interleave=1, stats_variant=0, emit_path=0, sort_match=2, dbg=0)
+DEFAULTS = dict(interleave=1, stats_variant=0, emit_path=0, sort_match=2, sort_path=0, dbg=0)
 VARIANTS = [
     ("emit_records", dict(emit_path=1)),
     ("emit_stream", dict(emit_path=2)),
@@ -26,6 +26,9 @@ VARIANTS = [
     ("contiguous_tiles", dict(interleave=0)),
     ("rank_ballots", dict(sort_match=0)),
     ("rank_match", dict(sort_match=1)),
+    ("sort_lsd", dict(sort_path=1)),
+    ("sort_lsd_ballots", dict(sort_path=1, sort_match=0)),
+    ("sort_lsd_stream", dict(sort_path=1, emit_path=2)),
 ]
 PATH_CASES = [c for c in CASES if c[0] in ("d1_c8_flat", "d1_c17_per_image", "d1_c25_flat", "d1_c25_flat_ignore",
                                            "d1_c25_all", "d2_c25_flat", "d2_c17_per_image_ignore", "d2_c25_list")]
