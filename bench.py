@@ -14,7 +14,12 @@ matrix), IoU/accuracy summary kernel.  Prints ONE JSON line (rank 0).
 `e2e`         same metric through the public API from pinned HOST buffers: H2D of logits+labels and D2H of
               loss+summary inside the timed region (double-buffered on a copy stream).
 `roofline`    dominant kernel group, timed live with CUDA events (b200seg_set_stage_events) in a separate loop of
-              the same process; `roofline_step` is the whole path against 2*4*C + L bytes/pixel.
+              the same process, against that kernel's COMPULSORY bytes only (4C+L for the stats pass,
+              8C for the backward pass); `roofline_step` is the whole path against 2*4*C + L bytes/pixel.
+`configs`     the other measured configurations beside the headline (device-timed, N=1 only): trained-like D2 C=25
+              flat, per-image C=17 (BASELINE configs[1]), C=8 flat, and a slice of the confusion-matrix sweep
+              (BASELINE configs[4]).  `--dist blocky` makes D2 the main workload; `--sweep-frames F` runs the
+              confusion-matrix sweep over F frames sharded over the ranks as the main workload.
 `cpu_baseline` / `--impl reference`: the reference's CPU PyTorch path (oracle/port.py, the pinned restatement)
               on this box's host cores, on a bounded sample of the same workload.
 """
@@ -35,18 +40,24 @@ import torch  # noqa: E402
 
 METRIC = "Mpixel/s Lovasz fwd+bwd + mIoU @540x960 C=25"
 UNIT = "Mpixel/s"
-STAGES = ["stats(+fused confmat, records)", "finalize+decide", "emit", "sort_prepare", "sort_pass0", "sort_pass1",
-          "sort_pass2", "jaccard+loss", None, "backward"]
+# kernel groups between the stage events of the library (hybrid sort path, the default; B200SEG_SORT_PATH=1: LSD names)
+STAGES_HYBRID = ["stats(+fused confmat, records)", "finalize+decide", "emit", "sort_prepare", "hyb_count", "hyb_partition",
+                 "hyb_local(rank+jaccard+loss)", "lsd_fallback(idle)", None, "backward"]
+STAGES_LSD = ["stats(+fused confmat, records)", "finalize+decide", "emit", "sort_prepare", "sort_pass0", "sort_pass1",
+              "sort_pass2", "jaccard+loss", None, "backward"]
+SORT_PATH = int(os.environ.get("B200SEG_SORT_PATH", "0"))
+STAGES = STAGES_LSD if SORT_PATH == 1 else STAGES_HYBRID
 N_EV = len(STAGES) + 1
-# stats, finalize+decide, emit (record path) + emit (streaming path, exits at once), sort prepare, 3 x (count, scatter),
-# fg_count, jaccard(+loss), backward, metrics
-KERNELS_PER_STEP = 15
+# hybrid: stats, finalize+decide, emit (record path) + emit (streaming path; one of the two exits at once), sort prepare,
+# hyb_count, hyb_partition, hyb_local, fallback (exits at once unless a segment overflowed), backward, metrics = 11
+# LSD: ... sort prepare, 3 x (count, scatter), fg_count, jaccard(+loss), backward, metrics = 15
+KERNELS_PER_STEP = 15 if SORT_PATH == 1 else 11
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--classes", type=int, default=25)
@@ -54,6 +65,12 @@ def parse():
     ap.add_argument("--height", type=int, default=540)
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--per-image", action="store_true")
+    ap.add_argument("--dist", default="d1", choices=["d1", "blocky"],
+                    help="d1: N(0,1) logits, uniform labels (BASELINE); blocky: trained-like D2 (blocky labels, confident logits)")
+    ap.add_argument("--sweep-frames", type=int, default=0,
+                    help="main workload = confusion-matrix sweep over this many frames (BASELINE configs[4]), sharded over the ranks")
+    ap.add_argument("--sweep-batch", type=int, default=64)
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary configurations")
     ap.add_argument("--cpu-sample-images", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -108,11 +125,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_inputs(args, device, seed):
+def make_inputs(args, device, seed, dist=None, classes=None, batch=None):
+    """D1: N(0,1) logits, uniform labels incl. the ignore label.  blocky (D2, trained-like): 16x16 blocks of
+    one label, several classes absent, logits = 6 * onehot(label with 10 % random flips) + N(0,1) (pixel accuracy ~0.9)."""
+    dist = dist or args.dist
+    c = classes or args.classes
+    n = batch or args.batch
+    h, w = args.height, args.width
     g = torch.Generator(device=device).manual_seed(seed)
-    x = torch.randn((args.batch, args.classes, args.height, args.width), generator=g, device=device)
-    hi = args.classes + 1 if args.classes in (17, 25) else args.classes
-    y = torch.randint(0, hi, (args.batch, args.height, args.width), generator=g, device=device)
+    x = torch.randn((n, c, h, w), generator=g, device=device)
+    hi = c + 1 if c in (17, 25) else c
+    if dist == "d1":
+        return x, torch.randint(0, hi, (n, h, w), generator=g, device=device)
+    coarse = torch.randint(0, hi, (n, (h + 15) // 16, (w + 15) // 16), generator=g, device=device)
+    coarse[coarse >= c // 2 + 2] = c if hi > c else 0
+    y = coarse.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :h, :w].contiguous()
+    noisy = y.clone()
+    flips = torch.rand((n, h, w), generator=g, device=device) < 0.10
+    noisy[flips] = torch.randint(0, c, (int(flips.sum()),), generator=g, device=device)
+    for i in range(n):                                   # image by image: the one-hot of a whole batch would double the footprint
+        x[i] += 6.0 * torch.nn.functional.one_hot(noisy[i].clamp(max=c - 1), c).permute(2, 0, 1).float()
     return x, y
 
 
@@ -126,12 +158,18 @@ def experiment_of(c):
 def cpu_step_fn(args, n_images):
     from oracle import port
     torch.set_num_threads(os.cpu_count() or 1)
-    g = torch.Generator().manual_seed(0)
     c = args.classes
-    x = torch.randn((n_images, c, args.height, args.width), generator=g)
-    hi = c + 1 if c in (17, 25) else c
-    y = torch.randint(0, hi, (n_images, args.height, args.width), generator=g)
+    x, y = make_inputs(args, torch.device("cpu"), seed=0, batch=n_images)
     exp = experiment_of(c)
+    if args.sweep_frames:
+        yi = y.int()
+
+        def sweep_step():
+            cm = port.confusion_matrix(x, yi)
+            port.mean_iou(cm, exp, True, rare=True)
+            return float(cm.sum())
+
+        return sweep_step, n_images * args.height * args.width
 
     def step():
         xr = x.clone().requires_grad_(True)
@@ -171,9 +209,17 @@ def run_reference_arm(args, rank):
 
 def workload_config(args):
     in_mb = args.batch * args.height * args.width * (4 * args.classes + 8) / 1e6
+    if args.sweep_frames:
+        return {"workload": f"confusion_matrix_sweep C={args.classes} {args.height}x{args.width} {args.sweep_frames} frames "
+                            f"(BASELINE.json configs[4]), batches of {args.sweep_batch} frames, one final all-reduce",
+                "labels": "int32, uniform 0..C (C = ignore)", "logits": "fp32 N(0,1)",
+                "l2": "one batch of logits (3.3 GB at 64 frames) exceeds the 126 MB L2",
+                "parallelism": "one process per GPU, frames sharded, one NCCL all-reduce of the CxC int64 matrix per sweep"}
     return {"workload": f"lovasz_softmax_{'per_image' if args.per_image else 'flat'}_fwd_bwd+confmat_miou C={args.classes} "
-                        f"{args.height}x{args.width} batch {args.batch}/GPU (BASELINE.json configs[2])",
-            "labels": "int64, uniform 0..C (C = ignore)", "logits": "fp32 N(0,1)",
+                        f"{args.height}x{args.width} batch {args.batch}/GPU (BASELINE.json configs[2])"
+                        + (" on trained-like D2 inputs" if args.dist == "blocky" else ""),
+            "labels": "int64, uniform 0..C (C = ignore)" if args.dist == "d1" else "int64, 16x16 blocks, classes absent",
+            "logits": "fp32 N(0,1)" if args.dist == "d1" else "fp32 6*onehot(label, 10% flips) + N(0,1)",
             "l2": f"inputs {in_mb:.0f} MB/GPU exceed the 126 MB L2 (no flush needed between iterations)",
             "parallelism": "one process per GPU, images sharded, one NCCL all-reduce of the CxC int64 matrix per step"}
 
@@ -181,6 +227,132 @@ def workload_config(args):
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
+def _device_time(fn, steps, warmup, barrier):
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def measure_config(b200, args, device, name, dist, classes, per_image, batch, steps, hbm):
+    """One secondary configuration, device-timed like the headline: fused loss + confusion matrix forward, backward, summary."""
+    exp = experiment_of(classes)
+    x, y = make_inputs(args, device, seed=1, dist=dist, classes=classes, batch=batch)
+    meter = b200.SegmentationMeter(exp, classes, device)
+    mod = b200.LovaszSoftmaxWithMetrics({"experiment": exp, "per_image": per_image}, meter)
+    xr = x.requires_grad_(True)
+
+    def step():
+        meter.reset()
+        xr.grad = None
+        loss = mod(xr, y)
+        loss.backward()
+        meter.summary()
+        return loss
+
+    ms = _device_time(step, steps, 3, torch.cuda.synchronize)
+    px = batch * args.height * args.width
+    bpp = 2 * 4 * classes + 8
+    gbs = px * bpp / (ms * 1e-3) / 1e9
+    out = {"name": name, "dist": dist, "classes": classes, "per_image": per_image, "batch": batch, "steps": steps,
+           "ms_per_step": ms, "value": px / (ms * 1e-3) / 1e6, "unit": UNIT, "bytes_per_pixel": bpp,
+           "roofline_step_frac": gbs / hbm, "loss": float(step().detach())}
+    del x, y, xr, meter, mod
+    torch.cuda.empty_cache()
+    return out
+
+
+def sweep_time(b200, args, device, frames_rank, world, barrier):
+    """Confusion-matrix sweep (managers/BaseManager.py:640-688 of the reference: t_get_confusion_matrix per frame, summed):
+    frames_rank frames on this rank in batches of --sweep-batch, int32 labels as the managers pass them, ONE all-reduce of
+    the int64 matrix at the end, then the IoU summary.  Returns (ms for the whole sweep, mIoU)."""
+    c, exp = args.classes, experiment_of(args.classes)
+    bsz = min(args.sweep_batch, frames_rank)
+    x, y = make_inputs(args, device, seed=7 + int(os.environ.get("RANK", "0")), dist="d1", batch=bsz)
+    y = y.int()
+    meter = b200.SegmentationMeter(exp, c, device)
+    nb, rem = divmod(frames_rank, bsz)
+
+    def sweep():
+        meter.reset()
+        for _ in range(nb):
+            meter.update(x, y)
+        if rem:
+            meter.update(x[:rem], y[:rem])
+        if world > 1:
+            meter.all_reduce()
+        return meter.summary()
+
+    sweep()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, summary = sweep()
+    e1.record()
+    barrier()
+    meter.check()
+    assert int(meter.cm.sum()) > 0
+    ms = e0.elapsed_time(e1)
+    del x, y
+    torch.cuda.empty_cache()
+    return ms, float(summary[0])
+
+
+def run_sweep_main(b200, bdist, args, rank, world, local, device):
+    """`--sweep-frames F`: the sweep is the main workload (BASELINE configs[4]); a step = one batch of frames."""
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lo, hi = bdist.shard_range(args.sweep_frames, rank, world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, miou = sweep_time(b200, args, device, hi - lo, world, barrier)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        hbm, peak_src = peaks()
+        px = args.sweep_frames * args.height * args.width
+        bpp = 4 * args.classes + 4
+        gbs = (hi - lo) * args.height * args.width * bpp / (ms * 1e-3) / 1e9
+        nbat = -(-(hi - lo) // min(args.sweep_batch, hi - lo))
+        print(json.dumps({
+            "metric": "Mpixel/s confusion-matrix mIoU sweep @540x960 C=25", "value": px / (ms * 1e-3) / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": nbat, "warmup": nbat, "ms_per_step": ms / nbat, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "i64", "data": "synthetic", "config": workload_config(args),
+            "clocks": clocks, "gpu_launches": nbat + 1, "sweep_ms": ms, "miou": miou,
+            "roofline": {"kernel": "confmat_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                         "frac": gbs / hbm, "traffic": None, "peak_source": peak_src,
+                         "note": "per GPU: (4C + 4) bytes/pixel (int32 labels), whole sweep incl. the final all-reduce"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def csrc_digest():
+    """Digest of the CUDA sources: stamps profiles/dram_traffic.json so a stale capture is not reported as current."""
+    import hashlib
+    d = os.path.join(ROOT, "miccai2021_cataract_semantic_segmentation_b200", "csrc")
+    hsh = hashlib.sha256()
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as f:
+                hsh.update(f.read())
+    return hsh.hexdigest()[:16]
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -197,6 +369,9 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (use --impl reference for the CPU arm)"
     rank, world, local = bdist.init_from_env()
     device = torch.device("cuda", local)
+    if args.sweep_frames:
+        run_sweep_main(b200, bdist, args, rank, world, local, device)
+        return
     c, exp = args.classes, experiment_of(args.classes)
     px_rank = args.batch * args.height * args.width
     x, y = make_inputs(args, device, seed=rank)
@@ -322,28 +497,32 @@ def main():
     hbm, peak_src = peaks()
     lab_bytes = 8
     p = px_rank
-    # algorithmic bytes per launch of each kernel group (DESIGN.md "Kernels"): compulsory reads + writes of that stage
-    alg = {
-        # logits + labels in; softmax state (8), compact label (1) and the 20-byte candidate record out
-        "stats(+fused confmat, records)": p * (4 * c + lab_bytes + 29),
-        # logits in, gradients out, 17 B/px of state (softmax max / denominator, own gradient, label8, candidate mask)
-        "backward": p * (2 * 4 * c + 17),
-    }
+    # COMPULSORY bytes per launch of the two streaming kernels (every input read once, every output written
+    # once): stats = logits + labels in, backward = logits in + gradients out.  The pipeline's own per-pixel state (softmax
+    # max / denominator, records, masks) is NOT charged; `achieved_with_own_state` adds it for the curious.
+    alg = {"stats(+fused confmat, records)": p * (4 * c + lab_bytes), "backward": p * (2 * 4 * c)}
+    own = {"stats(+fused confmat, records)": p * 29, "backward": p * 17}
     dom = max(stage_ms, key=stage_ms.get)
-    traffic = None
+    traffic, traffic_note = None, "no capture under profiles/dram_traffic.json"
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(dom)
+            tj = json.load(f)
+        if tj.get("_csrc") == csrc_digest():
+            traffic, traffic_note = tj.get(dom), f"ncu dram__bytes of {tj.get('_source')} (same kernel sources as this run)"
+        else:
+            traffic_note = f"capture {tj.get('_source')} is of other kernel sources: not reported"
     roof_dom = None
     if dom in alg:
         a = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        a2 = (alg[dom] + own[dom]) / (stage_ms[dom] * 1e-3) / 1e9
         roof_dom = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s", "frac": a / hbm,
-                    "traffic": traffic, "peak_source": peak_src, "ms": stage_ms[dom]}
+                    "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "ms": stage_ms[dom],
+                    "achieved_with_own_state": a2}
     else:       # a sort / scan stage dominates: charge it the whole path's compulsory bytes (it has none of its own)
         a = p * (2 * 4 * c + lab_bytes) / (stage_ms[dom] * 1e-3) / 1e9
         roof_dom = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s", "frac": a / hbm,
-                    "traffic": traffic, "peak_source": peak_src, "ms": stage_ms[dom],
+                    "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "ms": stage_ms[dom],
                     "note": "stage has no compulsory HBM bytes of its own; charged the path's 2*4*C+L bytes/pixel"}
     step_gbs = p * (2 * 4 * c + lab_bytes) / (ms_step * 1e-3) / 1e9
     out = {
@@ -357,6 +536,23 @@ def main():
                           "peak_source": peak_src},
         "stage_ms": stage_ms, "loss": loss_value, "miou": float(summary[0]),
     }
+    out["sort_path"] = "lsd" if SORT_PATH == 1 else "hybrid"
+    if world == 1 and not args.no_configs:
+        del xr, x, y
+        torch.cuda.empty_cache()
+        cfgs = []
+        for name, dist_, cc, pi in (("d2_blocky_c25_flat", "blocky", 25, False), ("d1_c17_per_image (BASELINE configs[1])", "d1", 17, True),
+                                    ("d1_c8_flat", "d1", 8, False), ("d2_blocky_c17_per_image", "blocky", 17, True)):
+            if (dist_, cc, pi) == (args.dist, c, args.per_image):
+                continue
+            cfgs.append(measure_config(b200, args, device, name, dist_, cc, pi, args.batch, min(args.steps, 20), hbm))
+        frames = 512
+        sms, smiou = sweep_time(b200, args, device, frames, 1, torch.cuda.synchronize)
+        spx = frames * args.height * args.width
+        cfgs.append({"name": "confmat_sweep_slice (BASELINE configs[4]: 512 of 4096 frames = one GPU's share at N=8)",
+                     "frames": frames, "batch": args.sweep_batch, "ms": sms, "value": spx / (sms * 1e-3) / 1e6, "unit": UNIT,
+                     "bytes_per_pixel": 4 * c + 4, "roofline_frac": spx * (4 * c + 4) / (sms * 1e-3) / 1e9 / hbm, "miou": smiou})
+        out["configs"] = cfgs
     if world == 1 and not args.no_cpu_baseline:
         cstep, cpx = cpu_step_fn(args, args.cpu_sample_images)
         cstep()

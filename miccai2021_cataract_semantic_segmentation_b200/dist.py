@@ -65,6 +65,18 @@ def all_reduce_confusion_matrix(cm: torch.Tensor, group=None, status: torch.Tens
     return _Pending(works) if async_op else None
 
 
+def all_reduce_packed(buf: torch.Tensor, group=None, async_op=False):
+    """ONE in-place SUM all-reduce of a meter's packed int64 buffer: the C x C matrix followed by the word that holds the
+    sticky status flags (SegmentationMeter lays them out that way).  After the sum the status word is non-zero on every
+    rank iff some rank flagged an out-of-range label, so all ranks raise together -- one collective per step instead of a
+    SUM for the matrix plus a MAX for the flag."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return _Pending([]) if async_op else None
+    assert buf.dtype == torch.int64 and buf.is_contiguous()
+    work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return _Pending([work]) if async_op else None
+
+
 def all_reduce_mean(value: torch.Tensor, group=None):
     """Mean of a per-rank scalar (e.g. the rank-local loss, for logging).  Not needed for training: DDP averages
     the model gradients, and with equal shards the mean of rank-local per-image losses is the global mean."""

@@ -27,13 +27,18 @@ class SegmentationMeter:
         self.num_classes = num_classes if num_classes is not None else len(
             [k for k in CLASS_INFO[experiment][1] if k != 255])
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.cm = torch.zeros((self.num_classes, self.num_classes), dtype=torch.int64, device=device)
-        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        # one packed int64 buffer: the matrix, then one word whose low half is the int32 status the kernels OR into
+        # (little-endian), so reset is one memset and the data-parallel sum one collective
+        cc = self.num_classes * self.num_classes
+        self._buf = torch.zeros(cc + 1, dtype=torch.int64, device=device)
+        self.cm = self._buf[:cc].view(self.num_classes, self.num_classes)
+        self.status = self._buf[cc:].view(torch.int32)[:1]
+        self._reduced = False
         self.drop_label = confusion_drop_label(self.num_classes, no_ignore_class)
 
     def reset(self):
-        self.cm.zero_()
-        self.status.zero_()
+        self._buf.zero_()
+        self._reduced = False
 
     def update(self, prediction: torch.Tensor, target: torch.Tensor):
         accumulate_confusion_matrix(prediction, target, self.cm, self.status, self.drop_label)
@@ -42,8 +47,9 @@ class SegmentationMeter:
         """Sum the matrix over the data-parallel ranks.  ``async_op=True``: returns a handle whose ``wait()`` must be
         called before the matrix is read; issue it right after the forward pass and wait after ``loss.backward()`` so the
         5 KB collective hides under the backward kernel."""
-        from .dist import all_reduce_confusion_matrix
-        pending = all_reduce_confusion_matrix(self.cm, group=group, status=self.status, async_op=async_op)
+        from .dist import all_reduce_packed
+        self._reduced = True
+        pending = all_reduce_packed(self._buf, group=group, async_op=async_op)
         return pending if async_op else self.cm
 
     def summary(self):
@@ -51,6 +57,10 @@ class SegmentationMeter:
         return metrics_summary(self.cm, self.experiment)
 
     def check(self):
+        if self._reduced:                                  # the status word is a sum over ranks now: non-zero = some rank flagged
+            if int(self._buf[-1].item()) != 0:
+                raise RuntimeError("Class values must be smaller than num_classes.")
+            return
         raise_if_label_out_of_range(self.status)
 
 
@@ -97,12 +107,27 @@ class LovaszSoftmaxCE(nn.Module):
         self.classes_to_consider = config.get('classes_to_consider', _PRESENT)
         self.ignore_index = ce_ignore_index(self.experiment)
         self.meter = meter
+        self._status = None                                    # sticky label-range flag of the calls without a meter
+
+    def check(self):
+        """nn.CrossEntropyLoss raises (or device-asserts) on a target outside [0, C) that is not ignore_index; the fused
+        pass sets a flag instead.  It is looked at lazily -- here, and at the start of the next forward -- so the hot
+        path never synchronises on the step it has just queued."""
+        if self._status is not None and int(self._status.item()) & _native.STATUS_LABEL_OOB:
+            self._status.zero_()
+            raise IndexError("Target is out of bounds (a label outside [0, C) other than ignore_index reached the fused "
+                             "cross entropy)")
 
     def forward(self, prediction: torch.Tensor, target: torch.Tensor):
         keep_absent, mask = _resolve_classes(self.classes_to_consider, prediction.shape[1])
-        kw = {}
         if self.meter is not None:
             kw = dict(confusion=self.meter.cm, confusion_drop_label=self.meter.drop_label, status=self.meter.status)
+        else:
+            if self._status is None or self._status.device != prediction.device:
+                self._status = torch.zeros(1, dtype=torch.int32, device=prediction.device)
+            else:
+                self.check()                                   # the previous call's flag (that work has long been queued)
+            kw = dict(status=self._status)
         return lovasz_softmax_ce(prediction, target, self.ignore_index, self.per_image, self.classes_to_ignore,
                                  keep_absent, mask, **kw)
 

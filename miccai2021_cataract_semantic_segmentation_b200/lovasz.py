@@ -15,6 +15,9 @@ from . import _native
 from .class_info import CLASS_INFO
 
 _PRESENT = sys.intern("present")
+# calls of lovasz_softmax_ce whose cross entropy was evaluated by torch.nn.functional.cross_entropy because the shape is
+# outside the pipelined kernels (C not in {8, 17, 25}, plane % 16 != 0, unaligned tensors): a library fallback, counted
+FALLBACK_COUNTS = {"cross_entropy_torch": 0}
 
 
 def _resolve_classes(classes_to_consider, n_classes: int):
@@ -41,6 +44,9 @@ def _resolve_classes(classes_to_consider, n_classes: int):
             continue
         if not 0 <= c < n_classes:
             raise IndexError(f"class index {c} out of range for {n_classes} classes")
+        if mask & (1 << c):
+            # the reference would add the class's term twice and divide by len(list); a weighted mean is outside this path
+            raise ValueError(f"class index {c} is listed twice in classes_to_consider: duplicates are not supported")
         mask |= 1 << c
     return 1, mask
 
@@ -48,38 +54,40 @@ def _resolve_classes(classes_to_consider, n_classes: int):
 class _LovaszFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, target, per_image, filter_label, keep_absent, class_mask, cm, cm_drop, status):
-        lib = _native.load()
-        n, c, h, w = logits.shape
-        hw = h * w
-        need_grad = bool(ctx.needs_input_grad[0])
-        nbytes = _native._sz(0)
-        _native.check(lib.b200seg_lovasz_workspace_bytes(n, c, hw, int(per_image), nbytes), "workspace query")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
-        loss = torch.empty((), dtype=torch.float32, device=logits.device)
-        _native.check(lib.b200seg_lovasz_forward(
-            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, hw, int(per_image),
-            filter_label, keep_absent, class_mask, int(need_grad), ws.data_ptr(), ws.numel(), loss.data_ptr(),
-            cm.data_ptr() if cm is not None else None, cm_drop,
-            status.data_ptr() if status is not None else None, _native.stream_ptr(logits.device)),
-            "b200seg_lovasz_forward")
-        if need_grad:
-            ctx.save_for_backward(logits, target, ws)
-            ctx.opts = (int(per_image), filter_label, keep_absent, class_mask)
-        return loss
+        with torch.cuda.device(logits.device):
+            lib = _native.load()
+            n, c, h, w = logits.shape
+            hw = h * w
+            need_grad = bool(ctx.needs_input_grad[0])
+            nbytes = _native._sz(0)
+            _native.check(lib.b200seg_lovasz_workspace_bytes(n, c, hw, int(per_image), nbytes), "workspace query")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
+            loss = torch.empty((), dtype=torch.float32, device=logits.device)
+            _native.check(lib.b200seg_lovasz_forward(
+                logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, hw, int(per_image),
+                filter_label, keep_absent, class_mask, int(need_grad), ws.data_ptr(), ws.numel(), loss.data_ptr(),
+                cm.data_ptr() if cm is not None else None, cm_drop,
+                status.data_ptr() if status is not None else None, _native.stream_ptr(logits.device)),
+                "b200seg_lovasz_forward")
+            if need_grad:
+                ctx.save_for_backward(logits, target, ws)
+                ctx.opts = (int(per_image), filter_label, keep_absent, class_mask)
+            return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        logits, target, ws = ctx.saved_tensors
-        per_image, filter_label, keep_absent, class_mask = ctx.opts
-        lib = _native.load()
-        n, c, h, w = logits.shape
-        go = grad_out.detach().to(torch.float32).contiguous()
-        dlogits = torch.empty_like(logits)
-        _native.check(lib.b200seg_lovasz_backward(
-            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, per_image, filter_label,
-            keep_absent, class_mask, ws.data_ptr(), ws.numel(), go.data_ptr(), dlogits.data_ptr(),
-            _native.stream_ptr(logits.device)), "b200seg_lovasz_backward")
-        return dlogits, None, None, None, None, None, None, None, None
+        with torch.cuda.device(ctx.saved_tensors[0].device):
+            logits, target, ws = ctx.saved_tensors
+            per_image, filter_label, keep_absent, class_mask = ctx.opts
+            lib = _native.load()
+            n, c, h, w = logits.shape
+            go = grad_out.detach().to(torch.float32).contiguous()
+            dlogits = torch.empty_like(logits)
+            _native.check(lib.b200seg_lovasz_backward(
+                logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, per_image, filter_label,
+                keep_absent, class_mask, ws.data_ptr(), ws.numel(), go.data_ptr(), dlogits.data_ptr(),
+                _native.stream_ptr(logits.device)), "b200seg_lovasz_backward")
+            return dlogits, None, None, None, None, None, None, None, None
 
 
 class _LovaszCEFunction(torch.autograd.Function):
@@ -88,41 +96,43 @@ class _LovaszCEFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, target, per_image, filter_label, keep_absent, class_mask, ce_ignore, cm, cm_drop, status):
-        lib = _native.load()
-        n, c, h, w = logits.shape
-        hw = h * w
-        need_grad = bool(ctx.needs_input_grad[0])
-        nbytes = _native._sz(0)
-        _native.check(lib.b200seg_lovasz_workspace_bytes(n, c, hw, int(per_image), nbytes), "workspace query")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
-        # two separate 0-dim tensors (not views of one buffer): callers mutate losses in place (LossWrapper.py:71)
-        loss = torch.empty((), dtype=torch.float32, device=logits.device)
-        ce = torch.empty((), dtype=torch.float32, device=logits.device)
-        _native.check(lib.b200seg_lovasz_ce_forward(
-            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, hw, int(per_image),
-            filter_label, keep_absent, class_mask, int(need_grad), ws.data_ptr(), ws.numel(), loss.data_ptr(),
-            ce_ignore, ce.data_ptr(), cm.data_ptr() if cm is not None else None, cm_drop,
-            status.data_ptr(), _native.stream_ptr(logits.device)), "b200seg_lovasz_ce_forward")
-        if need_grad:
-            ctx.save_for_backward(logits, target, ws)
-            ctx.opts = (int(per_image), filter_label, keep_absent, class_mask, ce_ignore)
-        return loss, ce
+        with torch.cuda.device(logits.device):
+            lib = _native.load()
+            n, c, h, w = logits.shape
+            hw = h * w
+            need_grad = bool(ctx.needs_input_grad[0])
+            nbytes = _native._sz(0)
+            _native.check(lib.b200seg_lovasz_workspace_bytes(n, c, hw, int(per_image), nbytes), "workspace query")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
+            # two separate 0-dim tensors (not views of one buffer): callers mutate losses in place (LossWrapper.py:71)
+            loss = torch.empty((), dtype=torch.float32, device=logits.device)
+            ce = torch.empty((), dtype=torch.float32, device=logits.device)
+            _native.check(lib.b200seg_lovasz_ce_forward(
+                logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, hw, int(per_image),
+                filter_label, keep_absent, class_mask, int(need_grad), ws.data_ptr(), ws.numel(), loss.data_ptr(),
+                ce_ignore, ce.data_ptr(), cm.data_ptr() if cm is not None else None, cm_drop,
+                status.data_ptr(), _native.stream_ptr(logits.device)), "b200seg_lovasz_ce_forward")
+            if need_grad:
+                ctx.save_for_backward(logits, target, ws)
+                ctx.opts = (int(per_image), filter_label, keep_absent, class_mask, ce_ignore)
+            return loss, ce
 
     @staticmethod
     def backward(ctx, grad_lovasz, grad_ce):
-        logits, target, ws = ctx.saved_tensors
-        per_image, filter_label, keep_absent, class_mask, ce_ignore = ctx.opts
-        lib = _native.load()
-        n, c, h, w = logits.shape
-        zero = torch.zeros((), dtype=torch.float32, device=logits.device)
-        gl = (zero if grad_lovasz is None else grad_lovasz.detach().to(torch.float32)).contiguous()
-        gc = (zero if grad_ce is None else grad_ce.detach().to(torch.float32)).contiguous()
-        dlogits = torch.empty_like(logits)
-        _native.check(lib.b200seg_lovasz_ce_backward(
-            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, per_image, filter_label,
-            keep_absent, class_mask, ws.data_ptr(), ws.numel(), gl.data_ptr(), ce_ignore, gc.data_ptr(),
-            dlogits.data_ptr(), _native.stream_ptr(logits.device)), "b200seg_lovasz_ce_backward")
-        return dlogits, None, None, None, None, None, None, None, None, None
+        with torch.cuda.device(ctx.saved_tensors[0].device):
+            logits, target, ws = ctx.saved_tensors
+            per_image, filter_label, keep_absent, class_mask, ce_ignore = ctx.opts
+            lib = _native.load()
+            n, c, h, w = logits.shape
+            zero = torch.zeros((), dtype=torch.float32, device=logits.device)
+            gl = (zero if grad_lovasz is None else grad_lovasz.detach().to(torch.float32)).contiguous()
+            gc = (zero if grad_ce is None else grad_ce.detach().to(torch.float32)).contiguous()
+            dlogits = torch.empty_like(logits)
+            _native.check(lib.b200seg_lovasz_ce_backward(
+                logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, per_image, filter_label,
+                keep_absent, class_mask, ws.data_ptr(), ws.numel(), gl.data_ptr(), ce_ignore, gc.data_ptr(),
+                dlogits.data_ptr(), _native.stream_ptr(logits.device)), "b200seg_lovasz_ce_backward")
+            return dlogits, None, None, None, None, None, None, None, None, None
 
 
 def lovasz_softmax_ce(prediction: torch.Tensor, target: torch.Tensor, ce_ignore_index: int | None,
@@ -152,6 +162,11 @@ def lovasz_softmax_ce(prediction: torch.Tensor, target: torch.Tensor, ce_ignore_
     if fused and classes_to_ignore is not None and 0 <= int(classes_to_ignore) < c and int(classes_to_ignore) != ce_ign:
         fused = False
     if not fused:
+        FALLBACK_COUNTS["cross_entropy_torch"] += 1
+        if FALLBACK_COUNTS["cross_entropy_torch"] == 1:
+            warnings.warn("lovasz_softmax_ce: shape outside the fused kernels (C in {8, 17, 25}, plane % 16 == 0, aligned "
+                          "tensors); the cross entropy of such calls is evaluated by torch (counted in "
+                          "lovasz.FALLBACK_COUNTS)", stacklevel=2)
         lov = lovasz_softmax(prediction, target, per_image, classes_to_ignore, keep_absent, class_mask, confusion,
                              confusion_drop_label, status)
         ce = torch.nn.functional.cross_entropy(prediction, target.long(),

@@ -45,9 +45,10 @@ def accumulate_confusion_matrix(prediction: torch.Tensor, target: torch.Tensor, 
     assert cm.dtype == torch.int64 and cm.is_contiguous() and tuple(cm.shape) == (c, c)
     assert status.dtype == torch.int32
     drop = _native.NO_LABEL if drop_label is None else int(drop_label)
-    _native.check(_native.load().b200seg_confmat_accumulate(
-        pred.data_ptr(), tgt.data_ptr(), _native.label_code(tgt), n, c, h * w, drop, cm.data_ptr(),
-        status.data_ptr(), _native.stream_ptr(pred.device)), "b200seg_confmat_accumulate")
+    with torch.cuda.device(pred.device):                      # launches go to the current device: make it the tensors'
+        _native.check(_native.load().b200seg_confmat_accumulate(
+            pred.data_ptr(), tgt.data_ptr(), _native.label_code(tgt), n, c, h * w, drop, cm.data_ptr(),
+            status.data_ptr(), _native.stream_ptr(pred.device)), "b200seg_confmat_accumulate")
 
 
 def raise_if_label_out_of_range(status: torch.Tensor):
@@ -103,10 +104,11 @@ def sliding_miou(prediction: torch.Tensor, target: torch.Tensor, kernel_size: in
     ver_num_wins, hor_num_wins = (h - kernel_size) // stride + 1, (w - kernel_size) // stride + 1
     out = torch.empty((n, ver_num_wins, hor_num_wins), dtype=torch.float32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    _native.check(lib.b200seg_sliding_miou(
-        pred.data_ptr(), tgt.data_ptr(), _native.label_code(tgt), n, c, h, w, kernel_size, stride,
-        scratch.data_ptr(), scratch.numel(), out.data_ptr(), status.data_ptr(), _native.stream_ptr(dev)),
-        "b200seg_sliding_miou")
+    with torch.cuda.device(dev):
+        _native.check(lib.b200seg_sliding_miou(
+            pred.data_ptr(), tgt.data_ptr(), _native.label_code(tgt), n, c, h, w, kernel_size, stride,
+            scratch.data_ptr(), scratch.numel(), out.data_ptr(), status.data_ptr(), _native.stream_ptr(dev)),
+            "b200seg_sliding_miou")
     if validate:
         raise_if_label_out_of_range(status)
     if not original_size:
@@ -207,9 +209,10 @@ def metrics_summary(cm: torch.Tensor, experiment: int):
     sets = (_native._u32 * 3)(mask_of(cats['instruments']), mask_of(cats['anatomies']), mask_of(cats['rare']))
     iou = torch.empty(c, dtype=torch.float32, device=cm.device)
     summary = torch.empty(6, dtype=torch.float32, device=cm.device)
-    _native.check(_native.load().b200seg_metrics_from_confmat(
-        cm.data_ptr(), c, mask_of(keys), sets, 3, iou.data_ptr(), summary.data_ptr(),
-        _native.stream_ptr(cm.device)), "b200seg_metrics_from_confmat")
+    with torch.cuda.device(cm.device):
+        _native.check(_native.load().b200seg_metrics_from_confmat(
+            cm.data_ptr(), c, mask_of(keys), sets, 3, iou.data_ptr(), summary.data_ptr(),
+            _native.stream_ptr(cm.device)), "b200seg_metrics_from_confmat")
     return iou, summary
 
 

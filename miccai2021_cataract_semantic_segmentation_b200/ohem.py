@@ -17,32 +17,34 @@ from .class_info import CLASS_INFO
 class _OhemFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, target, ignore_label, thresh, min_kept, status):
-        lib = _native.load()
-        n, c, h, w = logits.shape
-        nbytes = _native._sz(0)
-        _native.check(lib.b200seg_ohem_workspace_bytes(n, h * w, nbytes), "b200seg_ohem_workspace_bytes")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
-        loss = torch.empty((), dtype=torch.float32, device=logits.device)
-        _native.check(lib.b200seg_ohem_ce_forward(
-            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, ignore_label,
-            float(thresh), int(min_kept), ws.data_ptr(), ws.numel(), loss.data_ptr(), status.data_ptr(),
-            _native.stream_ptr(logits.device)), "b200seg_ohem_ce_forward")
-        if ctx.needs_input_grad[0]:
-            ctx.save_for_backward(logits, target, ws)
-            ctx.ignore_label = ignore_label
-        return loss
+        with torch.cuda.device(logits.device):
+            lib = _native.load()
+            n, c, h, w = logits.shape
+            nbytes = _native._sz(0)
+            _native.check(lib.b200seg_ohem_workspace_bytes(n, h * w, nbytes), "b200seg_ohem_workspace_bytes")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
+            loss = torch.empty((), dtype=torch.float32, device=logits.device)
+            _native.check(lib.b200seg_ohem_ce_forward(
+                logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, ignore_label,
+                float(thresh), int(min_kept), ws.data_ptr(), ws.numel(), loss.data_ptr(), status.data_ptr(),
+                _native.stream_ptr(logits.device)), "b200seg_ohem_ce_forward")
+            if ctx.needs_input_grad[0]:
+                ctx.save_for_backward(logits, target, ws)
+                ctx.ignore_label = ignore_label
+            return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        logits, target, ws = ctx.saved_tensors
-        n, c, h, w = logits.shape
-        go = grad_out.detach().to(torch.float32).contiguous()
-        dlogits = torch.empty_like(logits)
-        _native.check(_native.load().b200seg_ohem_ce_backward(
-            logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, ctx.ignore_label,
-            ws.data_ptr(), ws.numel(), go.data_ptr(), dlogits.data_ptr(), _native.stream_ptr(logits.device)),
-            "b200seg_ohem_ce_backward")
-        return dlogits, None, None, None, None, None
+        with torch.cuda.device(ctx.saved_tensors[0].device):
+            logits, target, ws = ctx.saved_tensors
+            n, c, h, w = logits.shape
+            go = grad_out.detach().to(torch.float32).contiguous()
+            dlogits = torch.empty_like(logits)
+            _native.check(_native.load().b200seg_ohem_ce_backward(
+                logits.data_ptr(), target.data_ptr(), _native.label_code(target), n, c, h * w, ctx.ignore_label,
+                ws.data_ptr(), ws.numel(), go.data_ptr(), dlogits.data_ptr(), _native.stream_ptr(logits.device)),
+                "b200seg_ohem_ce_backward")
+            return dlogits, None, None, None, None, None
 
 
 def ohem_cross_entropy(score: torch.Tensor, target: torch.Tensor, thresh: float = 0.7, min_kept: int = 100000,

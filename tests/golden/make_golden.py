@@ -125,6 +125,11 @@ def add_confmat(name, prediction, target, experiment, existing=None, no_ignore_c
         OUT[f"confmat/{name}/np_cm"] = ncm
         OUT[f"confmat/{name}/np_miou_categories"] = np.array(utils.get_mean_iou(ncm, 1, categories=True), np.float64)
         OUT[f"confmat/{name}/np_pixel_accuracy"] = np.array(utils.get_pixel_accuracy(ncm.copy()), np.float64)
+        OUT[f"confmat/{name}/np_miou"] = np.array(utils.get_mean_iou(ncm, 1), np.float64)
+        OUT[f"confmat/{name}/np_norm_row"] = np.asarray(utils.normalise_confusion_matrix(ncm.copy(), "row"), np.float64)
+        OUT[f"confmat/{name}/np_norm_col"] = np.asarray(utils.normalise_confusion_matrix(ncm.copy(), "col"), np.float64)
+        OUT[f"confmat/{name}/np_single_class_iou"] = np.array(
+            [utils.get_single_class_iou(ncm, 1, k) for k in range(prediction.shape[1])], np.float64)
     print(f"confmat {name:34s} sum={int(cm.sum())} miou={OUT[f'confmat/{name}/miou']:.8f}")
 
 

@@ -35,7 +35,7 @@ def test_gpu_arm_prints_the_contract_line():
     out = _run(["--steps", "3", "--warmup", "3", "--batch", "2"], 600)
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline", "roofline_step", "stage_ms"} <= set(out)
     assert out["n_gpus"] == 1 and out["dtype"] == "f32" and out["data"] == "synthetic" and out["scaling"] == "weak"
-    assert out["value"] > 0 and out["gpu_launches"] == 15 * out["steps"]
+    assert out["value"] > 0 and out["gpu_launches"] == 11 * out["steps"] and out["sort_path"] == "hybrid"
     e2e = out["e2e"]
     assert 0 < e2e["value"] < out["value"]                       # host buffers: PCIe-bound
     assert e2e["h2d_bytes_per_step"] == 2 * 540 * 960 * (25 * 4 + 8) and e2e["d2h_bytes_per_step"] > 0
@@ -45,3 +45,12 @@ def test_gpu_arm_prints_the_contract_line():
     cpu = out["cpu_baseline"]
     assert cpu["kind"] == "port" and cpu["value"] > 0 and cpu["cores"] >= 1 and cpu["sample"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(out["clocks"])
+    names = [cfg["name"] for cfg in out["configs"]]
+    assert any("d2_blocky_c25_flat" in n for n in names) and any("configs[1]" in n for n in names) and any("configs[4]" in n for n in names)
+    assert all(cfg["value"] > 0 for cfg in out["configs"])
+
+
+@pytest.mark.gpu
+def test_gpu_sweep_mode_prints_the_contract_line():
+    out = _run(["--sweep-frames", "48", "--sweep-batch", "16"], 600)
+    assert out["value"] > 0 and out["n_gpus"] == 1 and "configs[4]" in out["config"]["workload"] and out["roofline"]["frac"] > 0

@@ -191,3 +191,21 @@ def test_pair_outputs_survive_in_place_scaling_and_anomaly_mode(b200):
     lov2, ce2 = b200.LovaszSoftmaxCE({"experiment": exp})(xr, y.cuda())
     (lov2 * 0.5 + ce2 * 2.0).backward()
     assert torch.equal(xd.grad, xr.grad) and torch.isfinite(xd.grad).all()
+
+
+def test_fused_pair_raises_lazily_on_an_out_of_range_label(b200):
+    """nn.CrossEntropyLoss raises on a target outside [0, C) that is not ignore_index; the fused pass flags it and the
+    module raises at its next call (or at check()), never synchronising on the step it has just queued."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn((1, 8, 64, 96), generator=g, device="cuda")
+    y = torch.randint(0, 8, (1, 64, 96), generator=g, device="cuda")
+    mod = b200.LovaszSoftmaxCE({"experiment": 1})
+    mod(x, y)
+    mod.check()                                                    # clean labels: nothing to report
+    bad = y.clone()
+    bad[0, 3, 5] = 255                                             # experiment 1 ignores -100 only: 255 is out of range
+    mod(x, bad)
+    with pytest.raises(IndexError):
+        mod(x, y)                                                  # the flag of the previous call
+    mod(x, y)
+    mod.check()                                                    # cleared after raising

@@ -123,6 +123,13 @@ def test_confmat_matches_reference_golden(b200, name):
         assert ncm.dtype == np.int32 and np.array_equal(ncm, g.get("confmat", name, "np_cm"))
         assert np.allclose(np.array(b200.get_mean_iou(ncm, 1, categories=True)),
                            g.get("confmat", name, "np_miou_categories"), rtol=0, atol=1e-15)
+        # the other numpy twins (reference utils/metrics.py:28-54,87-114), on the matrix the GPU kernel counted
+        assert np.allclose(np.array(b200.get_pixel_accuracy(ncm.copy())), g.get("confmat", name, "np_pixel_accuracy"), rtol=0, atol=1e-15)
+        assert np.allclose(b200.get_mean_iou(ncm, 1), g.get("confmat", name, "np_miou"), rtol=0, atol=1e-15)
+        assert np.array_equal(b200.normalise_confusion_matrix(ncm.copy(), "row"), g.get("confmat", name, "np_norm_row"))
+        assert np.array_equal(b200.normalise_confusion_matrix(ncm.copy(), "col"), g.get("confmat", name, "np_norm_col"))
+        sc = np.array([b200.get_single_class_iou(ncm, 1, k) for k in range(x.shape[1])], np.float64)
+        assert np.array_equal(sc, g.get("confmat", name, "np_single_class_iou"))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -489,3 +496,45 @@ def test_large_batch_parity_with_the_oracle_on_device(b200):
     ref_loss, ref_grad = port.lovasz_softmax_with_grad(x, y, exp)
     assert rel_err(float(loss), float(ref_loss)) <= LOSS_RTOL
     assert float((grad - ref_grad).abs().max()) <= GRAD_RTOL * float(ref_grad.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the softmax the kernels form is ATen's CUDA softmax, bit for bit
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c,exp", [(8, 1), (17, 2), (25, 3)])
+def test_stats_kernel_softmax_is_atens_cuda_softmax_bit_for_bit(b200, c, exp):
+    """The stats kernel leaves max_c z and sum_c exp(z - max) per pixel (pix_m / pix_s); every later pass forms
+    p = exp(z - m) / s from them.  With the same two fp32 operations in torch (CUDA) on the kernel's m and s the result
+    must carry the same bits as torch.softmax(x, 1) -- so tie order on the device is the reference's own."""
+    from miccai2021_cataract_semantic_segmentation_b200 import _native
+    lib = _native.load()
+    n, h, w = 2, 128, 192
+    hw, P = h * w, n * h * w
+    g = torch.Generator(device="cuda").manual_seed(17 + c)
+    x = torch.randn((n, c, h, w), generator=g, device="cuda") * 3.0
+    x[0, :, :4] = (x[0, :, :4] * 2).round() / 2                      # exact ties among the classes
+    x[1, 0, :2] += 60.0                                                # saturated pixels: p = 1 and p = 0 exactly
+    y = torch.randint(0, c + (exp != 1), (n, h, w), generator=g, device="cuda")
+    nb = _native._sz(0)
+    _native.check(lib.b200seg_lovasz_workspace_bytes(n, c, hw, 0, nb), "workspace")
+    ws = torch.zeros(nb.value, dtype=torch.uint8, device="cuda")
+    loss = torch.empty((), device="cuda")
+    _native.check(lib.b200seg_lovasz_forward(x.data_ptr(), y.data_ptr(), _native.LABEL_I64, n, c, hw, 0, _native.NO_LABEL,
+                                             0, (1 << c) - 1, 0, ws.data_ptr(), ws.numel(), loss.data_ptr(), None,
+                                             _native.NO_LABEL, None, torch.cuda.current_stream().cuda_stream), "forward")
+    torch.cuda.synchronize()
+    offs = (ctypes.c_size_t * 8)()
+    _native.check(lib.b200seg_debug_layout(n, c, hw, 0, offs, 8), "layout")
+    m = ws[offs[0]:offs[0] + 4 * P].view(torch.float32).view(n, 1, h, w)
+    sden = ws[offs[1]:offs[1] + 4 * P].view(torch.float32).view(n, 1, h, w)
+    assert torch.equal(m, x.max(1, keepdim=True).values)
+    ours = torch.exp(x - m) / sden
+    ref = torch.softmax(x, 1)
+    diff = ours.view(torch.int32) != ref.view(torch.int32)
+    assert int(diff.sum()) == 0, f"{int(diff.sum())} of {diff.numel()} probabilities differ from ATen's CUDA softmax"
+    # ... and the own-class keys of the candidate records are those probabilities' errors, exactly
+    rec16 = ws[offs[4]:offs[4] + 16 * P].view(torch.int32).view(P, 4)
+    yy = y.view(-1)
+    valid = (yy < c).nonzero().squeeze(1)
+    own = ref.permute(0, 2, 3, 1).reshape(P, c)[valid, yy[valid]]
+    assert torch.equal(rec16[valid, 0], 0x3F800000 - (1.0 - own).view(torch.int32))

@@ -10,7 +10,8 @@ h, units, data = rows[0], rows[1], rows[2:]
 col = {k: i for i, k in enumerate(h)}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 stage_of = {"stats_kernel": "stats(+fused confmat, records)", "backward_kernel": "backward", "emit_kernel_cta": "emit",
-            "jaccard_kernel": "jaccard+loss"}
+            "jaccard_kernel": "jaccard+loss", "hyb_count": "hyb_count", "hyb_partition": "hyb_partition",
+            "hyb_local": "hyb_local(rank+jaccard+loss)"}
 res = {}
 for r in data:
     name = r[col["Kernel Name"]]
@@ -19,5 +20,9 @@ for r in data:
         if key in name:
             res[stage] = int(b)
 res["_source"] = rep.split("/")[-1]
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+res["_csrc"] = bench.csrc_digest()
 json.dump(res, open(out, "w"), indent=1)
 print(res)
