@@ -74,7 +74,6 @@ __device__ __forceinline__ void hyb_count_flush(const SortArgs& a, const HybArgs
 
 __global__ void __launch_bounds__(SORT_TPB) hyb_count_kernel(SortArgs a, HybArgs h, u32 total_bound) {
     extern __shared__ __align__(16) u32 s_hist[];          // [2][HYB_MAX_BINS]: elements, foreground flags
-    __shared__ u32 s_win[SORT_RUN_WINDOW + 1];
     __shared__ u32 s_warp[2 * SORT_WARPS];
     __shared__ u32 s_last;
     const int tid = threadIdx.x;
@@ -96,23 +95,20 @@ __global__ void __launch_bounds__(SORT_TPB) hyb_count_kernel(SortArgs a, HybArgs
             cur_seg = seg;
             ntl = 0;
         }
-        __syncthreads();                                   // bins cleared; previous tile done with s_win
-        const TileSrc T = tile_src_setup(a, 0, t, seg, off, s_win);
-        __syncthreads();
-        u32 key[SORT_KPT], fg[SORT_KPT];
-        u32 cur = tile_src_cursor(T);
+        __syncthreads();                                   // bins cleared
+        const u32* __restrict__ kp = a.keys[0] + (size_t)seg * a.cap + off;
+        u32 key[SORT_KPT];
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = k * SORT_TPB + tid;
-            const size_t src = idx < n ? tile_src_index(T, s_win, idx, cur) : 0;
-            key[k] = idx < n ? T.keys[src] : 0u;
-            fg[k] = idx < n ? (T.vals[src] & 1u) : 0u;
+            key[k] = idx < n ? kp[idx] : 0u;
         }
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
-            if (k * SORT_TPB + tid < n) {
-                atomicAdd(&s_hist[key[k] >> L], 1u);
-                if (fg[k]) atomicAdd(&s_hist[HYB_MAX_BINS + (key[k] >> L)], 1u);
+            if (k * SORT_TPB + tid < n) {                  // (the foreground flag rides in bit 31 of the key: the values are not read)
+                const u32 d = (key[k] & KEY_MASK) >> L;
+                atomicAdd(&s_hist[d], 1u);
+                if (key[k] & KEY_FG) atomicAdd(&s_hist[HYB_MAX_BINS + d], 1u);
             }
         }
         ++ntl;
@@ -124,7 +120,7 @@ __global__ void __launch_bounds__(SORT_TPB) hyb_count_kernel(SortArgs a, HybArgs
 struct PartSmem {
     u32 cnt[HYB_MAX_BINS / 2];    // u16 pairs: arrivals per bucket -> local start of the bucket in the staged tile
     u32 gd[SORT_TILE];            // indexed by the local start of a run: global slice start - local start
-    u32 keys[SORT_TILE];          // (the run-prefix window of the gathered source aliases keys while the tile is loaded)
+    u32 keys[SORT_TILE];
     u32 vals[SORT_TILE];          // (the list of non-empty buckets aliases vals until the tile is staged)
     u32 warp_sum[SORT_WARPS];
     u32 nlist;
@@ -149,27 +145,26 @@ __global__ void __launch_bounds__(SORT_TPB, 3) hyb_partition_kernel(SortArgs a, 
         __syncthreads();                                   // previous tile fully written out
         for (u32 b = tid; b < nwords; b += SORT_TPB) S.cnt[b] = 0;
         if (tid == 0) S.nlist = 0;
-        const TileSrc T = tile_src_setup(a, 0, t, seg, off, S.keys);
         __syncthreads();
         u32 key[SORT_KPT], val[SORT_KPT];
         unsigned short rnk[SORT_KPT];
         const u32 wbase = warp * (32 * SORT_KPT) + lane;
         {
-            u32 cur = tile_src_cursor(T);
+            const u32* __restrict__ kp = a.keys[0] + (size_t)seg * a.cap + off;
+            const u32* __restrict__ vp = a.vals[0] + (size_t)seg * a.cap + off;
 #pragma unroll
             for (int k = 0; k < SORT_KPT; ++k) {
                 const u32 idx = wbase + k * 32;
-                const size_t src = idx < n ? tile_src_index(T, S.keys, idx, cur) : 0;
-                key[k] = idx < n ? T.keys[src] : 0u;
-                val[k] = idx < n ? T.vals[src] : 0u;
+                key[k] = idx < n ? kp[idx] : 0u;
+                val[k] = idx < n ? vp[idx] : 0u;
             }
         }
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {               // arrival rank within the bucket (u16 halves: a tile has <= 4096 elements)
-            const u32 d = key[k] >> L, sh = (d & 1u) * 16u;
+            const u32 d = (key[k] & KEY_MASK) >> L, sh = (d & 1u) * 16u;
             rnk[k] = (wbase + k * 32 < n) ? (unsigned short)((atomicAdd(&S.cnt[d >> 1], 1u << sh) >> sh) & 0xFFFFu) : (unsigned short)0;
         }
-        __syncthreads();                                   // all arrivals counted; the window in S.keys is dead
+        __syncthreads();                                   // all arrivals counted
         {   // local starts (exclusive scan over the buckets; warp w owns a contiguous range of words, rows of 32) and the
             // list of non-empty buckets
             const u32 per_warp = (nwords + SORT_WARPS - 1) / SORT_WARPS;
@@ -224,7 +219,7 @@ __global__ void __launch_bounds__(SORT_TPB, 3) hyb_partition_kernel(SortArgs a, 
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             if (wbase + k * 32 < n) {
-                const u32 d = key[k] >> L;
+                const u32 d = (key[k] & KEY_MASK) >> L;
                 const u32 pos = ((S.cnt[d >> 1] >> ((d & 1u) * 16u)) & 0xFFFFu) + rnk[k];
                 S.keys[pos] = key[k];
                 S.vals[pos] = val[k];
@@ -236,7 +231,7 @@ __global__ void __launch_bounds__(SORT_TPB, 3) hyb_partition_kernel(SortArgs a, 
             const u32 i = k * SORT_TPB + tid;
             if (i < n) {
                 const u32 kk = S.keys[i];
-                const u32 d = kk >> L;
+                const u32 d = (kk & KEY_MASK) >> L;
                 const u32 ls = (S.cnt[d >> 1] >> ((d & 1u) * 16u)) & 0xFFFFu;
                 const u32 pos = S.gd[ls] + i;              // slice start - local start + local index
                 ko[pos] = kk;

@@ -71,7 +71,6 @@ struct LovaszParams {
     uint4* rec16;                       // per pixel candidate record (stats_kernel_async): {key_fg, p1, p2, guard p3}
     u32* rec4;                          //   label8 | class1 << 8 | class2 << 16
     u32* flags;                         // [0] emission path chosen by K1b (EMIT_PATH_*)
-    u32 *run_cnt, *run_prefix;          // [groups*n_runs][C] candidate counts per emission chunk; [n_seg][n_runs+1]
     EmitGeomDev geo_stream, geo_rec;    // chunk geometry of the streaming / record-driven emission kernels
     EmitGeomDev* geo;                   // the one in force (device memory; written by K1b / K1d, read by K2 and the sort)
     u32 *keysA, *valsA, *keysB, *valsB;
@@ -84,7 +83,7 @@ struct LovaszParams {
 
 struct LovaszLayout {
     size_t ctrl, seg_fg, seg_maxkey, seg_maxp, seg_count, grp_valid, seg_loss, seg_loss_h, seg_ovf, zero_end;
-    size_t seg_thr, seg_logthr, seg_w, seg_bits, grp_tmin, seg_order, run_cnt, run_prefix;
+    size_t seg_thr, seg_logthr, seg_w, seg_bits, grp_tmin, seg_order;
     size_t pix_m, pix_s, gown, lab8, cmask, rec16, rec4, keysA, valsA, keysB, valsB, gbg, sort_scratch, total;
     size_t hyb_hist, hyb_fgpre, hyb_done;
     SortScratch sort;
@@ -118,14 +117,6 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     const int groups = per_image ? N : 1;
     const size_t S = (size_t)groups * C;
     const size_t CP = (size_t)C * P;
-    size_t cap_max = 0, runs_max = 0;                      // every emission variant must fit
-    for (long long tile_px : {(long long)ECTA_TPB * 4, (long long)EMIT_TPB * 4, (long long)EMIT_TPB, (long long)EMIT_WARP_TILE}) {
-        const EmitGeom G = emit_geom(N, HW, per_image, tile_px);
-        if ((size_t)G.src_cap > cap_max) cap_max = (size_t)G.src_cap;
-        if ((size_t)G.n_runs > runs_max) runs_max = (size_t)G.n_runs;
-    }
-    const size_t holey = S * cap_max;                      // >= CP
-    const size_t runs = (size_t)groups * runs_max;
     size_t o = 0;
     L.ctrl = o;       o = align_up(o + 256, 256);
     L.seg_fg = o;     o = align_up(o + 4 * S, 256);
@@ -143,8 +134,6 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     L.seg_bits = o;   o = align_up(o + 4 * S, 256);
     L.grp_tmin = o;   o = align_up(o + 4 * (size_t)groups, 256);
     L.seg_order = o;  o = align_up(o + S, 256);
-    L.run_cnt = o;    o = align_up(o + 4 * runs * C, 256);
-    L.run_prefix = o; o = align_up(o + 4 * (runs + (size_t)groups) * C, 256);
     L.pix_m = o;      o = align_up(o + 4 * (size_t)P, 256);
     L.pix_s = o;      o = align_up(o + 4 * (size_t)P, 256);
     L.gown = o;       o = align_up(o + 4 * (size_t)P, 256);
@@ -152,8 +141,8 @@ static LovaszLayout lovasz_layout(int N, int C, long long HW, int per_image) {
     L.cmask = o;      o = align_up(o + 4 * (size_t)P, 256);
     L.rec16 = o;      o = align_up(o + 16 * (size_t)P, 256);
     L.rec4 = o;       o = align_up(o + 4 * (size_t)P, 256);
-    L.keysA = o;      o = align_up(o + 4 * holey, 256);
-    L.valsA = o;      o = align_up(o + 4 * holey, 256);
+    L.keysA = o;      o = align_up(o + 4 * CP, 256);
+    L.valsA = o;      o = align_up(o + 4 * CP, 256);
     L.keysB = o;      o = align_up(o + 4 * CP, 256);
     L.valsB = o;      o = align_up(o + 4 * CP, 256);
     // background-candidate gradients, indexed like the logits.  (Not aliased onto the dead sort buffer A any more: the
@@ -721,7 +710,7 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
     __shared__ u32 s_mask[B200SEG_MAX_CLASSES][WORDS];
     __shared__ u32 s_wpre[B200SEG_MAX_CLASSES][WORDS];
     __shared__ u32 s_tot[B200SEG_MAX_CLASSES];
-    __shared__ u32 s_run[B200SEG_MAX_CLASSES];
+    __shared__ u32 s_gbase[B200SEG_MAX_CLASSES];          // the tile's slice of every segment (reserved with one atomic per class)
     __shared__ float s_thr[B200SEG_MAX_CLASSES], s_logthr[B200SEG_MAX_CLASSES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = p.C;
@@ -741,7 +730,6 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
             if (tid < C) { s_thr[tid] = p.seg_thr[(size_t)g * C + tid]; s_logthr[tid] = p.seg_logthr[(size_t)g * C + tid]; }
             cur_g = g;
         }
-        if (tid < B200SEG_MAX_CLASSES) s_run[tid] = 0;
         for (int i = tid; i < B200SEG_MAX_CLASSES * WORDS; i += EMIT_TPB) (&s_mask[0][0])[i] = 0;
         __syncthreads();
 
@@ -821,7 +809,7 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
                 if (lane < WORDS) s_wpre[c][lane] = v - cnt;
-                if (lane == 31) s_tot[c] = v;
+                if (lane == 31) { s_tot[c] = v; s_gbase[c] = v ? atomicAdd(p.seg_count + (size_t)g * C + c, v) : 0u; }
             }
             __syncthreads();
 
@@ -836,20 +824,18 @@ __global__ void __launch_bounds__(EMIT_TPB) emit_kernel(LovaszParams p) {
                         float err, pr;
                         const bool fg = c == lab[j];
                         exact_accept(__ldg(lp + (size_t)c * p.HW + j), m[j], s[j], fg, s_thr[c], err, pr);
-                        const u32 rank = s_run[c] + s_wpre[c][bit >> 5] +
+                        const u32 rank = s_gbase[c] + s_wpre[c][bit >> 5] +
                                          __popc(s_mask[c][bit >> 5] & ((1u << (bit & 31)) - 1u));
-                        const size_t slot = ((size_t)g * C + c) * (size_t)G.src_cap + (size_t)r * G.run_stride + rank;
-                        p.keysA[slot] = err_key(err);
+                        const size_t slot = ((size_t)g * C + c) * (size_t)p.cap + rank;
+                        p.keysA[slot] = err_key(err) | (fg ? KEY_FG : 0u);
                         p.valsA[slot] = ((u32)(px0 + j) << 1) | (fg ? 1u : 0u);
                     }
                 }
             }
             __syncthreads();
-            if (tid < C) s_run[tid] += s_tot[tid];
             for (int i = tid; i < B200SEG_MAX_CLASSES * WORDS; i += EMIT_TPB) (&s_mask[0][0])[i] = 0;
             __syncthreads();
         }
-        if (tid < C) p.run_cnt[(size_t)chunk * C + tid] = s_run[tid];
     }
 }
 
@@ -923,7 +909,6 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
     prefetch(pre, true, 0);
 
     int cur_g = -1;
-    u32 run = 0;                                          // lane c: candidates of class c emitted so far in this chunk
     for (u32 it = 0; it < ntile; ++it) {
         const int stage = (int)(it & 1);
         const float m = nm, s = ns;
@@ -934,7 +919,6 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
         const int g = cur.g, n = cur.n;
         const u32 r = cur.r, k = cur.k;
         const bool exists = cur.gt < tpg;
-        if (k == 0) run = 0;
         if (g != cur_g) {
             __syncwarp();
             if (lane < CT) { s_thr[warp][lane] = p.seg_thr[(size_t)g * CT + lane]; s_logthr[warp][lane] = p.seg_logthr[(size_t)g * CT + lane]; }
@@ -988,7 +972,11 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
                 if (lane == c) mine = b;
             }
             __syncwarp();
-            if (lane < CT) { s_mask[warp][lane] = mine; s_base[warp][lane] = run; run += __popc(mine); }
+            if (lane < CT) {                               // the tile's slice of every segment: one atomic per class with candidates
+                const u32 cnt = __popc(mine);
+                s_mask[warp][lane] = mine;
+                s_base[warp][lane] = cnt ? atomicAdd(p.seg_count + (size_t)g * CT + lane, cnt) : 0u;
+            }
             __syncwarp();
             u32 mm = acc;
             int i = 0;
@@ -1000,12 +988,11 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
                 if (i >= 2) { float pr; exact_accept(Tz[c][lane], m, s, fg, thr[c], err, pr); }
                 ++i;
                 const u32 rank = s_base[warp][c] + __popc(s_mask[warp][c] & lt_mask);
-                const size_t slot = ((size_t)g * CT + c) * (size_t)G.src_cap + (size_t)r * G.run_stride + rank;
-                p.keysA[slot] = err_key(err);
+                const size_t slot = ((size_t)g * CT + c) * (size_t)p.cap + rank;
+                p.keysA[slot] = err_key(err) | (fg ? KEY_FG : 0u);
                 p.valsA[slot] = ((u32)px << 1) | (fg ? 1u : 0u);
             }
         }
-        if (k == tpc - 1 && lane < CT) p.run_cnt[((size_t)g * n_runs + r) * CT + lane] = run;
         emit_cursor_next(cur, tpc, n_runs, wtpi, p.per_image);
     }
     cp_async_wait<0>();
@@ -1042,11 +1029,9 @@ struct EctaSmem {
     u32 tot[B200SEG_MAX_CLASSES];                         // candidates of the class in this tile
     u32 coff[B200SEG_MAX_CLASSES];                        // offset of the class in the stage (current pass)
     u32 carry_cnt[B200SEG_MAX_CLASSES];                   // leftovers (< 8) waiting for the next tile
-    u32 emitted[B200SEG_MAX_CLASSES];                     // elements of the chunk already written (multiple of 8)
     u32 carryK[B200SEG_MAX_CLASSES][8], carryV[B200SEG_MAX_CLASSES][8];
     float thr[B200SEG_MAX_CLASSES];
     unsigned char order[B200SEG_MAX_CLASSES];             // classes by ascending threshold
-    unsigned long long cls_slot[B200SEG_MAX_CLASSES];     // first slot of the chunk's run of every class
     u32 wcoff[ECTA_TPB / 32][B200SEG_MAX_CLASSES];        // per-warp copy of the stage offsets (single-pass tiles)
     u32 stageK[ECTA_CAP], stageV[ECTA_CAP];
 };
@@ -1080,11 +1065,7 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
             tmin = p.grp_tmin[g];
             cur_g = g;
         }
-        const size_t chunk_slot0 = (size_t)g * CT * (size_t)G.src_cap + (size_t)r * G.run_stride;
-        if (tid < B200SEG_MAX_CLASSES) {
-            S.carry_cnt[tid] = 0; S.emitted[tid] = 0;
-            S.cls_slot[tid] = chunk_slot0 + (size_t)tid * (size_t)G.src_cap;
-        }
+        if (tid < B200SEG_MAX_CLASSES) S.carry_cnt[tid] = 0;
         for (int i = tid; i < B200SEG_MAX_CLASSES * ECTA_WORDS; i += ECTA_TPB) (&S.mask[0][0])[i] = 0;
         __syncthreads();
 
@@ -1200,7 +1181,7 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
                             a &= ~(1u << l8);
                             if ((int)l8 >= lo && (int)l8 < hi) {
                                 const u32 pos = coff[l8] - base + S.wpre[l8][word] + __popc(S.mask[l8][word] & bj);
-                                S.stageK[pos] = kfg[j]; S.stageV[pos] = v0 | 1u;
+                                S.stageK[pos] = kfg[j] | KEY_FG; S.stageV[pos] = v0 | 1u;
                             }
                         }
                         if ((a >> c1) & 1u) {
@@ -1234,8 +1215,12 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
                 // ---- write out: a warp per class, multiples of 8 elements = whole sectors; leftovers -> carry ----------------
                 for (int c = lo + warp; c < hi; c += NW) {
                     const u32 cc = S.carry_cnt[c], nt = S.tot[c], total = cc + nt, w = total & ~7u;
-                    const u32 co = coff[c] - base, done = S.emitted[c];
-                    const size_t cslot = S.cls_slot[c] + done;          // chunk_slot0 + c * src_cap, set per chunk
+                    const u32 co = coff[c] - base;
+                    // this tile's slice of the segment: one atomic per class (multiples of 8: slices start on sector boundaries)
+                    u32 gslot = 0;
+                    if (lane == 0 && w) gslot = atomicAdd(p.seg_count + (size_t)g * CT + c, w);
+                    gslot = __shfl_sync(FULL_MASK, gslot, 0);
+                    const size_t cslot = ((size_t)g * CT + c) * (size_t)p.cap + gslot;
                     u32* kd = p.keysA + cslot;
                     u32* vd = p.valsA + cslot;
                     for (u32 e = lane; e < w; e += 32) {
@@ -1253,7 +1238,7 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
                     }
                     __syncwarp();
                     if (lane < 8 && e < total) { S.carryK[c][lane] = lk; S.carryV[c][lane] = lv; }
-                    if (lane == 0) { S.carry_cnt[c] = total - w; S.emitted[c] = done + w; }
+                    if (lane == 0) S.carry_cnt[c] = total - w;
                 }
                 lo = hi;
                 if (lo >= CT)                               // last pass: the bit matrix is free, clear it for the next tile
@@ -1263,12 +1248,15 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
         }
         // ---- chunk end: flush the carries, publish the run lengths --------------------------------------------------------
         for (int c = warp; c < CT; c += NW) {
-            const u32 cc = S.carry_cnt[c], done = S.emitted[c];
+            const u32 cc = S.carry_cnt[c];
+            u32 gslot = 0;
+            if (lane == 0 && cc) gslot = atomicAdd(p.seg_count + (size_t)g * CT + c, cc);
+            gslot = __shfl_sync(FULL_MASK, gslot, 0);
             if (lane < cc) {
-                p.keysA[chunk_slot0 + (size_t)c * G.src_cap + done + lane] = S.carryK[c][lane];
-                p.valsA[chunk_slot0 + (size_t)c * G.src_cap + done + lane] = S.carryV[c][lane];
+                const size_t slot = ((size_t)g * CT + c) * (size_t)p.cap + gslot + lane;
+                p.keysA[slot] = S.carryK[c][lane];
+                p.valsA[slot] = S.carryV[c][lane];
             }
-            if (lane == 0) p.run_cnt[(size_t)chunk * CT + c] = done + cc;
         }
     }
 }
@@ -1448,19 +1436,18 @@ __global__ void __launch_bounds__(JAC_TPB, 4) jaccard_kernel(LovaszParams p, Sor
 #define LOC_CNT_STRIDE 260                                 // u16 row stride of the LSD passes: 256 bins + dummy bin, rows 8-byte aligned
 
 struct LocSmem {
-    u32 keys[LOC_CAP];                                     // as loaded (partition order)
-    u32 vals[LOC_CAP];
+    u32 keys[LOC_CAP];                                     // as loaded (partition order); bit 31 = foreground flag
+    u32 vals[LOC_CAP];                                     // copied under the counting phases: needed last
     unsigned short order[LOC_CAP];                         // element indices grouped by bin
     u32 bins[LOC_BINS];                                    // (count | fg count << 16) -> exclusive starts -> cursors (LSD passes: u16 counters)
     u32 warp_sum[LOC_WARPS];
-    double red[LOC_WARPS];
     u32 s_first, s_end, heavy, skip;
 };
 
 // One stable counting pass over the unit's n elements by digit ((A - sub) >> shift) & 255; B is moved along.
 // Element m lives in row m / 32; warp w owns rows [w * rpw, (w + 1) * rpw), so the order (warp, row, lane) is the
 // element order and the per-warp counters + a scan across warps give stable positions.  (Rare path: not inlined.)
-__device__ __noinline__ void loc_pass(LocSmem& S, u32* A, u32* Bv, u32 n, u32 rpw, u32 sub, u32 shift) {
+__device__ __noinline__ void loc_pass(LocSmem& S, u32* A, u32* Bv, u32 n, u32 rpw, u32 amask, u32 sub, u32 shift) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1;
     unsigned short (*cnt)[LOC_CNT_STRIDE] = reinterpret_cast<unsigned short (*)[LOC_CNT_STRIDE]>(S.bins);
@@ -1474,7 +1461,7 @@ __device__ __noinline__ void loc_pass(LocSmem& S, u32* A, u32* Bv, u32 n, u32 rp
 #pragma unroll
     for (int k = 0; k < LOC_KPT; ++k) {
         if ((u32)k < rpw) {                                // (warp-uniform)
-            const u32 d = (wb + k * 32 < n) ? (((a[k] - sub) >> shift) & 255u) : 256u;
+            const u32 d = (wb + k * 32 < n) ? ((((a[k] & amask) - sub) >> shift) & 255u) : 256u;
             const u32 m = peer_mask<9>(d);
             const int leader = __ffs(m) - 1;
             u32 old = 0;
@@ -1512,7 +1499,7 @@ __device__ __noinline__ void loc_pass(LocSmem& S, u32* A, u32* Bv, u32 n, u32 rp
 #pragma unroll
     for (int k = 0; k < LOC_KPT; ++k) {
         if ((u32)k < rpw && wb + k * 32 < n) {
-            const u32 d = ((a[k] - sub) >> shift) & 255u;
+            const u32 d = (((a[k] & amask) - sub) >> shift) & 255u;
             rnk[k] = (u32)binexcl[d] + cnt[warp][d] + rnk[k];
             A[rnk[k]] = a[k];
         }
@@ -1528,13 +1515,13 @@ __device__ __noinline__ void loc_pass(LocSmem& S, u32* A, u32* Bv, u32 n, u32 rp
 
 // The rare unit with a long bin group: full stable sort of (K, V) in place (LSD over the value bits, then the key bits),
 // then foreground prefix by ballots in sorted order and the gradient.  `fexcl` = foreground flags in front of the unit.
-__device__ __noinline__ double loc_heavy_unit(const LovaszParams& p, LocSmem& S, u32* K, u32* V, u32 n, u32 sub, u32 kbits,
-                                              u32 valbits, u32 pos0, u32 fexcl, float gts, float w, int c) {
+__device__ __noinline__ double loc_heavy_unit(const LovaszParams& p, LocSmem& S, u32* K, u32* V, u32 n, u32 sub,
+                                              u32 kbits, u32 valbits, u32 pos0, u32 fexcl, float gts, float w, int c) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 le_mask = lane == 31 ? FULL_MASK : ((2u << lane) - 1u);
     const u32 rpw = ((n + 31) / 32 + LOC_WARPS - 1) / LOC_WARPS;
-    for (u32 sh = 0; sh < valbits; sh += 8) loc_pass(S, V, K, n, rpw, 0u, sh);
-    for (u32 sh = 0; sh < kbits; sh += 8) loc_pass(S, K, V, n, rpw, sub, sh);
+    for (u32 sh = 0; sh < valbits; sh += 8) loc_pass(S, V, K, n, rpw, 0xFFFFFFFFu, 0u, sh);
+    for (u32 sh = 0; sh < kbits; sh += 8) loc_pass(S, K, V, n, rpw, KEY_MASK, sub, sh);
     const u32 wb = warp * rpw * 32 + lane;
     u32 run = 0;
     for (u32 k = 0; k < rpw; ++k) {
@@ -1584,21 +1571,15 @@ __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, S
 
         // ---- the unit's buckets: first digit change at or after p0, first digit change at or after p0 + T0 ----------
         // (keys and values travel global -> shared as 16-byte cp.async copies: no load -> store round trip per element)
-        const bool al16 = ((sbase & 3) == 0) && ((a.cap & 3) == 0) && ((((uintptr_t)gkeys | (uintptr_t)gvals) & 15) == 0);
+        const bool al16 = ((sbase & 3) == 0) && ((a.cap & 3) == 0) && (((uintptr_t)gkeys & 15) == 0);
         u32 prevkey = 0;
         if (tid == 0 && p0 > 0) prevkey = gkeys[sbase - 1];
         u32 loaded = 0, checked = 0, target = min(avail, (u32)(LOC_T0 + 1024));
         for (;;) {
             if (al16) {                                    // (whole 16-byte chunks: may read up to 3 elements past `target`, inside the segment)
-                for (u32 ch = loaded / 4 + tid; ch < (target + 3) / 4; ch += LOC_TPB) {
-                    cp_async<16>(&S.keys[4 * ch], gkeys + sbase + 4 * ch);
-                    cp_async<16>(&S.vals[4 * ch], gvals + sbase + 4 * ch);
-                }
+                for (u32 ch = loaded / 4 + tid; ch < (target + 3) / 4; ch += LOC_TPB) cp_async<16>(&S.keys[4 * ch], gkeys + sbase + 4 * ch);
             } else {
-                for (u32 i = loaded + tid; i < target; i += LOC_TPB) {
-                    cp_async<4>(&S.keys[i], gkeys + sbase + i);
-                    cp_async<4>(&S.vals[i], gvals + sbase + i);
-                }
+                for (u32 i = loaded + tid; i < target; i += LOC_TPB) cp_async<4>(&S.keys[i], gkeys + sbase + i);
             }
             cp_async_commit();
             cp_async_wait<0>();
@@ -1608,7 +1589,7 @@ __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, S
                 bool bnd = p0 + i == 0;
                 if (!bnd) {
                     const u32 prev = i > 0 ? S.keys[i - 1] : prevkey;      // (i == 0: thread 0, which holds the predecessor)
-                    bnd = (S.keys[i] >> L) != (prev >> L);
+                    bnd = ((S.keys[i] & KEY_MASK) >> L) != ((prev & KEY_MASK) >> L);
                 }
                 if (bnd) atomicMin(i < LOC_T0 ? &S.s_first : &S.s_end, i);
             }
@@ -1630,10 +1611,17 @@ __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, S
         }
         const u32 n = e_rel - s_rel;
         u32* K = S.keys + s_rel;
+        const u32* __restrict__ gv = gvals + sbase + s_rel;    // the unit's values, in the order of K
         u32* V = S.vals + s_rel;
-        if (p.dbg & 32) continue;
+        // the values are needed last (tie order, the pixel a gradient goes to): their copy runs under the counting phases
+        if (al16 && (((uintptr_t)gvals & 15) == 0)) {
+            for (u32 ch = s_rel / 4 + tid; ch < (e_rel + 3) / 4; ch += LOC_TPB) cp_async<16>(&S.vals[4 * ch], gvals + sbase + 4 * ch);
+        } else {
+            for (u32 i = tid; i < n; i += LOC_TPB) cp_async<4>(&V[i], gv + i);
+        }
+        cp_async_commit();
         // ---- counting pass over the span of the unit's keys ---------------------------------------------------------------------
-        const u32 dmin = K[0] >> L, dmax = K[n - 1] >> L;                   // buckets lie in digit order
+        const u32 dmin = (K[0] & KEY_MASK) >> L, dmax = (K[n - 1] & KEY_MASK) >> L;     // buckets lie in digit order
         const u32 sub = dmin << L;
         const u32 kbits = L + (dmax > dmin ? 32u - (u32)__clz((int)(dmax - dmin)) : 0u);
         const u32 bsh = kbits > LOC_BIN_BITS ? kbits - LOC_BIN_BITS : 0u;
@@ -1643,7 +1631,7 @@ __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, S
             for (u32 i = tid; i < LOC_BINS / 4; i += LOC_TPB) z[i] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
-        for (u32 i = tid; i < n; i += LOC_TPB) atomicAdd(&S.bins[(K[i] - sub) >> bsh], 1u + ((V[i] & 1u) << 16));
+        for (u32 i = tid; i < n; i += LOC_TPB) { const u32 k = K[i]; atomicAdd(&S.bins[((k & KEY_MASK) - sub) >> bsh], 1u + ((k >> 31) << 16)); }
         __syncthreads();
         {   // exclusive scan of both halves at once (totals <= LOC_CAP: no carry); thread t owns bins [16t, 16t + 16)
             uint4* b4 = reinterpret_cast<uint4*>(S.bins) + 4 * tid;
@@ -1678,11 +1666,11 @@ __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, S
         }
         __syncthreads();
         const bool heavy = S.heavy != 0;
-        if (p.dbg & 16) continue;
-        if (!heavy) {                                      // group the elements by bin (arrival order inside a bin)
-            for (u32 i = tid; i < n; i += LOC_TPB) S.order[atomicAdd(&S.bins[(K[i] - sub) >> bsh], 1u) & 0xFFFFu] = (unsigned short)i;
-            __syncthreads();
-        }
+        if (!heavy)                                        // group the elements by bin (arrival order inside a bin)
+            for (u32 i = tid; i < n; i += LOC_TPB)
+                S.order[atomicAdd(&S.bins[((K[i] & KEY_MASK) - sub) >> bsh], 1u) & 0xFFFFu] = (unsigned short)i;
+        cp_async_wait<0>();                                // the values have landed
+        __syncthreads();
         const int c = seg % p.C;
         const u32 pos0 = p0 + s_rel;                       // position of the unit's first element in its segment
         double acc = 0.0;
@@ -1690,34 +1678,28 @@ __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, S
         else {
             // ---- rank inside the bin group, Jaccard gradient ------------------------------------------------------------------
             for (u32 i = tid; i < n; i += LOC_TPB) {
-                const u32 k = K[i], v = V[i];
+                const u32 v = V[i];
+                const u32 kf = K[i], k = kf & KEY_MASK;
                 const u32 b = (k - sub) >> bsh;
                 const u32 lo = b ? S.bins[b - 1] : 0u;     // bins[b - 1]: (end of bin b-1 = start of b) | fg flags before bin b-1 ...
                 const u32 hi = S.bins[b];                  // ... and bins[b]: end of b | fg flags before bin b
                 const u32 start = lo & 0xFFFFu, stop = hi & 0xFFFFu;
-                u32 rank = start, F = fexcl + (hi >> 16) + (v & 1u);
-                for (u32 j = start; j < stop; ++j) {
+                u32 rank = start, F = fexcl + (hi >> 16) + (kf >> 31);
+                for (u32 j = start; j < stop; ++j) {       // the other members of the bin group: (key, value) order
                     const u32 o = S.order[j];
-                    const u32 k2 = K[o], v2 = V[o];
-                    const bool less = k2 < k || (k2 == k && v2 < v);
+                    const u32 kf2 = K[o], k2 = kf2 & KEY_MASK;
+                    const bool less = k2 < k || (k2 == k && V[o] < v);
                     rank += less;
-                    F += less & (v2 & 1u);
+                    F += less ? (kf2 >> 31) : 0u;
                 }
-                if (p.dbg & 8) acc += (double)(rank + F); else
                 acc += jaccard_element(p, k, v, pos0 + rank, F, gts, w, c);
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
-        if (lane == 0) S.red[warp] = acc;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-#pragma unroll
-            for (int w2 = 0; w2 < LOC_WARPS; ++w2) tot += S.red[w2];
-            atomicAdd(h.seg_loss + seg, tot);
-        }
+        if (lane == 0 && acc != 0.0) atomicAdd(h.seg_loss + seg, acc);
     }
+    __syncthreads();
     // the CTA that finishes last turns the per-segment sums into the loss, unless a segment needs the fallback
     if (tid == 0) {
         __threadfence();
@@ -1733,17 +1715,19 @@ __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, S
 // at once when no segment overflowed -- the usual case.
 __global__ void __launch_bounds__(SORT_TPB, 2) sort_fallback_kernel(LovaszParams p, SortArgs a, HybArgs h, u32 max_tiles) {
     if (!ld_relaxed(h.ovf_any)) return;                    // (grid-uniform: written by an earlier launch)
-    for (int pass = 0; pass < SORT_PASSES; ++pass) {
+    const int n_passes = a.val_passes + SORT_PASSES;
+    u32* bar = a.gbar + 2 * SORT_MAX_PASSES;               // (the first 2 * SORT_MAX_PASSES counters belong to sort_big_scan)
+    for (int pass = 0; pass < n_passes; ++pass) {
         sort_count_body(a, pass, max_tiles);
-        grid_barrier(a.gbar + 2 * SORT_PASSES + 2 * pass, a.status);
-        if (pass == 0) sort_scatter_body<false, true>(a, pass, max_tiles);
+        grid_barrier(bar + 2 * pass, a.status);
+        if (pass < a.val_passes) sort_scatter_body<false, true>(a, pass, max_tiles);
         else sort_scatter_body<false, false>(a, pass, max_tiles);
-        grid_barrier(a.gbar + 2 * SORT_PASSES + 2 * pass + 1, a.status);
+        grid_barrier(bar + 2 * pass + 1, a.status);
     }
     sort_fg_count_body(a, max_tiles);
-    grid_barrier(a.gbar + 4 * SORT_PASSES, a.status);
+    grid_barrier(bar + 2 * SORT_MAX_PASSES, a.status);
     jaccard_body(p, a);
-    grid_barrier(a.gbar + 4 * SORT_PASSES + 1, a.status);
+    grid_barrier(bar + 2 * SORT_MAX_PASSES + 1, a.status);
     if (blockIdx.x == 0 && threadIdx.x == 0) loss_finalize(p, h.seg_loss, h.seg_ovf);
 }
 
@@ -2079,7 +2063,7 @@ static int hybrid_enqueue(const LovaszParams& p, const SortArgs& a, const HybArg
     }
     const int sms = b200seg_sm_count();
     {
-        const int pgrid = a.n_seg < sms ? a.n_seg : sms;
+        const int pgrid = a.n_seg < sms ? a.n_seg : sms;     // CTA 0 plans the tiles, all of them clear the bucket tables
         sort_prepare_kernel<<<pgrid, SORT_PREP_TPB, 0, st>>>(a, h, L.max_tiles);
         LAUNCH_CHECK("sort_prepare_kernel");
     }
@@ -2158,7 +2142,6 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.ce_enabled = 0; p.has_ce_ignore = 0; p.ce_ignore = 0; p.ce_out = nullptr;
     p.ce_sum = reinterpret_cast<double*>(p.ctrl + CTRL_CE_SUM); p.ce_cnt = p.ctrl + CTRL_CE_CNT;
     p.ce_inv_n = reinterpret_cast<float*>(p.ctrl + CTRL_CE_INV_N);
-    p.run_cnt = (u32*)(ws + L.run_cnt); p.run_prefix = (u32*)(ws + L.run_prefix);
     p.geo_stream = EmitGeomDev{0, 0, 0, 0}; p.geo_rec = EmitGeomDev{0, 0, 0, 0};
     p.keysA = (u32*)(ws + L.keysA); p.valsA = (u32*)(ws + L.valsA);
     p.keysB = (u32*)(ws + L.keysB); p.valsB = (u32*)(ws + L.valsB);
@@ -2370,16 +2353,14 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
     char* ss = ws + L.sort_scratch;
     a.keys[0] = p.keysA; a.vals[0] = p.valsA; a.keys[1] = p.keysB; a.vals[1] = p.valsB;
     a.seg_count = p.seg_count; a.seg_bits = p.seg_bits; a.n_seg = p.n_seg; a.cap = p.cap;
-    a.src_keys = p.keysA; a.src_vals = p.valsA; a.run_prefix = p.run_prefix; a.geo = p.geo;
-    a.run_cnt = p.run_cnt; a.run_prefix_w = p.run_prefix; a.seg_count_w = p.seg_count; a.n_classes = c;
-    a.prep_ticket = p.ctrl + CTRL_PTICKET;
     a.tile_start = (u32*)(ss + L.sort.tile_start); a.tilehist = (u32*)(ss + L.sort.tilehist);
-    a.tile_desc = (uint4*)(ss + L.sort.tile_desc); a.tile_runs = (uint2*)(ss + L.sort.tile_runs);
+    a.tile_desc = (uint4*)(ss + L.sort.tile_desc);
     a.seg_done = (u32*)(ss + L.sort.seg_done);
     a.bin_base = (u32*)(ss + L.sort.bin_base); a.tile_fg = (u32*)(ss + L.sort.tile_fg);
     a.big = (u32*)(ss + L.sort.big); a.chunksum = (u32*)(ss + L.sort.chunksum); a.gbar = (u32*)(ss + L.sort.gbar);
     a.status = p.status;
     a.seg_sel = nullptr;
+    a.val_passes = SORT_VAL_PASSES;                        // the emission order is arbitrary: canonical ties come from the values
     if (b200seg_tuning().sort_path == 1) {                 // plain path: three LSD passes, then the Jaccard kernel
         if (int rc = sort_enqueue(a, L.sort, st)) return rc;
         jaccard_kernel<<<sms * 4, JAC_TPB, 0, st>>>(p, a);
@@ -2554,13 +2535,11 @@ extern "C" int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint3
     SortArgs a;
     a.keys[0] = keys_in; a.vals[0] = vals_in; a.keys[1] = keys_out; a.vals[1] = vals_out;
     a.seg_count = counts; a.seg_bits = key_bits; a.n_seg = n_segments; a.cap = capacity;
-    a.src_keys = nullptr; a.src_vals = nullptr; a.run_prefix = nullptr; a.geo = nullptr;
-    a.run_cnt = nullptr; a.run_prefix_w = nullptr; a.seg_count_w = nullptr; a.n_classes = 1; a.prep_ticket = nullptr;
     a.tile_start = (u32*)(ss + L.tile_start); a.tilehist = (u32*)(ss + L.tilehist);
-    a.tile_desc = (uint4*)(ss + L.tile_desc); a.tile_runs = (uint2*)(ss + L.tile_runs);
+    a.tile_desc = (uint4*)(ss + L.tile_desc);
     a.seg_done = (u32*)(ss + L.seg_done);
     a.bin_base = (u32*)(ss + L.bin_base); a.tile_fg = (u32*)(ss + L.tile_fg);
     a.big = (u32*)(ss + L.big); a.chunksum = (u32*)(ss + L.chunksum); a.gbar = (u32*)(ss + L.gbar);
-    a.status = status; a.seg_sel = nullptr;
+    a.status = status; a.seg_sel = nullptr; a.val_passes = 0;    // the hook sorts by key only, stably
     return sort_enqueue(a, L, (cudaStream_t)stream);
 }

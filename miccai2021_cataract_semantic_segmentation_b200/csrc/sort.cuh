@@ -12,10 +12,9 @@
 //            (segments above SORT_SCAN_LOCAL_MAX tiles: scanned by the whole scatter grid instead, sort_big_scan)
 //   scatter  re-read the tile (L2), stable ranks (ballot / MATCH.ANY peer masks + per-warp counters), reorder in shared
 //            memory, write to the other buffer with warp-contiguous stores; launched cooperatively (grid barriers)
-// The first pass can read a "holey" source: every segment is a concatenation of n_runs runs, run r starting at
-// s*src_cap + r*run_stride with run_prefix[s][r+1]-run_prefix[s][r] elements (what the emission kernels leave
-// behind without any cross-CTA ordering); sort_prepare_kernel turns the run counts into the prefix, notes for every
-// tile which runs it intersects, plans the tiles and writes their descriptors.
+// The emission kernels leave every segment compact but in no particular order (tiles reserve their slices with atomics), so
+// for the loss the three key passes are preceded by SORT_VAL_PASSES 8-bit passes over the value bits: equal keys then end up
+// in ascending pixel order = torch.sort(stable=True).  sort_prepare_kernel plans the tiles and writes their descriptors.
 // A last small kernel counts the foreground flags (value bit 0) per tile of the final order for the Jaccard scan and
 // drops the dead source buffer from L2.
 #pragma once
@@ -27,8 +26,9 @@
 #define SORT_WARPS (SORT_TPB / 32)
 #define SORT_TILE (SORT_TPB * SORT_KPT)      // 4096 elements
 #define SORT_MAX_BINS 1024
-#define SORT_PASSES 3
-#define SORT_RUN_WINDOW 1024                 // run-prefix entries staged in shared memory per tile
+#define SORT_PASSES 3                        // digit passes over the key bits
+#define SORT_VAL_PASSES 4                    // optional leading 8-bit passes over the value bits (unordered input)
+#define SORT_MAX_PASSES (SORT_PASSES + SORT_VAL_PASSES)
 #define SORT_SCAN_LOCAL_MAX 128               // segments with more tiles are scanned by the whole grid (see sort_big_scan)
 #define SORT_CHUNK 64                        // tiles per chunk of that scan
 #ifndef SORT_SCATTER_MINB
@@ -42,21 +42,9 @@ struct SortArgs {
     const u32* seg_bits;    // [n_seg] significant key bits (1..30)
     int n_seg;
     long long cap;          // segment stride of the ping-pong arrays (elements)
-    // holey source of pass 0 (run_prefix == nullptr: pass 0 reads keys[0] / vals[0], compact)
-    const u32* src_keys;
-    const u32* src_vals;
-    const u32* run_prefix;  // [n_seg][n_runs + 1]
-    const EmitGeomDev* geo; // n_runs, run_stride, src_cap of the holey source (device memory)
-    // inputs of the run scan (holey source only): candidates per (group, chunk, class) as the emission kernels leave them
-    const u32* run_cnt;     // [groups * n_runs][n_classes]
-    u32* run_prefix_w;      // = run_prefix, writable: filled by sort_prepare_kernel
-    u32* seg_count_w;       // = seg_count, writable: filled by sort_prepare_kernel
-    u32* prep_ticket;       // zeroed by the caller: CTAs of sort_prepare_kernel that finished part A
-    int n_classes;
     // scratch
     u32* tile_start;        // [n_seg + 1] exclusive prefix of tiles per segment
     uint4* tile_desc;       // [max_tiles] {segment, first element, element count, digit width}
-    uint2* tile_runs;       // [max_tiles] {first, last} source run intersecting the tile (holey pass-0 source only)
     u32* seg_done;          // [SORT_PASSES][n_seg] tiles counted so far (last CTA of a segment runs its scan)
     u32* tilehist;          // [max_tiles][1024]
     u32* bin_base;          // [n_seg][1024]
@@ -66,11 +54,12 @@ struct SortArgs {
     u32* gbar;              // [SORT_GBAR] grid-barrier counters: 2 per pass (sort_big_scan), the rest for the fused fallback
     int* status;
     const u32* seg_sel;     // nullptr: every segment; else only segments with seg_sel[seg] != 0 are processed
+    int val_passes;         // 0: stable sort by key (input order kept among equal keys); SORT_VAL_PASSES: sort by (key, value)
 };
-#define SORT_GBAR 24
+#define SORT_GBAR 40
 
 struct SortScratch {
-    size_t tile_start, tile_desc, tile_runs, seg_done, tilehist, bin_base, tile_fg, big, chunksum, gbar, total;
+    size_t tile_start, tile_desc, seg_done, tilehist, bin_base, tile_fg, big, chunksum, gbar, total;
     u32 max_tiles;
 };
 
@@ -80,8 +69,7 @@ static inline SortScratch sort_scratch_layout(int n_seg, long long total_capacit
     size_t o = 0;
     L.tile_start = o; o = align_up(o + sizeof(u32) * (size_t)(n_seg + 1), 256);
     L.tile_desc = o;  o = align_up(o + sizeof(uint4) * (size_t)L.max_tiles, 256);
-    L.tile_runs = o;  o = align_up(o + sizeof(uint2) * ((size_t)L.max_tiles + n_seg + 2), 256);
-    L.seg_done = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_PASSES, 256);
+    L.seg_done = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_MAX_PASSES, 256);
     L.bin_base = o;   o = align_up(o + sizeof(u32) * (size_t)n_seg * SORT_MAX_BINS, 256);
     L.tile_fg = o;    o = align_up(o + sizeof(u32) * (size_t)L.max_tiles, 256);
     L.big = o;        o = align_up(o + sizeof(u32) * (size_t)(n_seg + 1), 256);
@@ -140,6 +128,17 @@ __device__ __forceinline__ u32 sort_digit_width(u32 bits) {
     return w < 1 ? 1 : (w > 10 ? 10 : w);
 }
 
+// digit of pass `pass`: the leading a.val_passes passes take 8-bit digits of the value (so that equal keys end up in
+// ascending value = pixel order whatever order the input came in), the remaining SORT_PASSES passes w_key-bit digits of the key
+struct PassDigit { u32 shift, w; bool by_val; };
+__device__ __forceinline__ PassDigit sort_pass_digit(const SortArgs& a, int pass, u32 w_key) {
+    PassDigit d;
+    d.by_val = pass < a.val_passes;
+    d.w = d.by_val ? 8u : w_key;
+    d.shift = d.by_val ? 8u * (u32)pass : (u32)(pass - a.val_passes) * w_key;
+    return d;
+}
+
 // largest segment whose first tile is <= t (skips empty segments)
 __device__ __forceinline__ int sort_find_segment(const u32* tile_start, int n_seg, u32 t) {
     int lo = 0, hi = n_seg - 1;
@@ -151,83 +150,30 @@ __device__ __forceinline__ int sort_find_segment(const u32* tile_start, int n_se
 }
 
 // ---- prepare: everything between the emission and the first digit pass ----------------------------------------------
-//   A (holey source only; a CTA per segment, all CTAs): exclusive prefix of the segment's chunk counts (the run prefix),
-//     the segment's count, and for every tile the source runs it intersects -- written by the runs themselves (the run
-//     that holds a tile's first element says so), no searching
-//   B (the CTA that finishes last): tiles per segment -> exclusive prefix (tile_start); clears the per-pass counters;
-//     the list of big segments; one descriptor per tile {segment, first element, element count, digit width}, so the
-//     per-tile prologue of every later kernel is a single 16-byte load instead of a chain of dependent ones
+//   every CTA: clears the hybrid path's bucket tables of its segments (hist == nullptr: plain path, nothing to clear)
+//   CTA 0:     tiles per segment -> exclusive prefix (tile_start); clears the per-pass counters; the list of big segments;
+//              one descriptor per tile {segment, first element, element count, key digit width}, so the per-tile prologue
+//              of every later kernel is a single 16-byte load instead of a chain of dependent ones
 #define SORT_PREP_TPB 1024
-// tile_runs is indexed by capacity, not by the (not yet known) global tile number: slot of tile `tl` of segment `seg`
-__device__ __forceinline__ size_t sort_runs_slot(const SortArgs& a, int seg, u32 tl) {
-    return (size_t)(((long long)seg * a.cap) / SORT_TILE) + (size_t)seg + tl;
-}
-
 __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a, HybArgs h, u32 max_tiles) {
     __shared__ u32 s_warp[32];
-    __shared__ u32 s_carry, s_lastrun, s_islast;
+    __shared__ u32 s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (a.run_prefix) {
-        const int n_runs = a.geo->n_runs, C = a.n_classes;
+    if (h.hist) {
         for (int seg = blockIdx.x; seg < a.n_seg; seg += gridDim.x) {
-            const int g = seg / C, c = seg - g * C;
-            u32* out = a.run_prefix_w + (size_t)seg * (n_runs + 1);
-            uint2* truns = a.tile_runs + sort_runs_slot(a, seg, 0);
-            __syncthreads();
-            if (tid == 0) { s_carry = 0; s_lastrun = 0; }
-            __syncthreads();
-            for (int base = 0; base < n_runs; base += SORT_PREP_TPB) {
-                const int r = base + tid;
-                const u32 x = r < n_runs ? a.run_cnt[((size_t)g * n_runs + r) * C + c] : 0;
-                u32 v = x;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += y; }
-                if (lane == 31) s_warp[warp] = v;
-                __syncthreads();
-                if (warp == 0) {
-                    u32 wv = s_warp[lane];
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(FULL_MASK, wv, o); if (lane >= o) wv += y; }
-                    s_warp[lane] = wv;
-                }
-                __syncthreads();
-                const u32 p0 = s_carry + (warp ? s_warp[warp - 1] : 0) + v - x;      // elements before run r
-                if (r < n_runs) out[r] = p0;
-                if (x) {                                   // tiles whose first element lies in this run
-                    for (u32 tl = (p0 + SORT_TILE - 1) / SORT_TILE; tl * SORT_TILE < p0 + x; ++tl) truns[tl].x = (u32)r;
-                    atomicMax(&s_lastrun, (u32)r);
-                }
-                __syncthreads();
-                if (tid == SORT_PREP_TPB - 1) s_carry = p0 + x;
-                __syncthreads();
-            }
-            const u32 cnt = s_carry, nt = (cnt + SORT_TILE - 1) / SORT_TILE;
-            if (tid == 0) { out[n_runs] = cnt; a.seg_count_w[seg] = cnt; }
-            if (h.hist) {                                  // hybrid path: clear the segment's bucket histogram
-                const u32 nb = 1u << hyb_plan(a.seg_bits[seg], cnt).w;
-                u32* gh = h.hist + (size_t)seg * HYB_MAX_BINS;
-                u32* gf = h.fgpre + (size_t)seg * HYB_MAX_BINS;
-                for (u32 b = tid; b < nb; b += SORT_PREP_TPB) { gh[b] = 0; gf[b] = 0; }
-                if (tid == 0) h.seg_done[seg] = 0;
-            }
-            // last run a tile touches: at most the first run of the next tile (a bound is enough: it sizes the window)
-            for (u32 tl = tid; tl < nt; tl += SORT_PREP_TPB) truns[tl].y = tl + 1 < nt ? truns[tl + 1].x : s_lastrun;
+            const u32 nb = 1u << hyb_plan(a.seg_bits[seg], a.seg_count[seg]).w;
+            u32* gh = h.hist + (size_t)seg * HYB_MAX_BINS;
+            u32* gf = h.fgpre + (size_t)seg * HYB_MAX_BINS;
+            for (u32 b = tid; b < nb; b += SORT_PREP_TPB) { gh[b] = 0; gf[b] = 0; }
+            if (tid == 0) h.seg_done[seg] = 0;
         }
-        if (gridDim.x > 1) {                               // only the CTA that finishes last goes on
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) s_islast = atomicAdd(a.prep_ticket, 1u) == gridDim.x - 1;
-            __syncthreads();
-            if (!s_islast) return;
-            __threadfence();
-        }
-        __syncthreads();
     }
+    if (blockIdx.x != 0) return;
     if (tid == 0) s_carry = 0;
     __syncthreads();
     for (int base = 0; base < a.n_seg; base += SORT_PREP_TPB) {
         const int s = base + tid;
-        const u32 nt = s < a.n_seg ? (__ldcg(a.seg_count + s) + SORT_TILE - 1) / SORT_TILE : 0;
+        const u32 nt = s < a.n_seg ? (a.seg_count[s] + SORT_TILE - 1) / SORT_TILE : 0;
         u32 v = nt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
@@ -251,79 +197,20 @@ __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a,
     if (tid < SORT_GBAR) a.gbar[tid] = 0;
     __syncthreads();
     for (int sg = tid; sg < a.n_seg; sg += SORT_PREP_TPB)
-        if ((__ldcg(a.seg_count + sg) + SORT_TILE - 1) / SORT_TILE > SORT_SCAN_LOCAL_MAX) a.big[1 + atomicAdd(a.big, 1u)] = (u32)sg;
-    for (int i = tid; i < a.n_seg * SORT_PASSES; i += SORT_PREP_TPB) a.seg_done[i] = 0;
+        if ((a.seg_count[sg] + SORT_TILE - 1) / SORT_TILE > SORT_SCAN_LOCAL_MAX) a.big[1 + atomicAdd(a.big, 1u)] = (u32)sg;
+    for (int i = tid; i < a.n_seg * SORT_MAX_PASSES; i += SORT_PREP_TPB) a.seg_done[i] = 0;
     for (u32 i = tid; i < total && i < max_tiles; i += SORT_PREP_TPB) a.tile_fg[i] = 0;
-    if (h.hist) {
-        if (tid < 2) h.ticket[tid] = 0;
-    }
+    if (h.hist && tid < 2) h.ticket[tid] = 0;
     __syncthreads();
     for (int seg = warp; seg < a.n_seg; seg += SORT_PREP_TPB / 32) {      // descriptors: a warp per segment
         const u32 t_first = a.tile_start[seg], nt = a.tile_start[seg + 1] - t_first;
-        const u32 cnt = __ldcg(a.seg_count + seg), w = sort_digit_width(a.seg_bits[seg]);
+        const u32 cnt = a.seg_count[seg], w = sort_digit_width(a.seg_bits[seg]);
         for (u32 i = lane; i < nt && t_first + i < max_tiles; i += 32) {
             const u32 off = i * SORT_TILE;
             a.tile_desc[t_first + i] = make_uint4((u32)seg, off, min((u32)SORT_TILE, cnt - off), w);
         }
     }
 }
-
-// ---- tile addressing (compact or gathered through the run prefix) ------------------------------------------------
-struct TileSrc {
-    const u32* keys;
-    const u32* vals;
-    size_t base;            // compact: element 0 of the tile
-    // gathered:
-    bool gather;
-    const u32* prefix;      // run prefix of this segment (global)
-    u32 r_lo, r_hi;         // runs intersecting the tile: [r_lo, r_hi]
-    u32 voff;               // virtual index of tile element 0 within the segment
-    size_t seg_base;
-    long long run_stride;
-    bool window;            // prefix[r_lo .. r_hi + 1] staged in shared memory
-};
-
-// Block-wide setup; s_win needs SORT_RUN_WINDOW + 1 entries.  Contains a __syncthreads() when gathering.
-__device__ __forceinline__ TileSrc tile_src_setup(const SortArgs& a, int pass, u32 t, int seg, u32 off, u32* s_win) {
-    TileSrc T;
-    const bool odd = pass & 1;
-    T.gather = (pass == 0 && a.run_prefix != nullptr);
-    T.prefix = nullptr; T.r_lo = T.r_hi = T.voff = 0; T.seg_base = 0; T.run_stride = 0; T.window = false; T.base = 0;
-    if (!T.gather) {
-        T.keys = odd ? a.keys[1] : a.keys[0];
-        T.vals = odd ? a.vals[1] : a.vals[0];
-        T.base = (size_t)seg * a.cap + off;
-        return T;
-    }
-    const EmitGeomDev G = *a.geo;
-    T.keys = a.src_keys; T.vals = a.src_vals;
-    T.prefix = a.run_prefix + (size_t)seg * (G.n_runs + 1);
-    T.voff = off;
-    T.seg_base = (size_t)seg * G.src_cap;
-    T.run_stride = G.run_stride;
-    const uint2 rr = a.tile_runs[sort_runs_slot(a, seg, off / SORT_TILE)];
-    T.r_lo = rr.x; T.r_hi = rr.y;
-    T.window = (T.r_hi - T.r_lo + 2) <= SORT_RUN_WINDOW + 1;
-    if (T.window)
-        for (u32 i = threadIdx.x; i < T.r_hi - T.r_lo + 2; i += blockDim.x) s_win[i] = T.prefix[T.r_lo + i];
-    __syncthreads();
-    return T;
-}
-
-// Source index of tile element idx.  `r` is the caller's running run cursor (relative to r_lo when the window is
-// staged): a thread visits its elements in increasing order, so the run index only moves forward.
-__device__ __forceinline__ size_t tile_src_index(const TileSrc& T, const u32* s_win, u32 idx, u32& r) {
-    if (!T.gather) return T.base + idx;
-    const u32 v = T.voff + idx;
-    if (T.window) {
-        const u32 last = T.r_hi - T.r_lo;
-        while (r < last && s_win[r + 1] <= v) ++r;
-        return T.seg_base + (size_t)(r + T.r_lo) * T.run_stride + (v - s_win[r]);
-    }
-    while (r < T.r_hi && T.prefix[r + 1] <= v) ++r;
-    return T.seg_base + (size_t)r * T.run_stride + (v - T.prefix[r]);
-}
-__device__ __forceinline__ u32 tile_src_cursor(const TileSrc& T) { return T.window ? 0u : T.r_lo; }
 
 // ---- per-segment scan, run by the CTA that counted the segment's last tile ---------------------------------------------
 // column scan over the segment's tiles (tilehist[tile][bin] -> exclusive offset of the tile within the bin) and
@@ -370,7 +257,6 @@ __device__ __forceinline__ void segment_scan(const SortArgs& a, u32* rows, int s
 // ---- count: per-tile digit histogram (+ the segment's scan once its last tile is in) ---------------------------------
 __device__ __forceinline__ void sort_count_body(const SortArgs& a, int pass, u32 total_bound) {
     __shared__ __align__(16) u32 s_hist[SORT_MAX_BINS];
-    __shared__ u32 s_win[SORT_RUN_WINDOW + 1];
     __shared__ u32 s_warp[SORT_WARPS];
     __shared__ u32 s_last;
     const int tid = threadIdx.x;
@@ -378,19 +264,20 @@ __device__ __forceinline__ void sort_count_body(const SortArgs& a, int pass, u32
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const uint4 d4 = a.tile_desc[t];
         const int seg = (int)d4.x;
-        const u32 off = d4.y, n = d4.z, w = d4.w;
-        const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
+        const u32 off = d4.y, n = d4.z;
+        const PassDigit pd = sort_pass_digit(a, pass, d4.w);
+        const u32 nbins = 1u << pd.w, dmask = nbins - 1, shift = pd.shift;
         if (a.seg_sel && !a.seg_sel[seg]) continue;        // (CTA-uniform)
-        __syncthreads();                                   // previous iteration done with s_hist / s_win
+        __syncthreads();                                   // previous iteration done with s_hist
         for (u32 b = tid; b < SORT_MAX_BINS; b += SORT_TPB) s_hist[b] = 0;
-        const TileSrc T = tile_src_setup(a, pass, t, seg, off, s_win);
         __syncthreads();
+        const bool odd = pass & 1;                         // (static indexing of the kernel-parameter arrays only)
+        const u32* __restrict__ src = (pd.by_val ? (odd ? a.vals[1] : a.vals[0]) : (odd ? a.keys[1] : a.keys[0])) + (size_t)seg * a.cap + off;
         u32 key[SORT_KPT];
-        u32 cur = tile_src_cursor(T);
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 idx = k * SORT_TPB + tid;
-            key[k] = idx < n ? T.keys[tile_src_index(T, s_win, idx, cur)] : 0;
+            key[k] = idx < n ? src[idx] : 0;
         }
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k)
@@ -439,8 +326,8 @@ struct ScatterSmem {
     unsigned short cnt[SORT_WARPS][SORT_CNT_STRIDE];     // per-warp digit counters -> exclusive offsets across warps
     unsigned short binexcl[SORT_MAX_BINS];               // exclusive prefix of the tile's bin totals
     u32 binoff[SORT_MAX_BINS];                           // global position of local sorted index i in bin d: binoff[d] + i
-    u32 keys[SORT_TILE];                                 // (the run-prefix window of a gathered pass-0 tile aliases keys:
-    u32 vals[SORT_TILE];                                 //  it is dead once the tile is in registers)
+    u32 keys[SORT_TILE];
+    u32 vals[SORT_TILE];
     u32 warp_sum[SORT_WARPS];
 };
 
@@ -508,7 +395,7 @@ __device__ __forceinline__ void sort_big_scan(const SortArgs& a, int pass, u32* 
         const int seg = (int)a.big[1 + j];
         if (a.seg_sel && !a.seg_sel[seg]) continue;
         const u32 t0 = a.tile_start[seg], nt = a.tile_start[seg + 1] - t0;
-        const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]), nch = (nt + SORT_CHUNK - 1) / SORT_CHUNK;
+        const u32 nbins = 1u << sort_pass_digit(a, pass, sort_digit_width(a.seg_bits[seg])).w, nch = (nt + SORT_CHUNK - 1) / SORT_CHUNK;
         for (u32 lc = 0; lc < nch; ++lc, ++unit) {
             if (unit % gridDim.x != blockIdx.x || (u32)(4 * tid) >= nbins) continue;
             const u32 ta = t0 + lc * SORT_CHUNK, tb = min(ta + SORT_CHUNK, t0 + nt);
@@ -533,7 +420,7 @@ __device__ __forceinline__ void sort_big_scan(const SortArgs& a, int pass, u32* 
         const int seg = (int)a.big[1 + j];
         if (a.seg_sel && !a.seg_sel[seg]) continue;
         const u32 t0 = a.tile_start[seg], nt = a.tile_start[seg + 1] - t0;
-        const u32 nbins = 1u << sort_digit_width(a.seg_bits[seg]), nch = (nt + SORT_CHUNK - 1) / SORT_CHUNK;
+        const u32 nbins = 1u << sort_pass_digit(a, pass, sort_digit_width(a.seg_bits[seg])).w, nch = (nt + SORT_CHUNK - 1) / SORT_CHUNK;
         const u32 c0 = sort_chunk_id(t0, seg, 0);
         __syncthreads();
         segment_scan(a, a.chunksum, seg, c0, c0 + nch, nbins, s_warp);
@@ -541,8 +428,8 @@ __device__ __forceinline__ void sort_big_scan(const SortArgs& a, int pass, u32* 
     grid_barrier(a.gbar + 2 * pass + 1, a.status);
 }
 
-// GATHER = true: pass 0 over the holey source (values loaded with the keys: the source index is costly to form twice).
-// GATHER = false: compact source; the values are loaded only when they are placed, so key + rank are all that lives in
+// GATHER = true: keys and values are both loaded up front (needed by the passes over the value digits).
+// GATHER = false: the values are loaded only when they are placed, so key + rank are all that lives in
 // registers through the ranking and the kernel fits 4 CTAs per SM (1100 tiles: 2 rounds of 592 instead of 3 of 444).
 template <bool USE_MATCH, bool GATHER>
 __device__ __forceinline__ void sort_scatter_body(const SortArgs& a, int pass, u32 total_bound) {
@@ -559,8 +446,9 @@ __device__ __forceinline__ void sort_scatter_body(const SortArgs& a, int pass, u
     for (u32 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const uint4 d4 = a.tile_desc[t];
         const int seg = (int)d4.x;
-        const u32 off = d4.y, n = d4.z, w = d4.w;
-        const u32 nbins = 1u << w, dmask = nbins - 1, shift = pass * w;
+        const u32 off = d4.y, n = d4.z;
+        const PassDigit pd = sort_pass_digit(a, pass, d4.w);       // (by_val passes are launched with GATHER = true: both arrays in registers)
+        const u32 w = pd.w, nbins = 1u << w, dmask = nbins - 1, shift = pd.shift;
         u32* __restrict__ ko = kout + (size_t)seg * a.cap;
         u32* __restrict__ vo = vout + (size_t)seg * a.cap;
         if (a.seg_sel && !a.seg_sel[seg]) continue;        // (CTA-uniform)
@@ -569,39 +457,28 @@ __device__ __forceinline__ void sort_scatter_body(const SortArgs& a, int pass, u
             uint2* z = reinterpret_cast<uint2*>(&S.cnt[0][0]);
             for (u32 i = tid; i < sizeof(S.cnt) / 8; i += SORT_TPB) z[i] = make_uint2(0, 0);
         }
-        const TileSrc T = tile_src_setup(a, pass, t, seg, off, S.keys);
         __syncthreads();
+        const u32* __restrict__ kp = (odd ? a.keys[1] : a.keys[0]) + (size_t)seg * a.cap + off;
+        const u32* __restrict__ vp = (odd ? a.vals[1] : a.vals[0]) + (size_t)seg * a.cap + off;
 
         u32 key[SORT_KPT], val[GATHER ? SORT_KPT : 1], rnk[SORT_KPT];
         const u32 wbase = warp * (32 * SORT_KPT) + lane;
-        if (!GATHER) {
-            const u32* __restrict__ kp = T.keys + T.base + wbase;
 #pragma unroll
-            for (int k = 0; k < SORT_KPT; ++k) key[k] = (wbase + k * 32 < n) ? kp[k * 32] : 0xFFFFFFFFu;
-        } else if (!T.gather) {
-            const u32* __restrict__ kp = T.keys + T.base + wbase;
-            const u32* __restrict__ vp = T.vals + T.base + wbase;
-#pragma unroll
-            for (int k = 0; k < SORT_KPT; ++k) {
-                const bool valid = wbase + k * 32 < n;
-                key[k] = valid ? kp[k * 32] : 0xFFFFFFFFu;
-                val[GATHER ? k : 0] = valid ? vp[k * 32] : 0u;
-            }
-        } else {
-            u32 cur = tile_src_cursor(T);
-#pragma unroll
-            for (int k = 0; k < SORT_KPT; ++k) {
-                const u32 idx = wbase + k * 32;
-                const size_t src = idx < n ? tile_src_index(T, S.keys, idx, cur) : 0;
-                key[k] = idx < n ? T.keys[src] : 0xFFFFFFFFu;
-                val[GATHER ? k : 0] = idx < n ? T.vals[src] : 0u;
-            }
+        for (int k = 0; k < SORT_KPT; ++k) {
+            const bool valid = wbase + k * 32 < n;
+            key[k] = valid ? kp[wbase + k * 32] : 0xFFFFFFFFu;
+            if (GATHER) val[GATHER ? k : 0] = valid ? vp[wbase + k * 32] : 0u;
         }
-        switch (w) {                                      // uniform per tile
-            case 10: rank_rows<11, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
-            case 9: rank_rows<10, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
-            case 8: rank_rows<9, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
-            default: rank_rows<8, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+        if constexpr (GATHER) {
+            if (pd.by_val) rank_rows<9, USE_MATCH>(S, val, rnk, n, wbase, shift, dmask, nbins, warp, lane);   // digit of the value
+        }
+        if (!(GATHER && pd.by_val)) {
+            switch (w) {                                  // uniform per tile
+                case 10: rank_rows<11, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+                case 9: rank_rows<10, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+                case 8: rank_rows<9, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+                default: rank_rows<8, USE_MATCH>(S, key, rnk, n, wbase, shift, dmask, nbins, warp, lane); break;
+            }
         }
         __syncthreads();
         // thread b owns bins [4b, 4b+4): four u16 counters travel as one 64-bit word (no carries: totals <= 4096)
@@ -658,18 +535,17 @@ __device__ __forceinline__ void sort_scatter_body(const SortArgs& a, int pass, u
 #pragma unroll
             for (int k = 0; k < SORT_KPT; ++k) {
                 if (wbase + k * 32 < n) {
-                    const u32 d = (key[k] >> shift) & dmask;
+                    const u32 d = ((pd.by_val ? val[GATHER ? k : 0] : key[k]) >> shift) & dmask;
                     const u32 lpos = (u32)S.binexcl[d] + S.cnt[warp][d] + rnk[k];
                     S.keys[lpos] = key[k];
                     S.vals[lpos] = val[GATHER ? k : 0];
                 }
             }
         } else {                                           // values straight from the source tile (L2) to their place
-            const u32* __restrict__ vp = T.vals + T.base + wbase;
 #pragma unroll
             for (int k = 0; k < SORT_KPT; ++k) {
                 const bool valid = wbase + k * 32 < n;
-                const u32 v = valid ? vp[k * 32] : 0u;
+                const u32 v = valid ? vp[wbase + k * 32] : 0u;
                 const u32 d = (key[k] >> shift) & dmask;
                 rnk[k] = valid ? (u32)S.binexcl[d] + S.cnt[warp][d] + rnk[k] : 0xFFFFFFFFu;
                 if (valid) S.keys[rnk[k]] = key[k];
@@ -684,10 +560,10 @@ __device__ __forceinline__ void sort_scatter_body(const SortArgs& a, int pass, u
         for (int k = 0; k < SORT_KPT; ++k) {
             const u32 i = k * SORT_TPB + tid;
             if (i < n) {
-                const u32 kk = S.keys[i];
-                const u32 pos = S.binoff[(kk >> shift) & dmask] + i;
+                const u32 kk = S.keys[i], vv = S.vals[i];
+                const u32 pos = S.binoff[(((GATHER && pd.by_val) ? vv : kk) >> shift) & dmask] + i;
                 ko[pos] = kk;
-                vo[pos] = S.vals[i];
+                vo[pos] = vv;
             }
         }
     }
@@ -750,7 +626,7 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
     }
     {
         const int sms_p = b200seg_sm_count();
-        const int pgrid = a.run_prefix ? (a.n_seg < sms_p ? a.n_seg : sms_p) : 1;
+        const int pgrid = 1;
         sort_prepare_kernel<<<pgrid, SORT_PREP_TPB, 0, st>>>(a, h, L.max_tiles);
     }
     LAUNCH_CHECK("sort_prepare_kernel");
@@ -772,11 +648,12 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
         occ_gather[dev] = max(1, min(min(o[0], o[1]), SORT_SCATTER_MINB));
         occ_compact[dev] = max(1, min(min(o[2], o[3]), SORT_SCATTER_MINB + 1));
     }
-    for (int p = 0; p < SORT_PASSES; ++p) {
+    const int n_passes = a.val_passes + SORT_PASSES;
+    for (int p = 0; p < n_passes; ++p) {
         sort_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, p, L.max_tiles);
         LAUNCH_CHECK("sort_count_kernel");
-        const bool use_match = match_mode == 1 || (match_mode == 2 && p == SORT_PASSES - 1);
-        const bool gather = p == 0 && a.run_prefix != nullptr;
+        const bool use_match = p >= a.val_passes && (match_mode == 1 || (match_mode == 2 && p == n_passes - 1));
+        const bool gather = p < a.val_passes;              // value-digit passes keep both arrays in registers
         {   // cooperative launch: the grid is resident as a whole or not at all, so the grid barriers of sort_big_scan cannot
             // dead-lock against another partially resident grid (two loss heads on two streams)
             const u32 per_sm = (dev >= 0 && dev < 64) ? (u32)(gather ? occ_gather[dev] : occ_compact[dev]) : 1u;
@@ -789,7 +666,7 @@ static inline int sort_enqueue(const SortArgs& a, const SortScratch& L, cudaStre
                                     : (use_match ? (const void*)sort_scatter_kernel<true, false> : (const void*)sort_scatter_kernel<false, false>);
             CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(sgrid), dim3(SORT_TPB), args, sizeof(ScatterSmem), st));
         }
-        if (p + 1 < SORT_PASSES) b200seg_stage(5 + p, st);
+        if (p >= a.val_passes && p + 1 < n_passes) b200seg_stage(5 + p - a.val_passes, st);
     }
     sort_fg_count_kernel<<<cgrid, SORT_TPB, 0, st>>>(a, L.max_tiles);
     LAUNCH_CHECK("sort_fg_count_kernel");
