@@ -2,7 +2,7 @@
 RViMLab/MICCAI2021_Cataract_semantic_segmentation (losses/LovaszSoftmax.py, utils/torch_utils.py:221-346,
 utils/metrics.py, losses/iou.py).  Host side is PyTorch; compute goes through the C ABI in include/b200seg.h."""
 from .class_info import CATEGORIES, CLASS_INFO, NUM_CLASSES
-from .fused import (IoUTracker, LossWrapper, LovaszSoftmaxCE, LovaszSoftmaxWithMetrics, SegmentationMeter,
+from .fused import (AsyncToNumpy, BestModelTracker, GraphedValidationStep, IoUTracker, LossWrapper, LovaszSoftmaxCE, LovaszSoftmaxWithMetrics, SegmentationMeter,
                     TwoScaleLoss)
 from .install import install
 from .lovasz import LovaszSoftmax, lovasz_softmax, lovasz_softmax_ce
@@ -14,7 +14,7 @@ from .metrics import (IoU, accumulate_confusion_matrix, get_confusion_matrix, ge
 
 __all__ = [
     "CATEGORIES", "CLASS_INFO", "NUM_CLASSES", "LovaszSoftmax", "LovaszSoftmaxWithMetrics", "SegmentationMeter",
-    "lovasz_softmax", "lovasz_softmax_ce", "OhemCrossEntropy", "ohem_cross_entropy", "LovaszSoftmaxCE", "LossWrapper", "TwoScaleLoss", "IoUTracker", "install", "IoU", "accumulate_confusion_matrix", "metrics_summary", "set_confusion_dtype",
+    "lovasz_softmax", "lovasz_softmax_ce", "OhemCrossEntropy", "ohem_cross_entropy", "LovaszSoftmaxCE", "LossWrapper", "TwoScaleLoss", "IoUTracker", "AsyncToNumpy", "BestModelTracker", "GraphedValidationStep", "install", "IoU", "accumulate_confusion_matrix", "metrics_summary", "set_confusion_dtype",
     "sliding_miou", "t_get_confusion_matrix", "t_get_mean_iou", "t_get_miou", "t_get_pixel_accuracy", "t_get_single_class_iou",
     "t_normalise_confusion_matrix", "get_confusion_matrix", "get_mean_iou", "get_pixel_accuracy",
     "get_single_class_iou", "normalise_confusion_matrix",

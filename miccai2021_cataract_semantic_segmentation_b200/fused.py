@@ -301,3 +301,131 @@ class IoUTracker:
         elif not self.ema.is_cuda:
             self._latest = newest
         return self._host[self._latest].numpy()
+
+
+class AsyncToNumpy:
+    """Drop-in for the reference's ``utils.to_numpy`` (utils/utils.py:463-468) inside the manager modules, installed by
+    ``install(async_iou=True)``.  The one per-step caller on the training path is the adaptive sampler's
+    ``to_numpy(iou)`` (managers/OCRNet_Manager.py:114-117), a blocking device-to-host read of <= 26 floats in the middle
+    of the step.  For a small 1-D float CUDA tensor this version starts an asynchronous copy into pinned memory and hands
+    back the newest copy that has already completed -- the value of the previous step (the very first call waits).  The
+    sampler's exponential average is therefore one step behind and the training step no longer synchronises there.  Every
+    other argument (images, matrices for figures, CPU tensors) takes the reference's blocking path unchanged."""
+
+    MAX_ELEMENTS = 64
+
+    def __init__(self, blocking):
+        self.blocking = blocking
+        self.slots = {}                                          # (device, n) -> [buffers, events, next, latest]
+
+    def __call__(self, tensor):
+        if not (torch.is_tensor(tensor) and tensor.is_cuda and tensor.dim() == 1 and tensor.is_floating_point()
+                and tensor.numel() <= self.MAX_ELEMENTS):
+            return self.blocking(tensor)
+        key = (tensor.device, tensor.numel(), tensor.dtype)
+        st = self.slots.get(key)
+        with torch.no_grad():
+            if st is None:
+                bufs = [torch.empty(tensor.numel(), dtype=tensor.dtype, pin_memory=True) for _ in range(2)]
+                bufs[0].copy_(tensor)                            # first call: nothing older to hand out
+                torch.cuda.current_stream(tensor.device).synchronize()
+                self.slots[key] = st = [bufs, [None, None], 1, 0]
+                return bufs[0].numpy().copy()
+            bufs, events, nxt, latest = st
+            prev = 1 - nxt                                        # written by the previous call
+            if events[prev] is not None and events[prev].query():
+                latest = prev
+            bufs[nxt].copy_(tensor.detach(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(tensor.device))
+            events[nxt] = ev
+            st[2], st[3] = 1 - nxt, latest
+            if latest == nxt:                                     # never hand out the buffer being overwritten
+                events[nxt].synchronize()
+            return bufs[latest].numpy().copy()
+
+
+class BestModelTracker:
+    """Device-side twin of the best-model bookkeeping at the end of the reference's validation
+    (managers/OCRNet_Manager.py:208-223): the mean IoUs are rounded to 4 decimals (``round(float(x), 4)``) and a new best
+    is declared when the rounded mIoU exceeds the best so far.  ``update`` takes the device scalars
+    (``metrics_summary`` / ``t_get_mean_iou(..., True, rare=True)``) and neither synchronises nor leaves the device;
+    ``poll()`` tells the host, without blocking, whether the last update was a new best once its flag has arrived
+    (``wait=True`` blocks -- at epoch end, before the checkpoint is written).
+    Rounding: a float32 times 1e4 is exact in float64, so round-half-even of that product divided by 1e4 is the same
+    double as Python's correctly rounded ``round(float(x), 4)`` (checked bit for bit in tests/test_gpu_ce.py)."""
+
+    def __init__(self, device=None, best_miou: float = 0.0):
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.best = torch.zeros(4, dtype=torch.float64, device=device)       # mIoU, anatomies, instruments, rare
+        self.best[0] = best_miou
+        pin = device.type == "cuda"
+        self._host = torch.zeros(5, dtype=torch.float64, pin_memory=pin)     # flag, then the four values of the last update
+        self._event = None
+
+    @staticmethod
+    def round4(x: torch.Tensor) -> torch.Tensor:
+        return torch.round(x.to(torch.float64) * 1e4) / 1e4
+
+    def update(self, m_iou, m_iou_anatomies, m_iou_instruments, m_iou_rare):
+        vals = torch.stack([torch.as_tensor(v, device=self.best.device).reshape(()).to(torch.float64)
+                            for v in (m_iou, m_iou_anatomies, m_iou_instruments, m_iou_rare)])
+        vals = torch.cat([self.round4(vals[:3]), vals[3:]])                  # the reference rounds the first three only
+        flag = vals[0] > self.best[0]
+        self.best = torch.where(flag, vals, self.best)
+        self._host.copy_(torch.cat([flag.to(torch.float64).reshape(1), vals]), non_blocking=True)
+        if self.best.is_cuda:
+            self._event = torch.cuda.Event()
+            self._event.record(torch.cuda.current_stream(self.best.device))
+        return flag
+
+    def poll(self, wait: bool = False):
+        """(is_new_best, [mIoU, anatomies, instruments, rare]) of the last update, or None while its flag is in flight."""
+        if self._event is not None:
+            if wait:
+                self._event.synchronize()
+            elif not self._event.query():
+                return None
+        h = self._host.numpy()
+        return bool(h[0] != 0.0), [float(v) for v in h[1:]]
+
+
+class GraphedValidationStep:
+    """The reference validates frame by frame (managers/OCRNet_Manager.py:146-161: batch 1, ``torch.no_grad()``, loss value
+    + running confusion matrix per 544 x 960 frame).  At that size every kernel of the forward pass is a few microseconds
+    long and the step is bound by its ~10 launches.  This helper captures the forward-only step (fused loss + confusion
+    matrix) for one input shape in a CUDA graph and replays it per frame: one launch, no per-call allocation.
+
+        step = GraphedValidationStep({"experiment": 3}, meter, (1, 25, 544, 960))
+        for img, lbl in loader:
+            loss = step(model(img), lbl)          # device scalar; accumulate with `total += loss`, read once at the end
+    The logits and labels are copied into the graph's static buffers (one pass over the frame, ~20 us at 544 x 960); pass
+    ``step.logits`` as the model's output buffer (``out=`` / in-place) to avoid even that."""
+
+    def __init__(self, config, meter: SegmentationMeter, shape, label_dtype=torch.int64, device=None):
+        device = meter.cm.device if device is None else torch.device(device)
+        self.meter = meter
+        self.module = LovaszSoftmaxWithMetrics(config, meter)
+        self.logits = torch.zeros(shape, dtype=torch.float32, device=device)
+        self.labels = torch.zeros((shape[0], shape[2], shape[3]), dtype=label_dtype, device=device)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side), torch.no_grad():          # warm-up outside the capture (lazy initialisation of the library)
+            for _ in range(2):
+                self.module(self.logits, self.labels)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        saved = meter.cm.clone()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.loss = self.module(self.logits, self.labels)
+        meter.cm.copy_(saved)                                   # the warm-up frames are not part of anybody's statistics
+        meter.reset()
+
+    def __call__(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        if logits.data_ptr() != self.logits.data_ptr():
+            self.logits.copy_(logits, non_blocking=True)
+        if labels.data_ptr() != self.labels.data_ptr():
+            self.labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return self.loss

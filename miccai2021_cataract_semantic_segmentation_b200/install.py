@@ -80,10 +80,13 @@ def _two_stream_two_scale(ref_cls):
 
 
 def install(packages=("losses", "utils", "managers"), verbose: bool = False, fuse_ce: bool = False,
-            two_stream_heads: bool = False):
+            two_stream_heads: bool = False, async_iou: bool = False):
     """Returns {module_name: [rebound names]}.  ``fuse_ce=True`` additionally replaces ``LossWrapper`` wherever it is
     bound by a subclass that evaluates its CrossEntropyLoss + LovaszSoftmax pair in one fused pass (SURVEY.md 8 F1);
-    ``two_stream_heads=True`` replaces ``TwoScaleLoss`` by a subclass that runs its two heads on two CUDA streams."""
+    ``two_stream_heads=True`` replaces ``TwoScaleLoss`` by a subclass that runs its two heads on two CUDA streams;
+    ``async_iou=True`` rebinds ``to_numpy`` inside the ``managers.*`` modules to ``fused.AsyncToNumpy``: the adaptive
+    sampler's per-step read of the per-class IoU vector (managers/OCRNet_Manager.py:114-117) then no longer blocks on the
+    GPU (it sees the previous step's vector); every other ``to_numpy`` call keeps the reference's behaviour."""
     replaced = {}
     table = dict(_LOSS_NAMES)
     table.update(_METRIC_NAMES)
@@ -95,6 +98,15 @@ def install(packages=("losses", "utils", "managers"), verbose: bool = False, fus
         ref_lw = getattr(sys.modules.get("losses.LossWrapper"), "LossWrapper", None)
         if ref_lw is not None and not getattr(ref_lw, "_b200_fused", False):
             table["LossWrapper"] = _fused_loss_wrapper(ref_lw)
+    if async_iou:
+        from .fused import AsyncToNumpy
+        for mod_name, mod in list(sys.modules.items()):
+            if mod is None or not mod_name.startswith("managers."):
+                continue
+            cur = mod.__dict__.get("to_numpy")
+            if cur is not None and callable(cur) and not isinstance(cur, AsyncToNumpy):
+                mod.__dict__["to_numpy"] = AsyncToNumpy(cur)
+                replaced.setdefault(mod_name, []).append("to_numpy")
     for mod_name, mod in list(sys.modules.items()):
         if mod is None or not any(mod_name == p or mod_name.startswith(p + ".") for p in packages):
             continue
@@ -110,7 +122,7 @@ def install(packages=("losses", "utils", "managers"), verbose: bool = False, fus
                 mod.__dict__[name] = obj
                 hits.append(name)
         if hits:
-            replaced[mod_name] = hits
+            replaced[mod_name] = replaced.get(mod_name, []) + hits
             if verbose:
                 print(f"[b200seg.install] {mod_name}: {', '.join(hits)}")
     return replaced

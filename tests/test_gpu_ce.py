@@ -209,3 +209,35 @@ def test_fused_pair_raises_lazily_on_an_out_of_range_label(b200):
         mod(x, y)                                                  # the flag of the previous call
     mod(x, y)
     mod.check()                                                    # cleared after raising
+
+
+def test_async_to_numpy_hands_out_the_previous_step_without_blocking(b200):
+    """install(async_iou=True) semantics: small float CUDA vectors come back one call late from a pinned mirror; everything
+    else takes the blocking path."""
+    calls = []
+
+    def blocking(t):
+        calls.append(tuple(t.shape))
+        return t.detach().cpu().numpy()
+
+    f = b200.AsyncToNumpy(blocking)
+    vecs = [torch.full((25,), float(i), device="cuda") for i in range(5)]
+    got = []
+    for v in vecs:
+        got.append(f(v).copy())
+        torch.cuda.synchronize()                                    # (so that "the previous copy has completed" is deterministic here)
+    assert [float(g[0]) for g in got] == [0.0, 0.0, 1.0, 2.0, 3.0] and calls == []
+    big = torch.zeros((3, 8, 8), device="cuda")
+    assert f(big).shape == (3, 8, 8) and calls == [(3, 8, 8)]       # not a small vector: the reference's own path
+
+
+def test_best_model_tracker_on_device(b200):
+    tr = b200.BestModelTracker()
+    assert tr.poll(wait=True) == (False, [0.0, 0.0, 0.0, 0.0])
+    tr.update(torch.tensor(0.71946, device="cuda"), torch.tensor(0.8, device="cuda"), torch.tensor(0.6, device="cuda"),
+              torch.tensor(0.3, device="cuda"))
+    flag, vals = tr.poll(wait=True)
+    assert flag and vals[0] == round(float(np.float32(0.71946)), 4) == 0.7195
+    tr.update(torch.tensor(0.71949, device="cuda"), torch.tensor(0.9, device="cuda"), torch.tensor(0.9, device="cuda"),
+              torch.tensor(0.9, device="cuda"))
+    assert tr.poll(wait=True)[0] is False and float(tr.best[1]) == 0.8

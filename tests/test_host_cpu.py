@@ -272,8 +272,10 @@ import torch, utils, losses, managers
 import managers.OCRNet_Manager, managers.BaseManager
 import miccai2021_cataract_semantic_segmentation_b200 as b200
 ref_lovasz, ref_cm, ref_lw = losses.LovaszSoftmax, utils.t_get_confusion_matrix, sys.modules["losses.LossWrapper"].LossWrapper
-rep = b200.install(fuse_ce=True, two_stream_heads=True)
+rep = b200.install(fuse_ce=True, two_stream_heads=True, async_iou=True)
 out = {"replaced": rep}
+out["async_to_numpy"] = (isinstance(vars(sys.modules["managers.OCRNet_Manager"])["to_numpy"], b200.AsyncToNumpy)
+                         and not isinstance(utils.to_numpy, b200.AsyncToNumpy))
 mods = {"losses": losses, "losses.LossWrapper": sys.modules["losses.LossWrapper"], "losses.TwoScaleLoss": sys.modules["losses.TwoScaleLoss"],
         "managers.OCRNet_Manager": sys.modules["managers.OCRNet_Manager"], "managers.BaseManager": sys.modules["managers.BaseManager"],
         "utils": utils}
@@ -315,7 +317,7 @@ def test_install_against_the_real_reference_packages():
     assert out["miou"] and all(out["miou"].values())
     assert out["defining_modules_keep_reference"]
     assert out["losswrapper_is_subclass_of_reference"] and out["losswrapper_lovasz_is_dropin"]
-    assert out["twoscale_heads_are_dropins"] and out["manager_lookup"]
+    assert out["twoscale_heads_are_dropins"] and out["manager_lookup"] and out["async_to_numpy"]
     assert "managers.OCRNet_Manager" in out["replaced"] and "LovaszSoftmax" in out["replaced"]["managers.OCRNet_Manager"]
 
 
@@ -325,3 +327,32 @@ def test_duplicate_class_indices_are_rejected():
     assert _resolve_classes([0, 3, 7], 8) == (1, 0b10001001)
     with pytest.raises(ValueError):
         _resolve_classes([0, 3, 3], 8)
+
+
+def test_best_model_rounding_matches_python_round():
+    """BestModelTracker.round4 == round(float(x), 4) of the reference (managers/OCRNet_Manager.py:208-210), bit for bit."""
+    from miccai2021_cataract_semantic_segmentation_b200 import BestModelTracker
+    g = torch.Generator().manual_seed(9)
+    x = torch.cat([torch.rand(200000, generator=g), torch.tensor([0.0, 1.0, 0.12345, 0.5, 0.99995, 0.00005, 0.71945])])
+    # values sitting exactly on ties of the fp32 grid as well: k + 0.5 ulp patterns around 4-decimal boundaries
+    x = torch.cat([x, (torch.arange(0, 10000, 37, dtype=torch.float64) / 1e4 + 5e-5).float()])
+    got = BestModelTracker.round4(x).numpy()
+    ref = [round(float(v), 4) for v in x.numpy()]
+    assert all(a == b for a, b in zip(got.tolist(), ref))
+
+
+def test_best_model_tracker_sequence_on_cpu():
+    from miccai2021_cataract_semantic_segmentation_b200 import BestModelTracker
+    tr = BestModelTracker(device="cpu")
+    seq = [(0.41237, 0.5, 0.3, 0.1), (0.41239, 0.6, 0.2, 0.2), (0.41246, 0.7, 0.1, 0.3), (0.3, 0.9, 0.9, 0.9)]
+    best, flags = 0, []
+    for m, a, i, r in seq:
+        tr.update(torch.tensor(m), torch.tensor(a), torch.tensor(i), torch.tensor(r))
+        flag, vals = tr.poll(wait=True)
+        mm = round(float(torch.tensor(m).numpy()), 4)
+        ref_flag = mm > best
+        best = max(best, mm)
+        flags.append(flag)
+        assert flag == ref_flag and vals[0] == mm
+    assert flags == [True, False, True, False]              # 0.4124 -> 0.4124 (no strict improvement) -> 0.4125 -> worse
+    assert float(tr.best[0]) == 0.4125 and abs(float(tr.best[1]) - 0.7) < 1e-12

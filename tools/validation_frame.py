@@ -26,3 +26,27 @@ with torch.no_grad():
     torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (reps * len(frames))
 print(f"forward-only Lovasz + confusion matrix, 1 x {c} x {h} x {w}: {us:.1f} us / frame  ({h * w / us:.0f} Mpx/s)")
+
+# the same step captured in a CUDA graph (GraphedValidationStep): one launch per frame
+meter2 = b200.SegmentationMeter(exp, c)
+step = b200.GraphedValidationStep({"experiment": exp}, meter2, (1, c, h, w))
+ref_loss = []
+meter.reset()
+with torch.no_grad():
+    for x, y in frames:
+        ref_loss.append(float(mod(x, y)))
+got = [float(step(x, y)) for x, y in frames]
+assert got == ref_loss and torch.equal(meter.cm, meter2.cm), "graph replay differs from the eager step"
+for variant, copy in (("copying logits+labels into the static buffers", True), ("inputs already in the static buffers", False)):
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        for x, y in frames:
+            if copy:
+                step(x, y)
+            else:
+                step(step.logits, step.labels)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * len(frames))
+    print(f"CUDA graph replay, {variant}: {us:.1f} us / frame  ({h * w / us:.0f} Mpx/s)")
