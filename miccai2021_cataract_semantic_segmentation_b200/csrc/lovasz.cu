@@ -1000,15 +1000,12 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
 
 // Record-driven emission (the fast path after stats_kernel_async): candidates come from the 20-byte per-pixel records;
 // the logits are only touched by pixels whose guard says a class beyond the two recorded ones could qualify.
-// One CTA per chunk of consecutive ECTA_TILE-pixel tiles (512 threads x 4 pixels; 256 x 4 measured 1.5 us slower).  Per tile: every thread decodes 4 pixels, sets one bit per
-// (pixel, class) candidate in a shared bit matrix, a popcount prefix over the 32 words of each class gives the ranks in
-// pixel order, candidates are staged in shared memory grouped by class and written out by whole warps in multiples of 8
-// elements (full 32-byte sectors, each written exactly once: a partially written sector costs an L2 fill from DRAM and
-// a scattered 4-byte store a whole LSU wavefront); the < 8 leftovers of each class are carried to the next tile.
-// Same slot layout (chunk-private runs), outputs and tie order as the streaming kernel.  Exits at once unless K1d
-// selected this path.
-// classes outside `skip` whose probability reaches their threshold, for one pixel whose unrecorded classes all have
-// p <= guard (the rare path of the record kernel; deliberately not inlined so that the common path carries neither its
+// One CTA per chunk of consecutive ECTA_TILE-pixel tiles (512 threads x 4 pixels).  Per tile: every thread decodes 4 pixels
+// and takes an arrival rank per candidate from a shared per-class counter (the order inside a segment is free: the sort
+// restores the canonical one), the candidates are staged in shared memory grouped by class, and a warp per class reserves
+// the tile's slice of the segment with one global atomic and writes it with contiguous stores.
+// `emit_scan_pixel`: classes outside `skip` whose probability reaches their threshold, for one pixel whose unrecorded
+// classes all have p <= guard (the rare path; deliberately not inlined so that the common path carries neither its
 // instructions nor its registers).  `order` lists the classes by ascending threshold: only the leading ones with
 // threshold <= guard can qualify, typically a single class.
 __device__ __noinline__ u32 emit_scan_pixel(const float* lp, long long plane, int C, float m, float sden, float guard,
@@ -1022,17 +1019,15 @@ __device__ __noinline__ u32 emit_scan_pixel(const float* lp, long long plane, in
     return more;
 }
 
-#define ECTA_CAP 4096                                     // staged candidates per pass over the classes of a tile
+#define ECTA_CAP 6144                                     // staged candidates per pass over the classes of a tile (>= 3 per pixel)
 struct EctaSmem {
-    u32 mask[B200SEG_MAX_CLASSES][ECTA_WORDS];            // bit (pixel in tile) set = candidate of the class
-    u32 wpre[B200SEG_MAX_CLASSES][ECTA_WORDS];            // exclusive popcount prefix over the words
-    u32 tot[B200SEG_MAX_CLASSES];                         // candidates of the class in this tile
-    u32 coff[B200SEG_MAX_CLASSES];                        // offset of the class in the stage (current pass)
-    u32 carry_cnt[B200SEG_MAX_CLASSES];                   // leftovers (< 8) waiting for the next tile
-    u32 carryK[B200SEG_MAX_CLASSES][8], carryV[B200SEG_MAX_CLASSES][8];
+    // counters of two tiles in turn: while a tile is staged and written out, the next tile's set is cleared
+    u32 cnt2[2][B200SEG_MAX_CLASSES];                     // recorded candidates of the class in this tile (arrival counter)
+    u32 cntx2[2][B200SEG_MAX_CLASSES];                    // candidates beyond the recorded ones (rare path), counted ...
+    u32 curx2[2][B200SEG_MAX_CLASSES];                    // ... and placed behind the recorded ones of their class
     float thr[B200SEG_MAX_CLASSES];
     unsigned char order[B200SEG_MAX_CLASSES];             // classes by ascending threshold
-    u32 wcoff[ECTA_TPB / 32][B200SEG_MAX_CLASSES];        // per-warp copy of the stage offsets (single-pass tiles)
+    u32 wcoff[ECTA_TPB / 32][B200SEG_MAX_CLASSES];        // per-warp copy of the stage offsets of the classes
     u32 stageK[ECTA_CAP], stageV[ECTA_CAP];
 };
 
@@ -1047,40 +1042,43 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
     const long long tpi = (p.HW + ECTA_TILE - 1) / ECTA_TILE;
     const long long tpg = p.per_image ? tpi : tpi * p.N;
     const long long total_chunks = (long long)p.groups * G.n_runs;
-    const int word = tid >> 3, shift = (tid & 7) * 4;     // this thread's 4 pixels: bits [shift, shift + 4) of `word`
     int cur_g = -1;
     float tmin = 0.f;
+    u32 par = 0;                                          // counter set of the current tile
+    if (tid < B200SEG_MAX_CLASSES) { S.cnt2[0][tid] = 0; S.cntx2[0][tid] = 0; S.curx2[0][tid] = 0; }
+    __syncthreads();
 
     for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
         const int g = (int)(chunk / G.n_runs);
         const long long r = chunk - (long long)g * G.n_runs;
         const long long gt0 = r * G.tiles_per_chunk;
         const long long gt1 = min(gt0 + (long long)G.tiles_per_chunk, tpg);
-        __syncthreads();                                   // previous chunk fully written out
         if (g != cur_g) {
+            __syncthreads();                               // previous tile done with the thresholds
             if (tid < B200SEG_MAX_CLASSES) {
                 S.thr[tid] = tid < CT ? p.seg_thr[(size_t)g * CT + tid] : THR_INACTIVE;
                 S.order[tid] = tid < CT ? p.seg_order[(size_t)g * CT + tid] : 0;
             }
             tmin = p.grp_tmin[g];
             cur_g = g;
+            __syncthreads();                               // thresholds visible
         }
-        if (tid < B200SEG_MAX_CLASSES) S.carry_cnt[tid] = 0;
-        for (int i = tid; i < B200SEG_MAX_CLASSES * ECTA_WORDS; i += ECTA_TPB) (&S.mask[0][0])[i] = 0;
-        __syncthreads();
-
         // (image, tile-in-image) of the chunk's first tile; advanced by increments (no 64-bit division per tile)
         int n = p.per_image ? g : (int)(gt0 / tpi);
         long long ti = p.per_image ? gt0 : gt0 - (long long)n * tpi;
         for (long long gt = gt0; gt < gt1; ++gt, ++ti) {
             if (!p.per_image && ti == tpi) { ti = 0; ++n; }
+            u32* cnt = S.cnt2[par];
+            u32* cntx = S.cntx2[par];
+            u32* curx = S.curx2[par];
             const long long q0 = ti * ECTA_TILE + (long long)tid * 4;
             const bool inb = q0 < p.HW;                    // plane % 4 == 0: a thread's 4 pixels are in or out together
             const size_t px0 = (size_t)n * p.HW + q0;
             // ---- decode: per pixel up to three recorded candidates (own class, c1, c2), rarely more ----------------------
             u32 kfg[4], kc1[4], kc2[4], acc[4], cls[4];      // cls = label8 | c1 << 8 | c2 << 16
+            unsigned short r0[4], r1[4], r2[4];              // arrival ranks of the three recorded candidates
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { kfg[j] = 0; kc1[j] = 0; kc2[j] = 0; acc[j] = 0; cls[j] = LAB8_FILTERED; }
+            for (int j = 0; j < 4; ++j) { kfg[j] = 0; kc1[j] = 0; kc2[j] = 0; acc[j] = 0; cls[j] = LAB8_FILTERED; r0[j] = r1[j] = r2[j] = 0; }
             u32 extra = 0;                                 // pixels (bits 0..3) with candidates beyond the recorded ones
             if (inb) {
                 const uint4 r4v = *reinterpret_cast<const uint4*>(p.rec4 + px0);
@@ -1093,7 +1091,7 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
                     const u32 l8 = r4[j] & 255u, c1 = (r4[j] >> 8) & 31u, c2 = (r4[j] >> 16) & 31u;
                     cls[j] = r4[j] & 0x00FFFFFFu;
                     const float p1 = __uint_as_float(rec[j].y), p2 = __uint_as_float(rec[j].z);
-                    kfg[j] = rec[j].x; kc1[j] = err_key(p1); kc2[j] = err_key(p2);
+                    kfg[j] = rec[j].x | KEY_FG; kc1[j] = err_key(p1); kc2[j] = err_key(p2);
                     if (l8 != LAB8_FILTERED) {
                         u32 a = 0;
                         if (l8 < (u32)CT && thr_active(S.thr[l8 & 31u])) a |= 1u << l8;
@@ -1120,36 +1118,24 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
                     cm4 = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
                 }
                 *reinterpret_cast<uint4*>(p.cmask + px0) = cm4;
-                // one shared-memory OR per class the thread's pixels touch
-                u32 uni = acc[0] | acc[1] | acc[2] | acc[3];
-                while (uni) {
-                    const int c = __ffs(uni) - 1;
-                    uni &= uni - 1;
-                    const u32 nib = ((acc[0] >> c) & 1u) | (((acc[1] >> c) & 1u) << 1) | (((acc[2] >> c) & 1u) << 2) |
-                                    (((acc[3] >> c) & 1u) << 3);
-                    atomicOr(&S.mask[c][word], nib << shift);
+                // ---- arrival rank of every candidate within its class ------------------------------------------------------------
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const u32 l8 = cls[j] & 255u, c1 = (cls[j] >> 8) & 31u, c2 = (cls[j] >> 16) & 31u;
+                    u32 a = acc[j];
+                    if (l8 < (u32)CT && ((a >> l8) & 1u)) { r0[j] = (unsigned short)atomicAdd(&cnt[l8], 1u); a &= ~(1u << l8); }
+                    if ((a >> c1) & 1u) { r1[j] = (unsigned short)atomicAdd(&cnt[c1], 1u); a &= ~(1u << c1); }
+                    if ((a >> c2) & 1u) { r2[j] = (unsigned short)atomicAdd(&cnt[c2], 1u); a &= ~(1u << c2); }
+                    if ((extra >> j) & 1u)
+                        while (a) { atomicAdd(&cntx[__ffs(a) - 1], 1u); a &= a - 1; }
                 }
             }
-            __syncthreads();
-            // ---- ranks: exclusive popcount prefix over the 32 words of every class --------------------------------------
-            for (int c = warp; c < CT; c += NW) {
-                constexpr int WPL = ECTA_WORDS / 32;      // words per lane (consecutive)
-                u32 cnt[WPL], sum = 0;
-#pragma unroll
-                for (int k = 0; k < WPL; ++k) { cnt[k] = __popc(S.mask[c][lane * WPL + k]); sum += cnt[k]; }
-                u32 v = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
-                u32 run = v - sum;
-#pragma unroll
-                for (int k = 0; k < WPL; ++k) { S.wpre[c][lane * WPL + k] = run; run += cnt[k]; }
-                if (lane == 31) S.tot[c] = v;
-            }
-            __syncthreads();
+            __syncthreads();                               // all arrivals counted (and the previous tile written out)
+            if (tid < B200SEG_MAX_CLASSES) { S.cnt2[par ^ 1][tid] = 0; S.cntx2[par ^ 1][tid] = 0; S.curx2[par ^ 1][tid] = 0; }
             // ---- stage offsets: every warp scans the class totals for itself (no extra CTA barrier) ---------------------------
             u32 total_all;
             {
-                const u32 tc = lane < CT ? S.tot[lane] : 0u;
+                const u32 tc = lane < CT ? cnt[lane] + cntx[lane] : 0u;
                 u32 v = tc;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(FULL_MASK, v, o); if (lane >= o) v += x; }
@@ -1158,6 +1144,7 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
                 __syncwarp();
             }
             // ---- passes over class ranges whose candidates fit the stage (one pass unless > ECTA_CAP candidates) ---------
+            const u32* coff = S.wcoff[warp];
             int lo = 0;
             while (lo < CT) {
                 int hi = CT;
@@ -1165,98 +1152,56 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
                 if (total_all > ECTA_CAP) {
                     hi = lo;
                     u32 sum = 0;
-                    while (hi < CT && sum + S.tot[hi] <= ECTA_CAP) { sum += S.tot[hi]; ++hi; }     // tot <= 1024: hi > lo
-                    base = S.wcoff[warp][lo];
+                    while (hi < CT && sum + cnt[hi] + cntx[hi] <= ECTA_CAP) { sum += cnt[hi] + cntx[hi]; ++hi; }   // a class <= 2048: hi > lo
+                    base = coff[lo];
                 }
-                const u32* coff = S.wcoff[warp];
                 if (inb) {
-                    const u32 below = (1u << shift) - 1u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const u32 l8 = cls[j] & 255u, c1 = (cls[j] >> 8) & 31u, c2 = (cls[j] >> 16) & 31u;
                         const u32 v0 = (u32)(px0 + j) << 1;
-                        const u32 bj = below | ((1u << j) - 1u) << shift;    // earlier pixels of the word
                         u32 a = acc[j];
                         if (l8 < (u32)CT && ((a >> l8) & 1u)) {
                             a &= ~(1u << l8);
-                            if ((int)l8 >= lo && (int)l8 < hi) {
-                                const u32 pos = coff[l8] - base + S.wpre[l8][word] + __popc(S.mask[l8][word] & bj);
-                                S.stageK[pos] = kfg[j] | KEY_FG; S.stageV[pos] = v0 | 1u;
-                            }
+                            if ((int)l8 >= lo && (int)l8 < hi) { const u32 pos = coff[l8] - base + r0[j]; S.stageK[pos] = kfg[j]; S.stageV[pos] = v0 | 1u; }
                         }
                         if ((a >> c1) & 1u) {
                             a &= ~(1u << c1);
-                            if ((int)c1 >= lo && (int)c1 < hi) {
-                                const u32 pos = coff[c1] - base + S.wpre[c1][word] + __popc(S.mask[c1][word] & bj);
-                                S.stageK[pos] = kc1[j]; S.stageV[pos] = v0;
-                            }
+                            if ((int)c1 >= lo && (int)c1 < hi) { const u32 pos = coff[c1] - base + r1[j]; S.stageK[pos] = kc1[j]; S.stageV[pos] = v0; }
                         }
                         if ((a >> c2) & 1u) {
                             a &= ~(1u << c2);
-                            if ((int)c2 >= lo && (int)c2 < hi) {
-                                const u32 pos = coff[c2] - base + S.wpre[c2][word] + __popc(S.mask[c2][word] & bj);
-                                S.stageK[pos] = kc2[j]; S.stageV[pos] = v0;
-                            }
+                            if ((int)c2 >= lo && (int)c2 < hi) { const u32 pos = coff[c2] - base + r2[j]; S.stageK[pos] = kc2[j]; S.stageV[pos] = v0; }
                         }
-                        if ((extra >> j) & 1u) {            // rare: classes found by the scan
+                        if ((extra >> j) & 1u) {            // rare: classes found by the scan go behind the recorded ones of their class
                             while (a) {
                                 const int c = __ffs(a) - 1;
                                 a &= a - 1;
                                 if (c < lo || c >= hi) continue;
                                 const float pr = sm_prob(__ldg(p.logits + ((size_t)n * CT + c) * p.HW + q0 + j),
                                                          p.pix_m[px0 + j], p.pix_s[px0 + j]);
-                                const u32 pos = coff[c] - base + S.wpre[c][word] + __popc(S.mask[c][word] & bj);
+                                const u32 pos = coff[c] - base + cnt[c] + atomicAdd(&curx[c], 1u);
                                 S.stageK[pos] = err_key(pr); S.stageV[pos] = v0;
                             }
                         }
                     }
                 }
                 __syncthreads();
-                // ---- write out: a warp per class, multiples of 8 elements = whole sectors; leftovers -> carry ----------------
+                // ---- write out: a warp per class reserves the tile's slice of the segment and copies it ---------------------------
                 for (int c = lo + warp; c < hi; c += NW) {
-                    const u32 cc = S.carry_cnt[c], nt = S.tot[c], total = cc + nt, w = total & ~7u;
-                    const u32 co = coff[c] - base;
-                    // this tile's slice of the segment: one atomic per class (multiples of 8: slices start on sector boundaries)
+                    const u32 nc = cnt[c] + cntx[c];
+                    if (nc == 0) continue;                 // (warp-uniform)
                     u32 gslot = 0;
-                    if (lane == 0 && w) gslot = atomicAdd(p.seg_count + (size_t)g * CT + c, w);
+                    if (lane == 0) gslot = atomicAdd(p.seg_count + (size_t)g * CT + c, nc);
                     gslot = __shfl_sync(FULL_MASK, gslot, 0);
                     const size_t cslot = ((size_t)g * CT + c) * (size_t)p.cap + gslot;
-                    u32* kd = p.keysA + cslot;
-                    u32* vd = p.valsA + cslot;
-                    for (u32 e = lane; e < w; e += 32) {
-                        const bool fromc = e < cc;
-                        kd[e] = fromc ? S.carryK[c][e] : S.stageK[co + e - cc];
-                        vd[e] = fromc ? S.carryV[c][e] : S.stageV[co + e - cc];
-                    }
-                    // leftovers (< 8): lanes 0..7 read their element first, then all of them write the new carry
-                    const u32 e = w + lane;
-                    u32 lk = 0, lv = 0;
-                    if (lane < 8 && e < total) {
-                        const bool fromc = e < cc;
-                        lk = fromc ? S.carryK[c][e] : S.stageK[co + e - cc];
-                        lv = fromc ? S.carryV[c][e] : S.stageV[co + e - cc];
-                    }
-                    __syncwarp();
-                    if (lane < 8 && e < total) { S.carryK[c][lane] = lk; S.carryV[c][lane] = lv; }
-                    if (lane == 0) S.carry_cnt[c] = total - w;
+                    const u32 co = coff[c] - base;
+                    for (u32 e = lane; e < nc; e += 32) { p.keysA[cslot + e] = S.stageK[co + e]; p.valsA[cslot + e] = S.stageV[co + e]; }
                 }
                 lo = hi;
-                if (lo >= CT)                               // last pass: the bit matrix is free, clear it for the next tile
-                    for (int i = tid; i < CT * ECTA_WORDS; i += ECTA_TPB) (&S.mask[0][0])[i] = 0;
-                __syncthreads();
+                if (lo < CT) __syncthreads();               // next pass restages
             }
-        }
-        // ---- chunk end: flush the carries, publish the run lengths --------------------------------------------------------
-        for (int c = warp; c < CT; c += NW) {
-            const u32 cc = S.carry_cnt[c];
-            u32 gslot = 0;
-            if (lane == 0 && cc) gslot = atomicAdd(p.seg_count + (size_t)g * CT + c, cc);
-            gslot = __shfl_sync(FULL_MASK, gslot, 0);
-            if (lane < cc) {
-                const size_t slot = ((size_t)g * CT + c) * (size_t)p.cap + gslot + lane;
-                p.keysA[slot] = S.carryK[c][lane];
-                p.valsA[slot] = S.carryV[c][lane];
-            }
+            par ^= 1;
         }
     }
 }
