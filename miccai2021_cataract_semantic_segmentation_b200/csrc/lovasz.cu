@@ -23,6 +23,7 @@
 #include "hybrid.cuh"
 #include "pipe.cuh"
 #include <cstdlib>
+#include <cuda.h>
 
 #define STATS_TPB 128
 #define EMIT_TPB 256
@@ -549,6 +550,228 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
             if (s_cm[i]) atomicAdd(p.cm + i, (unsigned long long)s_cm[i]);
         if (tid == 0 && s_oob) atomicOr(p.status, STATUS_LABEL_OOB);
     }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K1 (TMA variant, stats_variant = 7): the same kernel fed by the tensor-memory accelerator instead of per-warp cp.async rings.
+// The logits are described to the TMA unit as a 3-D tensor {plane pixel, class, image}; ONE cp.async.bulk.tensor.3d request
+// brings the box {TMA_BOX pixels x C classes x 1 image} (12.8 KB at C = 25) into a stage, a second bulk copy the tile's labels;
+// both complete on the stage's mbarrier.  One elected thread issues, all 4 warps wait on the barrier and take 32 pixels each.
+// Same outputs, bit for bit, as stats_kernel_async (tests/test_gpu_paths.py); kept as the measured TMA-vs-LDGSTS comparison
+// (profiles/r02_tma_experiment.txt).
+// --------------------------------------------------------------------------------------------------------------
+#define TMA_BOX 128
+#define TMA_TPB 128
+#define TMA_STAGES 2
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(u32 dst, const CUtensorMap* map, u32 bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(u32 dst, const void* src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int CT, typename LT>
+__global__ void __launch_bounds__(TMA_TPB) stats_kernel_tma(LovaszParams p, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int NW = TMA_TPB / 32;
+    constexpr int Z_BYTES = CT * TMA_BOX * 4, LAB_BYTES = TMA_BOX * (int)sizeof(LT);
+    constexpr int STAGE_BYTES = (Z_BYTES + LAB_BYTES + 127) / 128 * 128;
+    extern __shared__ __align__(128) unsigned char tma_smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[TMA_STAGES];
+    __shared__ u32 s_cm[B200SEG_MAX_CLASSES * B200SEG_MAX_CLASSES];
+    __shared__ u32 s_fg[NW][B200SEG_MAX_CLASSES], s_key[NW][B200SEG_MAX_CLASSES];
+    __shared__ u32 s_valid, s_oob;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < CT * CT; i += TMA_TPB) s_cm[i] = 0;
+    s_fg[warp][lane] = 0; s_key[warp][lane] = 0;
+    if (tid == 0) {
+        s_valid = 0; s_oob = 0;
+        for (int s2 = 0; s2 < TMA_STAGES; ++s2) mbar_init(smem_u32(&s_bar[s2]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const u32 bpi = (u32)((p.HW + TMA_BOX - 1) / TMA_BOX);             // boxes per image
+    const u32 nbox = bpi * (u32)p.N;
+    const u32 my_n = blockIdx.x < nbox ? (nbox - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;     // boxes of this CTA (interleaved)
+    auto issue = [&](u32 it) {                             // (thread 0) request box `it` of this CTA into stage it % TMA_STAGES
+        const u32 t = blockIdx.x + it * gridDim.x;
+        const u32 n = t / bpi, b = t - n * bpi;
+        const u32 st = it % TMA_STAGES;
+        const u32 dst = smem_u32(tma_smem_raw + (size_t)st * STAGE_BYTES), bar = smem_u32(&s_bar[st]);
+        const long long q0 = (long long)b * TMA_BOX;
+        const u32 npx = (u32)min((long long)TMA_BOX, p.HW - q0);
+        const u32 lab_bytes = npx * (u32)sizeof(LT);       // (plane % 16 == 0 and 16-byte aligned labels: a multiple of 16)
+        mbar_expect_tx(bar, (u32)Z_BYTES + lab_bytes);     // the box is always written in full (out-of-range pixels: zeros)
+        tma_load_3d(dst, &tmap, bar, (int)q0, 0, (int)n);
+        bulk_load_1d(dst + Z_BYTES, (const unsigned char*)p.labels + ((size_t)n * p.HW + q0) * sizeof(LT), lab_bytes, bar);
+    };
+    if (tid == 0)
+        for (u32 it = 0; it < TMA_STAGES - 1 && it < my_n; ++it) issue(it);
+
+    auto flush_group = [&](int g, u32 nvalid) {           // warp-private counters -> global (per-image mode)
+        __syncwarp();
+        if (lane < CT) {
+            const size_t seg = (size_t)g * CT + lane;
+            const u32 f = s_fg[warp][lane];
+            if (f) { atomicAdd(p.seg_fg + seg, f); atomicMax(p.seg_maxkey + seg, s_key[warp][lane]); }
+            s_fg[warp][lane] = 0; s_key[warp][lane] = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(FULL_MASK, nvalid, o);
+        if (lane == 0 && nvalid) atomicAdd(p.grp_valid + g, nvalid);
+        __syncwarp();
+    };
+    int cur_g = -1;
+    u32 nvalid = 0, oob = 0, ce_n = 0, ce_oob = 0;
+    float ce_acc = 0.f;
+    ExpConsts ek;
+    ek.load();
+    for (u32 it = 0; it < my_n; ++it) {
+        if (tid == 0 && it + TMA_STAGES - 1 < my_n) issue(it + TMA_STAGES - 1);     // (its stage was released by the barrier below)
+        const u32 st = it % TMA_STAGES;
+        mbar_wait(smem_u32(&s_bar[st]), (it / TMA_STAGES) & 1u);
+        const u32 t = blockIdx.x + it * gridDim.x;
+        const int n = (int)(t / bpi);
+        const long long q = (long long)(t - (u32)n * bpi) * TMA_BOX + warp * 32 + lane;
+        const int g = p.per_image ? n : 0;
+        if (g != cur_g) {
+            if (cur_g >= 0) { flush_group(cur_g, nvalid); nvalid = 0; }
+            cur_g = g;
+        }
+        const unsigned char* sb = tma_smem_raw + (size_t)st * STAGE_BYTES;
+        const float (*T)[TMA_BOX] = reinterpret_cast<const float (*)[TMA_BOX]>(sb);
+        const int col = warp * 32 + lane;
+        if (q < p.HW) {
+            const size_t px = (size_t)n * p.HW + q;
+            int lab;
+            if constexpr (sizeof(LT) == 8) lab = sat_i32(reinterpret_cast<const long long*>(sb + Z_BYTES)[col]);
+            else lab = (int)reinterpret_cast<const LT*>(sb + Z_BYTES)[col];
+            float z[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) z[c] = T[c][col];
+            float m = z[0];
+#pragma unroll
+            for (int c = 1; c < CT; ++c) m = fmaxf(m, z[c]);
+            float s = 0.f;
+            int b1 = -1, b2 = -1, b3 = -1;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const float e = sm_exp_k(z[c], m, ek);
+                s = __fadd_rn(s, e);
+                int v = (int)__byte_perm(__float_as_uint(e), (u32)c, 0x3214);
+                v = (c == lab) ? -1 : v;
+                const int t1v = min(b1, v); b1 = max(b1, v);
+                const int t2v = min(b2, t1v); b2 = max(b2, t1v);
+                b3 = max(b3, t2v);
+            }
+            p.pix_m[px] = m; p.pix_s[px] = s;
+            const u32 l8 = lab8_encode(lab, CT, p.has_filter, p.filter);
+            p.lab8[px] = (unsigned char)l8;
+            u32 kfg = 0;
+            if (l8 != LAB8_FILTERED) {
+                ++nvalid;
+                if (l8 < (u32)CT) {
+                    const float pr = sm_prob(T[l8][col], m, s);
+                    kfg = err_key(__fsub_rn(1.0f, pr));
+                    atomicAdd(&s_fg[warp][l8], 1u);
+                    atomicMax(&s_key[warp][l8], kfg);
+                }
+            }
+            {
+                const int c1 = b1 & 31, c2 = b2 & 31;
+                const float p1 = sm_prob(T[c1][col], m, s), p2 = sm_prob(T[c2][col], m, s);
+                const float p3 = __fdiv_ru(__uint_as_float((u32)b3 | 255u), s);
+                p.rec16[px] = make_uint4(kfg, __float_as_uint(p1), __float_as_uint(p2), __float_as_uint(p3));
+                p.rec4[px] = l8 | ((u32)c1 << 8) | ((u32)c2 << 16);
+            }
+            if (p.cm && !(p.has_drop && lab == p.drop)) {
+                if ((unsigned)lab < (unsigned)CT) {
+                    int arg = 0;
+#pragma unroll
+                    for (int c = CT - 1; c >= 0; --c) arg = (z[c] == m) ? c : arg;
+                    if (s != s || m != m) {
+                        float best = z[0];
+                        arg = 0;
+#pragma unroll
+                        for (int c = 1; c < CT; ++c) argmax_step(z[c], c, best, arg);
+                    }
+                    atomicAdd(&s_cm[arg * CT + lab], 1u);
+                } else oob = 1;
+            }
+            if (p.ce_enabled && !(p.has_ce_ignore && lab == p.ce_ignore)) {
+                if ((unsigned)lab < (unsigned)CT) { ce_acc += (m + logf(s)) - T[lab][col]; ++ce_n; }
+                else ce_oob = 1;
+            }
+        }
+        __syncthreads();                                   // the stage may be refilled
+    }
+    if (p.ce_enabled) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ce_acc += __shfl_xor_sync(FULL_MASK, ce_acc, o); ce_n += __shfl_xor_sync(FULL_MASK, ce_n, o); }
+        if (lane == 0 && ce_n) { atomicAdd(p.ce_sum, (double)ce_acc); atomicAdd(p.ce_cnt, ce_n); }
+        if (__any_sync(FULL_MASK, ce_oob) && lane == 0 && p.status) atomicOr(p.status, STATUS_LABEL_OOB);
+    }
+    if (cur_g >= 0 && p.per_image) { flush_group(cur_g, nvalid); nvalid = 0; }
+    if (oob) s_oob = 1;
+    if (!p.per_image) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(FULL_MASK, nvalid, o);
+        if (lane == 0 && nvalid) atomicAdd(&s_valid, nvalid);
+    }
+    __syncthreads();
+    if (!p.per_image) {
+        if (tid < CT) {
+            u32 f = 0, k = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { f += s_fg[w][tid]; k = max(k, s_key[w][tid]); }
+            if (f) { atomicAdd(p.seg_fg + tid, f); atomicMax(p.seg_maxkey + tid, k); }
+        }
+        if (tid == 0 && s_valid) atomicAdd(p.grp_valid, s_valid);
+    }
+    if (p.cm) {
+        for (int i = tid; i < CT * CT; i += TMA_TPB)
+            if (s_cm[i]) atomicAdd(p.cm + i, (unsigned long long)s_cm[i]);
+        if (tid == 0 && s_oob) atomicOr(p.status, STATUS_LABEL_OOB);
+    }
+}
+
+// tensor map of the logits for stats_kernel_tma: {plane pixel, class, image}, box {TMA_BOX, C, 1}
+static int make_logits_tensor_map(CUtensorMap* map, const float* logits, int n, int c, long long hw) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { b200seg_set_error("cuTensorMapEncodeTiled is not available"); return B200SEG_E_UNSUPPORTED; }
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)c, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)hw * 4, (cuuint64_t)hw * c * 4};
+    const cuuint32_t box[3] = {TMA_BOX, (cuuint32_t)c, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)logits, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b200seg_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return B200SEG_E_UNSUPPORTED; }
+    return 0;
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -2210,6 +2433,25 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
         else if (c == 17) LAUNCH_STATS_ASYNC(17, TT, SS)               \
         else LAUNCH_STATS_ASYNC(25, TT, SS)                            \
     }
+        if (stats_variant == 7) {                          // the TMA-fed variant (see stats_kernel_tma)
+            CUtensorMap tmap;
+            if (int rc = make_logits_tensor_map(&tmap, logits, n, c, hw)) return rc;
+#define LAUNCH_STATS_TMA(CC)                                                                                     \
+    {                                                                                                           \
+        const size_t stage = ((size_t)CC * TMA_BOX * 4 + TMA_BOX * sizeof(LT) + 127) / 128 * 128;               \
+        const size_t smem = stage * TMA_STAGES + 128;                                                           \
+        CUDA_TRY(cudaFuncSetAttribute(stats_kernel_tma<CC, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int per_sm = (int)((224 * 1024) / (smem + 8 * 1024));                                                   \
+        if (per_sm < 1) per_sm = 1;                                                                             \
+        stats_kernel_tma<CC, LT><<<sms * per_sm, TMA_TPB, smem, st>>>(p, tmap);                                 \
+    }
+            DISPATCH_LABEL(label_dtype, {
+                if (c == 8) LAUNCH_STATS_TMA(8)
+                else if (c == 17) LAUNCH_STATS_TMA(17)
+                else LAUNCH_STATS_TMA(25)
+            });
+#undef LAUNCH_STATS_TMA
+        } else
         DISPATCH_LABEL(label_dtype, {
             switch (stats_variant) {
                 // measured (C=25, 8x540x960, in the stream): <384,2> 149 us, <256,2> 152, <512,2> 153, <128,2> 161, <128,3> 169

@@ -23,6 +23,7 @@ VARIANTS = [
     ("stats_128x4", dict(stats_variant=3)),
     ("stats_128x3", dict(stats_variant=5)),
     ("stats_512x2", dict(stats_variant=6)),
+    ("stats_tma", dict(stats_variant=7)),
     ("contiguous_tiles", dict(interleave=0)),
     ("rank_ballots", dict(sort_match=0)),
     ("rank_match", dict(sort_match=1)),
