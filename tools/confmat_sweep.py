@@ -12,9 +12,22 @@ if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 c, h, w = 25, 540, 960
 g = torch.Generator(device="cuda").manual_seed(0)
-for n in (1, 8, 64):
+# label / prediction statistics: uniform (every lane of a warp hits another bin), blocky (16 x 16 blocks of one label and a
+# confident prediction of it: whole warps on ONE bin -- the worst case for the shared-memory atomics), one-class (everything
+# on a single bin, the CaDIS cornea-dominated frames taken to the limit)
+for dist in ("uniform", "blocky", "one-class"):
+  print(f"--- labels: {dist}")
+  for n in (1, 8, 64):
     x = torch.randn((n, c, h, w), generator=g, device="cuda")
     y = torch.randint(0, c + 1, (n, h, w), generator=g, device="cuda", dtype=torch.int32)
+    if dist == "blocky":
+        coarse = torch.randint(0, c, (n, (h + 15) // 16, (w + 15) // 16), generator=g, device="cuda")
+        y = coarse.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :h, :w].contiguous().int()
+        for i in range(n):
+            x[i] += 6.0 * torch.nn.functional.one_hot(y[i].long(), c).permute(2, 0, 1).float()
+    elif dist == "one-class":
+        y = torch.full((n, h, w), 3, device="cuda", dtype=torch.int32)
+        x[:, 3] += 8.0
     meter = b200.SegmentationMeter(3, c)
     reps = 200 if n == 1 else (50 if n == 8 else 10)
     for _ in range(5):
