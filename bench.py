@@ -46,6 +46,7 @@ STAGES_HYBRID = ["stats(+fused confmat, records)", "finalize+decide", "emit", "s
 STAGES_LSD = ["stats(+fused confmat, records)", "finalize+decide", "emit", "sort_prepare", "sort_pass0", "sort_pass1",
               "sort_pass2", "jaccard+loss", None, "backward"]
 SORT_PATH = int(os.environ.get("B200SEG_SORT_PATH", "0"))
+NO_ALLREDUCE = os.environ.get("B200SEG_BENCH_NO_ALLREDUCE", "0") == "1"    # diagnosis only: N independent replicas
 STAGES = STAGES_LSD if SORT_PATH == 1 else STAGES_HYBRID
 N_EV = len(STAGES) + 1
 # hybrid: stats, finalize+decide, emit (record path) + emit (streaming path; one of the two exits at once), sort prepare,
@@ -382,7 +383,8 @@ def main():
         meter.reset()
         xr.grad = None
         loss = loss_mod(xr, yy)
-        pending = meter.all_reduce(async_op=True) if world > 1 else None    # the matrix is complete after the forward pass
+        # the matrix is complete after the first kernel of the forward pass: the collective waits for that event only
+        pending = meter.all_reduce(async_op=True) if (world > 1 and not NO_ALLREDUCE) else None
         loss.backward()
         if pending is not None:
             pending.wait()                                                   # the 5 KB all-reduce ran under the backward kernel
@@ -411,7 +413,11 @@ def main():
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    ms_ranks = [float(ms) / args.steps]
     if world > 1:
+        allms = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(allms, ms)
+        ms_ranks = [float(v) / args.steps for v in allms]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / args.steps
     value = px_rank * world / (ms_step * 1e-3) / 1e6
@@ -535,7 +541,10 @@ def main():
                           "unit": "GB/s", "frac": step_gbs / hbm, "per_gpu_mpx_s": value / world,
                           "peak_source": peak_src},
         "stage_ms": stage_ms, "loss": loss_value, "miou": float(summary[0]),
+        "ms_per_step_ranks": ms_ranks,
     }
+    if NO_ALLREDUCE:
+        out["diagnosis"] = "B200SEG_BENCH_NO_ALLREDUCE=1: independent replicas, no collective (not a valid bench line)"
     out["sort_path"] = "lsd" if SORT_PATH == 1 else "hybrid"
     if world == 1 and not args.no_configs:
         del xr, x, y

@@ -192,12 +192,24 @@ int b200seg_ohem_ce_backward(const float* logits, const void* labels, int32_t la
  * boundary i, so a caller can time each kernel group with cudaEventElapsedTime without a profiler.
  *   0 forward entry        1 stats kernel done          2 threshold finalisation done
  *   3 candidate emission (+ run scan) done                4 sort plan + tile descriptors done
- *   5 / 6 / 7 sort pass 0 / 1 / 2 (count + scatter) done (7 includes the per-tile foreground count)
- *   8 Jaccard + loss done  9 backward entry            10 backward kernel done
+ *   5 / 6 / 7 hybrid path: bucket histogram / partition / local rank + Jaccard + loss done
+ *             (LSD path, B200SEG_SORT_PATH=1: key passes 0 / 1 / 2 done, 7 includes the per-tile foreground count)
+ *   8 hybrid path: overflow fallback done (LSD path: Jaccard + loss done)  9 backward entry            10 backward kernel done
  * Pass NULL / 0 to clear.  Entries that are NULL are skipped.
  * ------------------------------------------------------------------------------------------------ */
 #define B200SEG_N_STAGES 11
 int b200seg_set_stage_events(void* const* events, int32_t n_events);
+
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel hook: an event (cudaEvent_t, owned by the caller) that b200seg_lovasz_forward /
+ * b200seg_lovasz_ce_forward record on their stream right after the first kernel, i.e. as soon as the
+ * fused confusion matrix and the label-range flag of the call are complete.  The host side makes its
+ * all-reduce of the matrix wait for THIS event instead of for the whole forward pass, so the collective
+ * runs under the emission / sort kernels (which leave room on the SMs) rather than queueing behind the
+ * backward kernel (which fills them).  Replaces nothing in the reference (single-GPU there,
+ * managers/BaseManager.py:83-86).  NULL clears.  Process-wide, like the stage events.
+ * ------------------------------------------------------------------------------------------------ */
+int b200seg_set_confmat_event(void* event);
 
 /* ------------------------------------------------------------------------------------------------
  * Test hook: the segmented stable radix sort used inside b200seg_lovasz_forward, exposed so tests can

@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200seg_ohem_ce_forward": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _c.c_float, _i64, _vp, _sz, _vp, _vp, _vp]),
     "b200seg_ohem_ce_backward": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
     "b200seg_set_stage_events": (_c.c_int, [_c.POINTER(_vp), _i32]),
+    "b200seg_set_confmat_event": (_c.c_int, [_vp]),
     "b200seg_set_tuning": (_c.c_int, [_c.c_char_p, _i32]),
     "b200seg_debug_exp_mismatches": (_c.c_int, [_vp, _i32, _vp, _vp]),
     "b200seg_debug_layout": (_c.c_int, [_i32, _i32, _i64, _i32, _c.POINTER(_sz), _i32]),

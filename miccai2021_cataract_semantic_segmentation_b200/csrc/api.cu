@@ -71,3 +71,13 @@ extern "C" int b200seg_set_stage_events(void* const* events, int32_t n_events) {
 void b200seg_stage(int i, cudaStream_t st) {
     if (i < g_n_stage_events && g_stage_events[i]) cudaEventRecord(g_stage_events[i], st);
 }
+
+// ---- confusion-matrix-ready event (data-parallel hook) ---------------------------------------------------------------------
+static cudaEvent_t g_cm_event = nullptr;
+extern "C" int b200seg_set_confmat_event(void* event) {
+    g_cm_event = (cudaEvent_t)event;
+    return 0;
+}
+void b200seg_cm_ready(cudaStream_t st) {
+    if (g_cm_event) cudaEventRecord(g_cm_event, st);
+}

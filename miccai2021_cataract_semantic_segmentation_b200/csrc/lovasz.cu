@@ -2476,6 +2476,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
         DISPATCH_LABEL(label_dtype, stats_kernel_generic<LT><<<sms * 8, STATS_TPB, 0, st>>>(p));
     }
     LAUNCH_CHECK("stats_kernel");
+    if (cm) b200seg_cm_ready(st);                          // the fused confusion matrix and the status word are complete
     b200seg_stage(1, st);
     if (p.keep_absent) {
         DISPATCH_LABEL(label_dtype, absent_max_kernel<LT><<<dim3(p.n_seg, 32), 256, 0, st>>>(p));

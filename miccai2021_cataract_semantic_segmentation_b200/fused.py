@@ -35,10 +35,13 @@ class SegmentationMeter:
         self.status = self._buf[cc:].view(torch.int32)[:1]
         self._reduced = False
         self.drop_label = confusion_drop_label(self.num_classes, no_ignore_class)
+        self.cm_ready = None                                   # event recorded when the fused matrix of the last forward is complete
+        self._side = None
 
     def reset(self):
         self._buf.zero_()
         self._reduced = False
+        self.cm_ready = None
 
     def update(self, prediction: torch.Tensor, target: torch.Tensor):
         accumulate_confusion_matrix(prediction, target, self.cm, self.status, self.drop_label)
@@ -49,6 +52,17 @@ class SegmentationMeter:
         5 KB collective hides under the backward kernel."""
         from .dist import all_reduce_packed
         self._reduced = True
+        if async_op and self.cm_ready is not None and self.cm.is_cuda:
+            # the matrix is complete after the FIRST kernel of the fused forward (event recorded by the library): let the
+            # collective wait for that event only, on a side stream, so it runs under the emission / sort kernels instead
+            # of queueing behind whatever the current stream has been given since (the backward kernel fills every SM)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.cm.device)
+            self._side.wait_event(self.cm_ready)
+            with torch.cuda.stream(self._side):
+                pending = all_reduce_packed(self._buf, group=group, async_op=True)
+            self._buf.record_stream(self._side)
+            return pending
         pending = all_reduce_packed(self._buf, group=group, async_op=async_op)
         return pending if async_op else self.cm
 
@@ -78,14 +92,27 @@ class LovaszSoftmaxWithMetrics(nn.Module):
         self.classes_to_ignore = config.get('classes_to_ignore', None)
         self.classes_to_consider = config.get('classes_to_consider', _PRESENT)
         self.meter = meter
+        self._event = None
 
     def forward(self, prediction: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         if self.meter is None:
             self.meter = SegmentationMeter(self.experiment, prediction.shape[1], prediction.device)
         keep_absent, mask = _resolve_classes(self.classes_to_consider, prediction.shape[1])
-        return lovasz_softmax(prediction, target, self.per_image, self.classes_to_ignore, keep_absent, mask,
-                              confusion=self.meter.cm, confusion_drop_label=self.meter.drop_label,
-                              status=self.meter.status)
+        lib = _native.load()
+        if prediction.is_cuda:
+            if self._event is None:
+                self._event = torch.cuda.Event()
+                self._event.record(torch.cuda.current_stream(prediction.device))      # creates the underlying cudaEvent_t
+            _native.check(lib.b200seg_set_confmat_event(self._event.cuda_event), "b200seg_set_confmat_event")
+        try:
+            loss = lovasz_softmax(prediction, target, self.per_image, self.classes_to_ignore, keep_absent, mask,
+                                  confusion=self.meter.cm, confusion_drop_label=self.meter.drop_label,
+                                  status=self.meter.status)
+        finally:
+            if prediction.is_cuda:
+                lib.b200seg_set_confmat_event(None)
+        self.meter.cm_ready = self._event
+        return loss
 
 
 def ce_ignore_index(experiment: int) -> int:
