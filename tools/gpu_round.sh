@@ -16,6 +16,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
   --log-file $OUT/${TAG}_launches.csv python tools/prof_step.py > $OUT/${TAG}_launch.log 2>&1
 python tools/launch_times.py $OUT/${TAG}_launches.csv | grep -v "at::" 
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k regex:'stats_kernel|emit_kernel|sort_count|sort_scatter|jaccard|backward_kernel' \
+  -k regex:'stats_kernel|finalize_decide|emit_kernel|sort_prepare|hyb_|sort_fallback|backward_kernel|metrics_kernel' \
   -o $OUT/${TAG}_full -f python tools/prof_step.py > $OUT/${TAG}_full.log 2>&1
 python tools/ncu_summary.py $OUT/${TAG}_full.ncu-rep
