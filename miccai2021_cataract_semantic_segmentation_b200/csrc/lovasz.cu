@@ -7,12 +7,16 @@
 //                 cross-entropy sum
 //   K1c absent    (keep_absent only) max_i p_c(i) for considered classes without foreground
 //   K1b finalize  thresholds, key widths, class weights 1/n_present(/n_images), class order; chooses the emission path
-//   K2 emit       every (pixel, class) with error >= threshold becomes a candidate (key = 0x3F800000 - bits(error),
-//                 value = pixel<<1 | fg), written in pixel order per (chunk, class) so a stable sort gives canonical tie order;
-//                 from the records (CTA kernel, no logits) or, for confident logits, from a second pass over the logits
-//   K3..K4 sort   segmented stable LSD radix sort (sort.cuh)
-//   K5 jaccard    scan of fg flags in sorted order -> Jaccard gradient, loss partials, per-candidate g; the last CTA
-//                 takes the mean over present classes (sequential fp32, class order) and over images
+//   K2 emit       every (pixel, class) with error >= threshold becomes a candidate (key = 0x3F800000 - bits(error) | fg << 31,
+//                 value = pixel<<1 | fg); segments are written compactly, in no particular order (tiles reserve their slices
+//                 with atomics); from the records (CTA kernel, no logits) or, for confident logits, from a second pass over
+//                 the logits
+//   K3h/K4h       hybrid sort (hybrid.cuh + hyb_local_kernel below): bucket histogram, ONE partition pass by the top key bits,
+//                 then a local kernel that ranks whole buckets in shared memory in the canonical (key, pixel) order and goes
+//                 straight to the Jaccard gradient, loss partials and per-candidate g; the CTA that finishes last takes the
+//                 mean over present classes (sequential fp32, class order) and over images
+//   K4f fallback  segments whose buckets did not fit shared memory: stable LSD radix sort (sort.cuh) + Jaccard kernel, fused
+//                 into one cooperative launch; exits at once otherwise.  (sort_path = 1 runs that path for everything.)
 //   K6 backward   re-read logits: dz_k = go * p_k (g_k - sum_j g_j p_j) (+ the cross-entropy gradient), sparse g per pixel
 //
 // Exactness notes: candidates are a superset of every element with non-zero Jaccard gradient (SURVEY.md §7.3,
@@ -90,9 +94,8 @@ struct LovaszLayout {
     SortScratch sort;
 };
 
-// Emission geometry for one pixel-vector width: tiles of EMIT_TPB*vec pixels never straddle images; a chunk is
-// `tpc` consecutive tiles of one group and owns run_stride = tpc * tile_px candidate slots per class.
-struct EmitGeom { long long tile_px, tpi, tpg, tpc, n_runs, run_stride, src_cap; };
+// Emission work split for one tile size: tiles never straddle images; a chunk is `tpc` consecutive tiles of one group.
+struct EmitGeom { long long tile_px, tpi, tpg, tpc, n_runs; };
 #define EMIT_WARP_TILE 32            // pixels per warp tile of the pipelined emission kernel
 static EmitGeom emit_geom(int N, long long HW, int per_image, long long tile_px) {
     EmitGeom G;
@@ -107,8 +110,6 @@ static EmitGeom emit_geom(int N, long long HW, int per_image, long long tile_px)
     if (G.tpc < 1) G.tpc = 1;
     G.n_runs = (G.tpg + G.tpc - 1) / G.tpc;
     if (G.n_runs < 1) G.n_runs = 1;
-    G.run_stride = G.tpc * G.tile_px;
-    G.src_cap = G.n_runs * G.run_stride;
     return G;
 }
 
@@ -1140,7 +1141,6 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
         emit_cursor_next(pre, tpc, n_runs, wtpi, p.per_image);
         prefetch(pre, it + 1 < ntile, stage ^ 1);
         const int g = cur.g, n = cur.n;
-        const u32 r = cur.r, k = cur.k;
         const bool exists = cur.gt < tpg;
         if (g != cur_g) {
             __syncwarp();
@@ -2110,8 +2110,20 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
         if (lab >= 0 && !thr_active(s_thr[warp][lab])) lab = -1;   // class not summed: no own-class term
         // dot = sum_j g_j p_j over the pixel's candidates (background candidates ascending, then the own class)
         float d = 0.f, pk1 = 0.f, pk2 = 0.f, g1 = 0.f, g2 = 0.f;
+        // candidates beyond the two the ring prefetched (trained-like logits: ~7 per pixel): their gradients are requested
+        // together, so the pixel pays one round trip instead of one per candidate
+        constexpr int NX = 6;
+        float gx[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) gx[j] = 0.f;
         if (cmask_cur) {
             g1 = C.g1[lane]; g2 = C.g2[lane];
+            u32 rest = cmask_cur & (cmask_cur - 1);
+            rest &= rest - 1;                              // without the first two
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                if (rest) { gx[j] = gb[(size_t)(__ffs(rest) - 1) * plane]; rest &= rest - 1; }
+            }
             u32 mm = cmask_cur;
             int i = 0;
             while (mm) {
@@ -2119,7 +2131,12 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
                 mm &= mm - 1;
                 const float pr = sm_prob(T[c][lane], m, s);
                 float gk;
-                if (i == 0) { gk = g1; pk1 = pr; } else if (i == 1) { gk = g2; pk2 = pr; } else gk = gb[(size_t)c * plane];
+                if (i == 0) { gk = g1; pk1 = pr; } else if (i == 1) { gk = g2; pk2 = pr; }
+                else if (i < 2 + NX) {
+                    gk = gx[0];
+#pragma unroll
+                    for (int j = 1; j < NX; ++j) gk = (i == 2 + j) ? gx[j] : gk;
+                } else gk = gb[(size_t)c * plane];
                 d += gk * pr;
                 ++i;
             }
@@ -2147,7 +2164,14 @@ __global__ void __launch_bounds__(TPB) backward_kernel_async(LovaszParams p, con
                 mm &= mm - 1;
                 float gk, pk;
                 if (i == 0) { gk = g1; pk = pk1; } else if (i == 1) { gk = g2; pk = pk2; }
-                else { gk = gb[(size_t)c * plane]; pk = sm_prob(T[c][lane], m, s); }
+                else {
+                    pk = sm_prob(T[c][lane], m, s);
+                    if (i < 2 + NX) {
+                        gk = gx[0];
+#pragma unroll
+                        for (int j = 1; j < NX; ++j) gk = (i == 2 + j) ? gx[j] : gk;
+                    } else gk = gb[(size_t)c * plane];
+                }
                 dp[(size_t)c * plane] = gsc * pk * (gk - d) + gcp * pk;
                 ++i;
             }
@@ -2310,7 +2334,7 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
     p.ce_enabled = 0; p.has_ce_ignore = 0; p.ce_ignore = 0; p.ce_out = nullptr;
     p.ce_sum = reinterpret_cast<double*>(p.ctrl + CTRL_CE_SUM); p.ce_cnt = p.ctrl + CTRL_CE_CNT;
     p.ce_inv_n = reinterpret_cast<float*>(p.ctrl + CTRL_CE_INV_N);
-    p.geo_stream = EmitGeomDev{0, 0, 0, 0}; p.geo_rec = EmitGeomDev{0, 0, 0, 0};
+    p.geo_stream = EmitGeomDev{0, 0}; p.geo_rec = EmitGeomDev{0, 0};
     p.keysA = (u32*)(ws + L.keysA); p.valsA = (u32*)(ws + L.valsA);
     p.keysB = (u32*)(ws + L.keysB); p.valsB = (u32*)(ws + L.valsB);
     p.gbg = (float*)(ws + L.gbg);
@@ -2486,8 +2510,8 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
     const bool pipe_ok = v4 && known_c;
     const EmitGeom Gs = emit_geom(n, hw, per_image, pipe_ok ? EMIT_WARP_TILE : (long long)EMIT_TPB * (v4 ? 4 : 1));
     const EmitGeom Gr = emit_geom(n, hw, per_image, ECTA_TILE);
-    p.geo_stream = EmitGeomDev{(int)Gs.n_runs, (int)Gs.tpc, Gs.run_stride, Gs.src_cap};
-    p.geo_rec = EmitGeomDev{(int)Gr.n_runs, (int)Gr.tpc, Gr.run_stride, Gr.src_cap};
+    p.geo_stream = EmitGeomDev{(int)Gs.n_runs, (int)Gs.tpc};
+    p.geo_rec = EmitGeomDev{(int)Gr.n_runs, (int)Gr.tpc};
     finalize_decide_kernel<<<DECIDE_BLOCKS, DECIDE_TPB, 0, st>>>(p);
     LAUNCH_CHECK("finalize_decide_kernel");
     b200seg_stage(2, st);
@@ -2536,7 +2560,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
     }
     b200seg_stage(3, st);
 
-    // sort: holey source in A (gathered through the run prefix), ping-pong B -> A -> B
+    // sort: compact, unordered emission output in A; hybrid path A -> B (buckets); LSD path ping-pong, result in B
     SortArgs a;
     char* ss = ws + L.sort_scratch;
     a.keys[0] = p.keysA; a.vals[0] = p.valsA; a.keys[1] = p.keysB; a.vals[1] = p.valsB;
