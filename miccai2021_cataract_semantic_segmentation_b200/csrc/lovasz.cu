@@ -1733,6 +1733,10 @@ __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, S
         __syncthreads();                                   // previous unit done with the shared state
         // (the give-up flag of the segment can be raised by another CTA at any time: one thread reads it, all follow that reading)
         if (tid == 0) { S.s_first = LOC_NONE; S.s_end = LOC_NONE; S.heavy = 0; S.skip = ld_relaxed(h.seg_ovf + seg); }
+        {   // the bins of the counting pass are cleared here: the barriers of the staging loop below cover it
+            uint4* z = reinterpret_cast<uint4*>(S.bins);
+            for (u32 i = tid; i < LOC_BINS / 4; i += LOC_TPB) z[i] = make_uint4(0, 0, 0, 0);
+        }
         const u32 L = hyb_plan(a.seg_bits[seg], ns).L;
         const size_t sbase = (size_t)seg * a.cap + p0;
         const u32 avail = min(ns - p0, (u32)LOC_CAP);
@@ -1794,11 +1798,6 @@ __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, S
         const u32 kbits = L + (dmax > dmin ? 32u - (u32)__clz((int)(dmax - dmin)) : 0u);
         const u32 bsh = kbits > LOC_BIN_BITS ? kbits - LOC_BIN_BITS : 0u;
         const u32 fexcl = __ldcg(h.fgpre + (size_t)seg * HYB_MAX_BINS + dmin);      // foreground flags in front of the unit
-        {
-            uint4* z = reinterpret_cast<uint4*>(S.bins);
-            for (u32 i = tid; i < LOC_BINS / 4; i += LOC_TPB) z[i] = make_uint4(0, 0, 0, 0);
-        }
-        __syncthreads();
         for (u32 i = tid; i < n; i += LOC_TPB) { const u32 k = K[i]; atomicAdd(&S.bins[((k & KEY_MASK) - sub) >> bsh], 1u + ((k >> 31) << 16)); }
         __syncthreads();
         {   // exclusive scan of both halves at once (totals <= LOC_CAP: no carry); thread t owns bins [16t, 16t + 16)

@@ -50,7 +50,8 @@ for case in range(n_cases):
         lst = sorted(set(int(v) for v in rng.randint(0, c, size=3)))
         cfg["classes_to_consider"] = kw["classes_to_consider"] = lst
     ldt = [torch.int64, torch.int32, torch.uint8][rng.randint(3)]
-    _native.set_tuning(emit_path=int(rng.randint(3)), interleave=int(rng.randint(2)), stats_variant=int(rng.choice([0, 0, 1, 2, 6])))
+    _native.set_tuning(emit_path=int(rng.randint(3)), interleave=int(rng.randint(2)), stats_variant=int(rng.choice([0, 0, 1, 2, 6, 7])),
+                       sort_path=int(rng.choice([0, 0, 0, 1])))
     xd = x.cuda().requires_grad_(True)
     yd = y.cuda().to(ldt)
     tag = f"case {case}: C={c} n={n} {h}x{w} style={style} cfg={cfg} labels={ldt}"
@@ -89,7 +90,7 @@ for case in range(n_cases):
     except Exception as e:                                    # noqa: BLE001
         bad += 1
         print("ERROR", tag, repr(e)[:300])
-_native.set_tuning(emit_path=0, interleave=1, stats_variant=0)
+_native.set_tuning(emit_path=0, interleave=1, stats_variant=0, sort_path=0)
 
 # ---- the widened rows: fused CE + Lovasz pair, OHEM cross entropy, windowed IoU map ------------------------------
 for case in range(n_cases):
