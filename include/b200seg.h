@@ -228,12 +228,16 @@ int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_o
  * they exist so tests can exercise every code path and profiles can compare variants in one process.
  *   "interleave"    1 (default) warps of the streaming kernels take interleaved tiles, 0 contiguous ranges
  *   "stats_variant" 0 (default) pipelined stats kernel, 384-thread CTAs, 2 ring stages; 2..6: other CTA sizes /
- *                   stage counts; 1: register-tile kernel without per-pixel records (forces the streaming emission)
+ *                   stage counts; 1: register-tile kernel without per-pixel records (forces the streaming emission);
+ *                   7: the same kernel fed by TMA (3-D tensor map, cp.async.bulk.tensor + mbarrier)
  *   "emit_path"     0 (default) chosen on the device from the records; 1 record-driven; 2 streaming
- *   "sort_match"    2 (default) MATCH.ANY peer masks in the top digit pass only; 0 ballots; 1 MATCH.ANY
+ *   "sort_path"     0 (default) hybrid: one most-significant-digit partition pass + a shared-memory ranking kernel fused
+ *                   with the Jaccard gradient (segments whose buckets overflow shared memory fall back to 1);
+ *                   1: stable LSD radix sort by (key, value) in seven passes + a separate Jaccard kernel
+ *   "sort_match"    (LSD path) 2 (default) MATCH.ANY peer masks in the top digit pass only; 0 ballots; 1 MATCH.ANY
  *   "dbg"           timing experiments only (skips work: results become wrong)
  * Initial values come from the environment variables B200SEG_INTERLEAVE, B200SEG_STATS_VARIANT,
- * B200SEG_EMIT_PATH, B200SEG_SORT_MATCH, B200SEG_DBG.
+ * B200SEG_EMIT_PATH, B200SEG_SORT_PATH, B200SEG_SORT_MATCH, B200SEG_DBG.
  * ------------------------------------------------------------------------------------------------ */
 int b200seg_set_tuning(const char* key, int32_t value);
 

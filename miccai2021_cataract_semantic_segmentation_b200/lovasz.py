@@ -141,7 +141,10 @@ def lovasz_softmax_ce(prediction: torch.Tensor, target: torch.Tensor, ce_ignore_
                       confusion_drop_label: int | None = None, status: torch.Tensor | None = None):
     """(Lovasz-Softmax, cross entropy) of the same logits, the cross entropy with nn.CrossEntropyLoss(ignore_index)
     semantics (mean over the non-ignored pixels).  One pass over the logits forward, one backward, whenever the
-    library's pipelined kernels cover the call; otherwise the cross entropy is evaluated by torch on the side."""
+    library's pipelined kernels cover the call; otherwise the cross entropy is evaluated by torch on the side (counted in
+    ``FALLBACK_COUNTS``).  A target outside [0, C) other than ``ce_ignore_index`` does not raise here as torch would: the
+    fused pass ORs ``STATUS_LABEL_OOB`` into ``status`` -- pass a status tensor and look at it, or use the modules
+    (``LovaszSoftmaxCE`` / ``LossWrapper``), which keep one and raise at their next call / ``check()``."""
     if prediction.dim() != 4:
         raise ValueError("prediction must be [N, C, H, W]")
     _native.require_cuda(prediction, target)
