@@ -251,6 +251,38 @@ int b200seg_debug_layout(int32_t n_images, int32_t n_classes, int64_t plane, int
  * uses (expf()'s instruction sequence with two constants held in registers) differs from expf(x[i]) in any bit. */
 int b200seg_debug_exp_mismatches(const float* x, int32_t n, int32_t* mismatches, void* stream);
 
+/* ---- Lovasz-Softmax (+ cross entropy, + confusion matrix) from LOW-RESOLUTION logits ----------------------
+ * The reference's models upsample their stride-8 / stride-4 logits with F.interpolate(size=input_resolution,
+ * mode='bilinear', align_corners=True) right before the loss (models/OCR.py:126-131, models/DeepLabv3Plus.py:65-68).
+ * These entry points take lowres[n_images, n_classes, h, w] (fp32, contiguous) and labels[n_images, H, W] and compute
+ * exactly what b200seg_lovasz_forward / _ce_forward compute on the upsampled tensor -- the interpolation is ATen's CUDA
+ * arithmetic bit for bit, so loss, confusion matrix and tie order are unchanged -- without forming that tensor; the
+ * backward pass returns the gradient with respect to `lowres` (dlowres[n_images, n_classes, h, w]; float atomics, like
+ * ATen's upsample_bilinear2d_backward: reproducible to rounding).  Workspace: b200seg_lovasz_workspace_bytes(n_images,
+ * n_classes, H * W, per_image).  ce_enabled != 0 adds the cross-entropy term (ce_out, status required) as
+ * b200seg_lovasz_ce_forward does.  Covered: n_classes in {8, 17, 25}, W % 32 == 0, horizontal scale >= ~3.2 (a 32-pixel
+ * strip touches at most 12 source columns); anything else returns B200SEG_E_UNSUPPORTED (ask b200seg_lovasz_up_supported,
+ * which returns 1 / 0). */
+int b200seg_lovasz_up_supported(int32_t n_images, int32_t n_classes, int32_t h, int32_t w, int32_t H, int32_t W);
+int b200seg_lovasz_up_forward(const float* lowres, int32_t h, int32_t w, const void* labels, int32_t label_dtype,
+                              int32_t n_images, int32_t n_classes, int32_t H, int32_t W, int32_t per_image,
+                              int64_t filter_label, int32_t keep_absent, uint32_t class_mask, int32_t need_grad,
+                              void* workspace, size_t workspace_bytes, float* loss_out, int32_t ce_enabled,
+                              int64_t ce_ignore_index, float* ce_out, int64_t* cm, int64_t cm_drop_label,
+                              int32_t* status, void* stream);
+int b200seg_lovasz_up_backward(const float* lowres, int32_t h, int32_t w, const void* labels, int32_t label_dtype,
+                               int32_t n_images, int32_t n_classes, int32_t H, int32_t W, int32_t per_image,
+                               int64_t filter_label, int32_t keep_absent, uint32_t class_mask, const void* workspace,
+                               size_t workspace_bytes, const float* grad_lovasz, int32_t ce_enabled,
+                               int64_t ce_ignore_index, const float* grad_ce, float* dlowres, void* stream);
+
+/* Test hook: out[planes, H, W] = bilinear upsampling (align_corners = True) of lowres[planes, h, w] exactly as the fused
+ * b200seg_lovasz_up_* kernels compute it (pattern < 0), i.e. bit for bit what F.interpolate gives on the same device
+ * (models/OCR.py:126, models/DeepLabv3Plus.py:65); pattern 0..35 selects one of the candidate multiply-add contractions
+ * (tools/upsample_pattern.py). */
+int b200seg_debug_upsample(const float* lowres, int32_t planes, int32_t h, int32_t w, int32_t H, int32_t W,
+                           float* out, int32_t pattern, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

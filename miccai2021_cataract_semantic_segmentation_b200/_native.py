@@ -34,6 +34,11 @@ SIGNATURES = {
                                               _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "b200seg_lovasz_ce_backward": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i32, _i64, _i32, _u32, _vp, _sz,
                                                _vp, _i64, _vp, _vp, _vp]),
+    "b200seg_lovasz_up_supported": (_c.c_int, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "b200seg_lovasz_up_forward": (_c.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i32, _u32, _i32,
+                                              _vp, _sz, _vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "b200seg_lovasz_up_backward": (_c.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i32, _u32,
+                                               _vp, _sz, _vp, _i32, _i64, _vp, _vp, _vp]),
     "b200seg_confmat_accumulate": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp]),
     "b200seg_metrics_from_confmat": (_c.c_int, [_vp, _i32, _u32, _c.POINTER(_u32), _i32, _vp, _vp, _vp]),
     "b200seg_sliding_miou_scratch_bytes": (_c.c_int, [_i32, _i64, _i64, _c.POINTER(_sz)]),
@@ -45,6 +50,7 @@ SIGNATURES = {
     "b200seg_set_confmat_event": (_c.c_int, [_vp]),
     "b200seg_set_tuning": (_c.c_int, [_c.c_char_p, _i32]),
     "b200seg_debug_exp_mismatches": (_c.c_int, [_vp, _i32, _vp, _vp]),
+    "b200seg_debug_upsample": (_c.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b200seg_debug_layout": (_c.c_int, [_i32, _i32, _i64, _i32, _c.POINTER(_sz), _i32]),
     "b200seg_sort_scratch_bytes": (_c.c_int, [_i32, _i64, _c.POINTER(_sz)]),
     "b200seg_sort_segments": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _sz, _vp, _vp]),

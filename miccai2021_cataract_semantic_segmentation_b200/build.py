@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libb200seg.so")
 SOURCES = ["api.cu", "lovasz.cu", "confmat.cu", "sliding.cu", "ohem.cu"]
-HEADERS = ["common.cuh", "sort.cuh", "hybrid.cuh", "pipe.cuh"]
+HEADERS = ["common.cuh", "sort.cuh", "hybrid.cuh", "pipe.cuh", "upsample.cuh", "lovasz_up.cuh"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -26,6 +26,7 @@
 #include "sort.cuh"
 #include "hybrid.cuh"
 #include "pipe.cuh"
+#include "upsample.cuh"
 #include <cstdlib>
 #include <cuda.h>
 
@@ -47,7 +48,8 @@ enum { CTRL_STATUS = 8, CTRL_FLAGS = 16, CTRL_SLOW = 24, CTRL_SAMPLES = 25, CTRL
 enum { EMIT_PATH_STREAM = 0, EMIT_PATH_RECORDS = 1 };
 
 struct LovaszParams {
-    const float* logits;
+    const float* logits;                // full-resolution logits, or nullptr when `up` names low-resolution ones
+    UpSrc up;                           // fused bilinear upsampling (lovasz_up.cuh); up.lo == nullptr: not used
     const void* labels;
     int N, C;
     long long HW, P, cap;
@@ -372,6 +374,75 @@ __global__ void __launch_bounds__(STATS_TPB) stats_kernel_generic(LovaszParams p
 //   rec4  = label8 | class of p1 << 8 | class of p2 << 16
 // Every class outside {label, c1, c2} has p <= the guard, so a pixel whose guard is below the smallest class threshold
 // has no further candidates (always true when that threshold exceeds 1/3); the rest take emit_kernel_rec's slow path.
+// One pixel of K1 (shared by the pipelined kernel and the upsampling kernel): T[c][lane] holds the pixel's logits.
+struct StatsAcc {
+    u32 nvalid = 0, oob = 0, ce_n = 0, ce_oob = 0;
+    float ce_acc = 0.f;
+};
+template <int CT, int WT>
+__device__ __forceinline__ void stats_pixel(const LovaszParams& p, const float (*T)[WT], int lane, int lab, size_t px,
+                                            u32* s_fg_w, u32* s_key_w, u32* s_cm, const ExpConsts& ek, StatsAcc& A) {
+    float z[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) z[c] = T[c][lane];
+    float m = z[0];
+#pragma unroll
+    for (int c = 1; c < CT; ++c) m = fmaxf(m, z[c]);
+    // softmax denominator (ascending class order, like ATen) and the three largest exps among the other classes:
+    // exps are positive, so their bit patterns order like integers; the class index rides in the low byte
+    float s = 0.f;
+    int b1 = -1, b2 = -1, b3 = -1;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        const float e = sm_exp_k(z[c], m, ek);
+        s = __fadd_rn(s, e);
+        int v = (int)__byte_perm(__float_as_uint(e), (u32)c, 0x3214);   // low byte <- class (one PRMT)
+        v = (c == lab) ? -1 : v;
+        const int t1v = min(b1, v); b1 = max(b1, v);
+        const int t2v = min(b2, t1v); b2 = max(b2, t1v);
+        b3 = max(b3, t2v);
+    }
+    p.pix_m[px] = m; p.pix_s[px] = s;
+    const u32 l8 = lab8_encode(lab, CT, p.has_filter, p.filter);
+    p.lab8[px] = (unsigned char)l8;
+    u32 kfg = 0;
+    if (l8 != LAB8_FILTERED) {
+        ++A.nvalid;
+        if (l8 < (u32)CT) {
+            const float pr = sm_prob(T[l8][lane], m, s);
+            kfg = err_key(__fsub_rn(1.0f, pr));
+            atomicAdd(&s_fg_w[l8], 1u);
+            atomicMax(&s_key_w[l8], kfg);
+        }
+    }
+    {
+        const int c1 = b1 & 31, c2 = b2 & 31;          // CT >= 4: b1..b3 are real classes
+        const float p1 = sm_prob(T[c1][lane], m, s), p2 = sm_prob(T[c2][lane], m, s);
+        const float p3 = __fdiv_ru(__uint_as_float((u32)b3 | 255u), s);  // >= p of every class not recorded
+        p.rec16[px] = make_uint4(kfg, __float_as_uint(p1), __float_as_uint(p2), __float_as_uint(p3));
+        p.rec4[px] = l8 | ((u32)c1 << 8) | ((u32)c2 << 16);
+    }
+    if (p.cm && !(p.has_drop && lab == p.drop)) {
+        if ((unsigned)lab < (unsigned)CT) {
+            int arg = 0;
+#pragma unroll
+            for (int c = CT - 1; c >= 0; --c) arg = (z[c] == m) ? c : arg;          // first maximum
+            if (s != s || m != m) {                   // NaN / inf among the logits: torch's argmax lets NaN win
+                float best = z[0];
+                arg = 0;
+#pragma unroll
+                for (int c = 1; c < CT; ++c) argmax_step(z[c], c, best, arg);
+            }
+            atomicAdd(&s_cm[arg * CT + lab], 1u);
+        } else A.oob = 1;
+    }
+    if (p.ce_enabled && !(p.has_ce_ignore && lab == p.ce_ignore)) {
+        // -log softmax(z)[label] = max + log(sum) - z_label        (log_softmax + nll_loss of nn.CrossEntropyLoss)
+        if ((unsigned)lab < (unsigned)CT) { A.ce_acc += (m + logf(s)) - T[lab][lane]; ++A.ce_n; }
+        else A.ce_oob = 1;                               // torch raises on such a target
+    }
+}
+
 template <int CT, int TPB, int STAGES, typename LT>
 __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
     using W = WarpTile<CT, 1>;
@@ -434,8 +505,7 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
     };
 
     int cur_g = -1, stage = 0, pstage = STAGES - 1;
-    u32 nvalid = 0, oob = 0, ce_n = 0, ce_oob = 0;
-    float ce_acc = 0.f;
+    StatsAcc A;
     ExpConsts ek;
     ek.load();
     for (u32 t = t0; t < t1; t += step) {
@@ -448,7 +518,7 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
         while (cti >= wtpi) { cti -= wtpi; ++cn; }
         const int g = p.per_image ? n : 0;
         if (g != cur_g) {
-            if (cur_g >= 0) { flush_group(cur_g, nvalid); nvalid = 0; }
+            if (cur_g >= 0) { flush_group(cur_g, A.nvalid); A.nvalid = 0; }
             cur_g = g;
         }
         cp_async_wait<STAGES - 1>();
@@ -461,77 +531,20 @@ __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
         int lab;
         if constexpr (sizeof(LT) == 8) lab = sat_i32(reinterpret_cast<const long long*>(sb + CT * WT * 4)[lane]);
         else lab = (int)reinterpret_cast<const LT*>(sb + CT * WT * 4)[lane];
-        float z[CT];
-#pragma unroll
-        for (int c = 0; c < CT; ++c) z[c] = T[c][lane];
-        float m = z[0];
-#pragma unroll
-        for (int c = 1; c < CT; ++c) m = fmaxf(m, z[c]);
-        // softmax denominator (ascending class order, like ATen) and the three largest exps among the other classes:
-        // exps are positive, so their bit patterns order like integers; the class index rides in the low byte
-        float s = 0.f;
-        int b1 = -1, b2 = -1, b3 = -1;
-#pragma unroll
-        for (int c = 0; c < CT; ++c) {
-            const float e = sm_exp_k(z[c], m, ek);
-            s = __fadd_rn(s, e);
-            int v = (int)__byte_perm(__float_as_uint(e), (u32)c, 0x3214);   // low byte <- class (one PRMT)
-            v = (c == lab) ? -1 : v;
-            const int t1v = min(b1, v); b1 = max(b1, v);
-            const int t2v = min(b2, t1v); b2 = max(b2, t1v);
-            b3 = max(b3, t2v);
-        }
-        p.pix_m[px] = m; p.pix_s[px] = s;
-        const u32 l8 = lab8_encode(lab, CT, p.has_filter, p.filter);
-        p.lab8[px] = (unsigned char)l8;
-        u32 kfg = 0;
-        if (l8 != LAB8_FILTERED) {
-            ++nvalid;
-            if (l8 < (u32)CT) {
-                const float pr = sm_prob(T[l8][lane], m, s);
-                kfg = err_key(__fsub_rn(1.0f, pr));
-                atomicAdd(&s_fg[warp][l8], 1u);
-                atomicMax(&s_key[warp][l8], kfg);
-            }
-        }
-        {
-            const int c1 = b1 & 31, c2 = b2 & 31;          // CT >= 4: b1..b3 are real classes
-            const float p1 = sm_prob(T[c1][lane], m, s), p2 = sm_prob(T[c2][lane], m, s);
-            const float p3 = __fdiv_ru(__uint_as_float((u32)b3 | 255u), s);  // >= p of every class not recorded
-            p.rec16[px] = make_uint4(kfg, __float_as_uint(p1), __float_as_uint(p2), __float_as_uint(p3));
-            p.rec4[px] = l8 | ((u32)c1 << 8) | ((u32)c2 << 16);
-        }
-        if (p.cm && !(p.has_drop && lab == p.drop)) {
-            if ((unsigned)lab < (unsigned)CT) {
-                int arg = 0;
-#pragma unroll
-                for (int c = CT - 1; c >= 0; --c) arg = (z[c] == m) ? c : arg;          // first maximum
-                if (s != s || m != m) {                   // NaN / inf among the logits: torch's argmax lets NaN win
-                    float best = z[0];
-                    arg = 0;
-#pragma unroll
-                    for (int c = 1; c < CT; ++c) argmax_step(z[c], c, best, arg);
-                }
-                atomicAdd(&s_cm[arg * CT + lab], 1u);
-            } else oob = 1;
-        }
-        if (p.ce_enabled && !(p.has_ce_ignore && lab == p.ce_ignore)) {
-            // -log softmax(z)[label] = max + log(sum) - z_label        (log_softmax + nll_loss of nn.CrossEntropyLoss)
-            if ((unsigned)lab < (unsigned)CT) { ce_acc += (m + logf(s)) - T[lab][lane]; ++ce_n; }
-            else ce_oob = 1;                               // torch raises on such a target
-        }
+        stats_pixel<CT, WT>(p, T, lane, lab, px, s_fg[warp], s_key[warp], s_cm, ek, A);
     }
     cp_async_wait<0>();
     if (p.ce_enabled) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { ce_acc += __shfl_xor_sync(FULL_MASK, ce_acc, o); ce_n += __shfl_xor_sync(FULL_MASK, ce_n, o); }
-        if (lane == 0 && ce_n) { atomicAdd(p.ce_sum, (double)ce_acc); atomicAdd(p.ce_cnt, ce_n); }
-        if (__any_sync(FULL_MASK, ce_oob) && lane == 0 && p.status) atomicOr(p.status, STATUS_LABEL_OOB);
+        for (int o = 16; o > 0; o >>= 1) { A.ce_acc += __shfl_xor_sync(FULL_MASK, A.ce_acc, o); A.ce_n += __shfl_xor_sync(FULL_MASK, A.ce_n, o); }
+        if (lane == 0 && A.ce_n) { atomicAdd(p.ce_sum, (double)A.ce_acc); atomicAdd(p.ce_cnt, A.ce_n); }
+        if (__any_sync(FULL_MASK, A.ce_oob) && lane == 0 && p.status) atomicOr(p.status, STATUS_LABEL_OOB);
     }
-    if (cur_g >= 0 && p.per_image) { flush_group(cur_g, nvalid); nvalid = 0; }
+    if (cur_g >= 0 && p.per_image) { flush_group(cur_g, A.nvalid); A.nvalid = 0; }
     // flat mode: combine the CTA's warps first (one global atomic per class and CTA)
-    if (oob) s_oob = 1;
+    if (A.oob) s_oob = 1;
     if (!p.per_image) {
+        u32 nvalid = A.nvalid;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(FULL_MASK, nvalid, o);
         if (lane == 0 && nvalid) atomicAdd(&s_valid, nvalid);
@@ -794,7 +807,7 @@ __global__ void __launch_bounds__(256) absent_max_kernel(LovaszParams p) {
         const int lab = load_label<LT>(p.labels, (size_t)px);
         if (p.has_filter && lab == p.filter) continue;
         const long long n = px / p.HW, q = px - n * p.HW;
-        const float z = __ldg(p.logits + ((size_t)n * p.C + c) * p.HW + q);
+        const float z = p.up.lo ? up_logit(p.up, p.C, (int)n, c, q) : __ldg(p.logits + ((size_t)n * p.C + c) * p.HW + q);
         const float pr = sm_prob(z, p.pix_m[px], p.pix_s[px]);
         best = max(best, __float_as_uint(pr));
     }
@@ -1087,6 +1100,75 @@ __device__ __forceinline__ void emit_cursor_next(EmitCursor& c, u32 tpc, u32 n_r
     }
 }
 
+// One 32-pixel tile of the streaming emission (lane = pixel; Tz[c][lane] = the pixel's logits): exact candidate test per class,
+// one reservation per (tile, class), lane-private stores.  Shared by emit_kernel_async and emit_kernel_up.
+template <int CT, int WT>
+__device__ __forceinline__ void emit_tile(const LovaszParams& p, const float (*Tz)[WT], int lane, u32 lt_mask, float m, float s,
+                                          u32 l8, bool inb, size_t px, int g, const float* thr, const float* logthr_w,
+                                          u32* mask_w, u32* base_w) {
+    u32 acc = 0;                                      // accepted classes of this lane's pixel
+    float e0 = 0.f, e1 = 0.f;                         // errors of the first two of them (the rest is recomputed)
+    const int lab = l8 < (u32)CT ? (int)l8 : -1;
+    if (inb) {
+        const float theta = pre_theta(m, s);
+        u32 pm = 0;
+        const float4* lt4 = reinterpret_cast<const float4*>(logthr_w);   // broadcast 128-bit reads
+#pragma unroll
+        for (int c4 = 0; c4 < (CT + 3) / 4; ++c4) {
+            const float4 lt = lt4[c4];
+            const float l[4] = {lt.x, lt.y, lt.z, lt.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 4 * c4 + j;
+                if (c < CT) pm |= (Tz[c][lane] >= theta + l[j]) ? (1u << c) : 0u;
+            }
+        }
+        if (l8 == LAB8_FILTERED) pm = 0;
+        else if (lab >= 0 && thr_active(thr[lab])) pm |= 1u << lab;
+        while (pm) {
+            const int c = __ffs(pm) - 1;
+            pm &= pm - 1;
+            float err, pr;
+            if (exact_accept(Tz[c][lane], m, s, c == lab, thr[c], err, pr)) {
+                if (acc == 0) e0 = err; else if ((acc & (acc - 1)) == 0) e1 = err;
+                acc |= 1u << c;
+            }
+        }
+        p.cmask[px] = lab >= 0 ? (acc & ~(1u << lab)) : acc;
+    }
+    if (__any_sync(FULL_MASK, acc != 0)) {
+        // lane c collects the ballot of class c (independent votes, unrolled: a data-dependent loop over the classes
+        // present would serialise their latencies) and reserves the slots; the table goes through shared memory
+        u32 mine = 0;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const u32 b = __ballot_sync(FULL_MASK, (acc >> c) & 1u);
+            if (lane == c) mine = b;
+        }
+        __syncwarp();
+        if (lane < CT) {                               // the tile's slice of every segment: one atomic per class with candidates
+            const u32 cnt = __popc(mine);
+            mask_w[lane] = mine;
+            base_w[lane] = cnt ? atomicAdd(p.seg_count + (size_t)g * CT + lane, cnt) : 0u;
+        }
+        __syncwarp();
+        u32 mm = acc;
+        int i = 0;
+        while (mm) {                                   // this lane's own candidates
+            const int c = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const bool fg = c == lab;
+            float err = i == 0 ? e0 : e1;
+            if (i >= 2) { float pr; exact_accept(Tz[c][lane], m, s, fg, thr[c], err, pr); }
+            ++i;
+            const u32 rank = base_w[c] + __popc(mask_w[c] & lt_mask);
+            const size_t slot = ((size_t)g * CT + c) * (size_t)p.cap + rank;
+            p.keysA[slot] = err_key(err) | (fg ? KEY_FG : 0u);
+            p.valsA[slot] = ((u32)px << 1) | (fg ? 1u : 0u);
+        }
+    }
+}
+
 template <int CT, int TPB>
 __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
     if (p.flags[0] != EMIT_PATH_STREAM) return;           // ctrl is zeroed per call: the default path is this one
@@ -1153,69 +1235,7 @@ __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
         const size_t px = (size_t)n * p.HW + q;
         cp_async_wait<STAGES - 1>();
         __syncwarp();
-        const float (*Tz)[WT] = Z[stage];
-        const float* thr = s_thr[warp];
-        u32 acc = 0;                                      // accepted classes of this lane's pixel
-        float e0 = 0.f, e1 = 0.f;                         // errors of the first two of them (the rest is recomputed)
-        const int lab = l8 < (u32)CT ? (int)l8 : -1;
-        if (inb) {
-            const float theta = pre_theta(m, s);
-            u32 pm = 0;
-            const float4* lt4 = reinterpret_cast<const float4*>(s_logthr[warp]);   // broadcast 128-bit reads
-#pragma unroll
-            for (int c4 = 0; c4 < (CT + 3) / 4; ++c4) {
-                const float4 lt = lt4[c4];
-                const float l[4] = {lt.x, lt.y, lt.z, lt.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = 4 * c4 + j;
-                    if (c < CT) pm |= (Tz[c][lane] >= theta + l[j]) ? (1u << c) : 0u;
-                }
-            }
-            if (l8 == LAB8_FILTERED) pm = 0;
-            else if (lab >= 0 && thr_active(thr[lab])) pm |= 1u << lab;
-            while (pm) {
-                const int c = __ffs(pm) - 1;
-                pm &= pm - 1;
-                float err, pr;
-                if (exact_accept(Tz[c][lane], m, s, c == lab, thr[c], err, pr)) {
-                    if (acc == 0) e0 = err; else if ((acc & (acc - 1)) == 0) e1 = err;
-                    acc |= 1u << c;
-                }
-            }
-            p.cmask[px] = lab >= 0 ? (acc & ~(1u << lab)) : acc;
-        }
-        if (__any_sync(FULL_MASK, acc != 0)) {
-            // lane c collects the ballot of class c (independent votes, unrolled: a data-dependent loop over the classes
-            // present would serialise their latencies) and reserves the slots; the table goes through shared memory
-            u32 mine = 0;
-#pragma unroll
-            for (int c = 0; c < CT; ++c) {
-                const u32 b = __ballot_sync(FULL_MASK, (acc >> c) & 1u);
-                if (lane == c) mine = b;
-            }
-            __syncwarp();
-            if (lane < CT) {                               // the tile's slice of every segment: one atomic per class with candidates
-                const u32 cnt = __popc(mine);
-                s_mask[warp][lane] = mine;
-                s_base[warp][lane] = cnt ? atomicAdd(p.seg_count + (size_t)g * CT + lane, cnt) : 0u;
-            }
-            __syncwarp();
-            u32 mm = acc;
-            int i = 0;
-            while (mm) {                                   // this lane's own candidates
-                const int c = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const bool fg = c == lab;
-                float err = i == 0 ? e0 : e1;
-                if (i >= 2) { float pr; exact_accept(Tz[c][lane], m, s, fg, thr[c], err, pr); }
-                ++i;
-                const u32 rank = s_base[warp][c] + __popc(s_mask[warp][c] & lt_mask);
-                const size_t slot = ((size_t)g * CT + c) * (size_t)p.cap + rank;
-                p.keysA[slot] = err_key(err) | (fg ? KEY_FG : 0u);
-                p.valsA[slot] = ((u32)px << 1) | (fg ? 1u : 0u);
-            }
-        }
+        emit_tile<CT, WT>(p, Z[stage], lane, lt_mask, m, s, l8, inb, px, g, s_thr[warp], s_logthr[warp], s_mask[warp], s_base[warp]);
         emit_cursor_next(cur, tpc, n_runs, wtpi, p.per_image);
     }
     cp_async_wait<0>();
@@ -1242,6 +1262,19 @@ __device__ __noinline__ u32 emit_scan_pixel(const float* lp, long long plane, in
     return more;
 }
 
+// the same scan over interpolated logits (fused upsampling: the record path is the only emission path there)
+__device__ __noinline__ float up_logit_call(UpSrc u, int C, int n, int c, long long q) { return up_logit(u, C, n, c, q); }
+__device__ __noinline__ u32 emit_scan_pixel_up(UpSrc u, int C, int n, long long q, float m, float sden, float guard,
+                                               const float* thr, const unsigned char* order, u32 skip) {
+    u32 more = 0;
+    for (int i = 0; i < C; ++i) {
+        const int c = order[i];
+        if (thr[c] > guard) break;
+        if (!((skip >> c) & 1u) && sm_prob(up_logit(u, C, n, c, q), m, sden) >= thr[c]) more |= 1u << c;
+    }
+    return more;
+}
+
 #define ECTA_CAP 6144                                     // staged candidates per pass over the classes of a tile (>= 3 per pixel)
 struct EctaSmem {
     // counters of two tiles in turn: while a tile is staged and written out, the next tile's set is cleared
@@ -1254,7 +1287,7 @@ struct EctaSmem {
     u32 stageK[ECTA_CAP], stageV[ECTA_CAP];
 };
 
-template <int CT>
+template <int CT, bool UP>
 __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszParams p) {
     if (p.flags[0] != EMIT_PATH_RECORDS) return;
     extern __shared__ __align__(16) unsigned char ecta_smem_raw[];
@@ -1322,7 +1355,12 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
                         if (p2 >= S.thr[c2]) a |= 1u << c2;
                         if (__uint_as_float(rec[j].w) >= tmin) {          // rare: scan the other classes (a real call)
                             const u32 skip = (l8 < (u32)CT ? 1u << l8 : 0u) | (1u << c1) | (1u << c2);
-                            const u32 more = (p.dbg & 4) ? 0u : emit_scan_pixel(p.logits + (size_t)n * CT * p.HW + q0 + j, p.HW, CT,
+                            u32 more;
+                            if constexpr (UP)
+                                more = emit_scan_pixel_up(p.up, CT, n, q0 + j, p.pix_m[px0 + j], p.pix_s[px0 + j],
+                                                          __uint_as_float(rec[j].w), S.thr, S.order, skip);
+                            else
+                                more = (p.dbg & 4) ? 0u : emit_scan_pixel(p.logits + (size_t)n * CT * p.HW + q0 + j, p.HW, CT,
                                                              p.pix_m[px0 + j], p.pix_s[px0 + j], __uint_as_float(rec[j].w),
                                                              S.thr, S.order, skip);
                             if (more) { a |= more; extra |= 1u << j; }
@@ -1401,8 +1439,10 @@ __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszPar
                                 const int c = __ffs(a) - 1;
                                 a &= a - 1;
                                 if (c < lo || c >= hi) continue;
-                                const float pr = sm_prob(__ldg(p.logits + ((size_t)n * CT + c) * p.HW + q0 + j),
-                                                         p.pix_m[px0 + j], p.pix_s[px0 + j]);
+                                float zc;
+                                if constexpr (UP) zc = up_logit_call(p.up, CT, n, c, q0 + j);
+                                else zc = __ldg(p.logits + ((size_t)n * CT + c) * p.HW + q0 + j);
+                                const float pr = sm_prob(zc, p.pix_m[px0 + j], p.pix_s[px0 + j]);
                                 const u32 pos = coff[c] - base + cnt[c] + atomicAdd(&curx[c], 1u);
                                 S.stageK[pos] = err_key(pr); S.stageV[pos] = v0;
                             }
@@ -2237,6 +2277,8 @@ __global__ void __launch_bounds__(BWD_TPB) backward_kernel_generic(LovaszParams 
 
 // Enqueue the hybrid path: prepare, bucket histogram, partition, local sort + Jaccard, fallback (a no-op unless a
 // segment overflowed).  All decisions are taken on the device.
+#include "lovasz_up.cuh"
+
 static int hybrid_enqueue(const LovaszParams& p, const SortArgs& a, const HybArgs& h, const SortScratch& L, cudaStream_t st) {
     static bool attr_set[64] = {false};
     static int fb_occ[64] = {0};
@@ -2309,6 +2351,7 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
                         int32_t n, int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
                         int32_t keep_absent, uint32_t class_mask) {
     p.logits = logits; p.labels = labels;
+    p.up = UpSrc{nullptr, 0, 0, 0, 0, 0.f, 0.f};
     p.N = n; p.C = c; p.HW = hw; p.P = (long long)n * hw;
     p.inv_hw = hw >= 2 ? (u32)((1ull << 32) / (unsigned long long)hw) : 0xFFFFFFFFu;
     p.per_image = per_image ? 1 : 0;
@@ -2382,7 +2425,8 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
                                int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
                                int32_t keep_absent, uint32_t class_mask, int32_t need_grad, void* workspace,
                                size_t workspace_bytes, float* loss_out, int64_t* cm, int64_t cm_drop_label,
-                               int32_t* status, void* stream, bool ce_enabled, int64_t ce_ignore, float* ce_out) {
+                               int32_t* status, void* stream, bool ce_enabled, int64_t ce_ignore, float* ce_out,
+                               const UpSrc* up = nullptr) {
     if (int rc = check_shape(n, c, hw)) return rc;
     if (!loss_out) { b200seg_set_error("loss_out is NULL"); return B200SEG_E_INVALID; }
     if ((long long)n * hw == 0) {      // empty batch: nothing to read, loss 0 (cross entropy of nothing: NaN, like torch)
@@ -2392,7 +2436,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
     }
     if (ce_enabled) {
         if (!ce_out || !status) { b200seg_set_error("ce_out / status is NULL"); return B200SEG_E_INVALID; }
-        if (!pipelined_ok(logits, labels, label_dtype, c, hw)) {
+        if (!up && !pipelined_ok(logits, labels, label_dtype, c, hw)) {
             b200seg_set_error("the fused cross-entropy term needs the pipelined kernels (C in {8,17,25}, plane %% 16 == 0, "
                               "16-byte aligned tensors): ask b200seg_lovasz_ce_supported first");
             return B200SEG_E_UNSUPPORTED;
@@ -2403,7 +2447,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
             return B200SEG_E_UNSUPPORTED;
         }
     }
-    if (!logits || !labels || !workspace || (cm && !status)) {
+    if ((!logits && !up) || !labels || !workspace || (cm && !status)) {
         b200seg_set_error("null pointer argument");
         return B200SEG_E_INVALID;
     }
@@ -2416,6 +2460,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
     char* ws = (char*)workspace;
     LovaszParams p;
     fill_params(p, L, ws, logits, labels, n, c, hw, per_image, filter_label, keep_absent, class_mask);
+    if (up) p.up = *up;
     p.loss_out = loss_out;
     p.need_grad = need_grad ? 1 : 0;
     p.dbg = b200seg_tuning().dbg;
@@ -2430,14 +2475,33 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
 
     CUDA_TRY(cudaMemsetAsync(ws + L.ctrl, 0, L.zero_end - L.ctrl, st));
     const int sms = b200seg_sm_count();
-    const bool v4 = vec4_ok(logits, labels, label_dtype, hw);
+    const bool v4 = up ? true : vec4_ok(logits, labels, label_dtype, hw);   // (fused upsampling: W % 32 == 0, labels read one by one)
     b200seg_stage(0, st);
 
     // K1
     const bool known_c = (c == 8 || c == 17 || c == 25);
     const int stats_variant = b200seg_tuning().stats_variant, emit_force = b200seg_tuning().emit_path;
     const bool async_ok = v4 && known_c && hw % 16 == 0 && aligned16(labels);
-    if (async_ok && stats_variant != 1) {
+    if (up) {
+        p.have_records = 1;
+        p.emit_force = emit_force;
+#define LAUNCH_STATS_UP(CC)                                                                                       \
+    {                                                                                                             \
+        constexpr int TT = 128;                                                                                   \
+        const size_t smem = (size_t)(TT / 32) * 3 * CC * 32 * 4;                                                  \
+        CUDA_TRY(cudaFuncSetAttribute(stats_kernel_up<CC, TT, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      (int)smem));                                                                \
+        int per_sm = (int)((224 * 1024) / (smem + 6 * 1024));                                                     \
+        if (per_sm * TT > 2048) per_sm = 2048 / TT;                                                               \
+        stats_kernel_up<CC, TT, LT><<<sms * per_sm, TT, smem, st>>>(p);                                           \
+    }
+        DISPATCH_LABEL(label_dtype, {
+            if (c == 8) LAUNCH_STATS_UP(8)
+            else if (c == 17) LAUNCH_STATS_UP(17)
+            else LAUNCH_STATS_UP(25)
+        });
+#undef LAUNCH_STATS_UP
+    } else if (async_ok && stats_variant != 1) {
         p.have_records = 1;
         p.emit_force = emit_force;
 #define LAUNCH_STATS_ASYNC(CC, TT, SS)                                                                          \
@@ -2524,8 +2588,13 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
             const size_t smem = sizeof(EctaSmem);
 #define LAUNCH_EMIT_CTA(CC)                                                                                          \
     {                                                                                                                \
-        CUDA_TRY(cudaFuncSetAttribute(emit_kernel_cta<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        emit_kernel_cta<CC><<<grid, ECTA_TPB, smem, st>>>(p);                                                        \
+        if (up) {                                                                                                    \
+            CUDA_TRY(cudaFuncSetAttribute(emit_kernel_cta<CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            emit_kernel_cta<CC, true><<<grid, ECTA_TPB, smem, st>>>(p);                                              \
+        } else {                                                                                                     \
+            CUDA_TRY(cudaFuncSetAttribute(emit_kernel_cta<CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            emit_kernel_cta<CC, false><<<grid, ECTA_TPB, smem, st>>>(p);                                             \
+        }                                                                                                            \
     }
             if (c == 8) LAUNCH_EMIT_CTA(8)
             else if (c == 17) LAUNCH_EMIT_CTA(17)
@@ -2533,7 +2602,22 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
 #undef LAUNCH_EMIT_CTA
             LAUNCH_CHECK("emit_kernel_cta");
         }
-        if (pipe_ok) {
+        if (up) {
+#define LAUNCH_EMIT_UP(CC)                                                                                        \
+    {                                                                                                             \
+        constexpr int ET = 128;                                                                                   \
+        const size_t smem = (size_t)(ET / 32) * 3 * CC * 32 * 4;                                                  \
+        CUDA_TRY(cudaFuncSetAttribute(emit_kernel_up<CC, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      (int)smem));                                                                \
+        int per_sm = (int)((224 * 1024) / (smem + 2048));                                                         \
+        if (per_sm * ET > 2048) per_sm = 2048 / ET;                                                               \
+        emit_kernel_up<CC, ET><<<sms * per_sm, ET, smem, st>>>(p);                                                \
+    }
+            if (c == 8) LAUNCH_EMIT_UP(8)
+            else if (c == 17) LAUNCH_EMIT_UP(17)
+            else LAUNCH_EMIT_UP(25)
+#undef LAUNCH_EMIT_UP
+        } else if (pipe_ok) {
 #define LAUNCH_EMIT_ASYNC(CC)                                                                                   \
     {                                                                                                           \
         constexpr int ET = 128, ES = 2;                                                                         \
@@ -2611,10 +2695,10 @@ static int lovasz_backward_impl(const float* logits, const void* labels, int32_t
                                 int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
                                 int32_t keep_absent, uint32_t class_mask, const void* workspace,
                                 size_t workspace_bytes, const float* grad_out, float* dlogits, void* stream,
-                                bool ce_enabled, int64_t ce_ignore, const float* grad_ce) {
+                                bool ce_enabled, int64_t ce_ignore, const float* grad_ce, const UpSrc* up = nullptr) {
     if (int rc = check_shape(n, c, hw)) return rc;
     if ((long long)n * hw == 0) return 0;
-    if (!logits || !labels || !workspace || !grad_out || !dlogits) {
+    if ((!logits && !up) || !labels || !workspace || !grad_out || !dlogits) {
         b200seg_set_error("null pointer argument");
         return B200SEG_E_INVALID;
     }
@@ -2632,6 +2716,29 @@ static int lovasz_backward_impl(const float* logits, const void* labels, int32_t
     p.has_ce_ignore = (ce_enabled && ce_ignore >= INT_MIN && ce_ignore <= INT_MAX) ? 1 : 0;
     p.ce_ignore = p.has_ce_ignore ? (int)ce_ignore : 0;
     const int sms = b200seg_sm_count();
+    if (up) {                                              // fused upsampling: the gradient goes to the low-resolution logits
+        p.up = *up;
+        p.dbg = b200seg_tuning().dbg;
+        b200seg_stage(9, st);
+        CUDA_TRY(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)n * c * up->h * up->w, st));
+#define LAUNCH_BWD_UP(CC)                                                                                         \
+    {                                                                                                             \
+        constexpr int TT = 128;                                                                                   \
+        const size_t smem = (size_t)(TT / 32) * sizeof(UpBwdSmem<CC>);                                            \
+        CUDA_TRY(cudaFuncSetAttribute(backward_kernel_up<CC, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                      (int)smem));                                                                \
+        int per_sm = (int)((224 * 1024) / (smem + 2048));                                                         \
+        if (per_sm > 3) per_sm = 3;                                                                               \
+        backward_kernel_up<CC, TT><<<sms * per_sm, TT, smem, st>>>(p, grad_out, grad_ce, dlogits);                \
+    }
+        if (c == 8) LAUNCH_BWD_UP(8)
+        else if (c == 17) LAUNCH_BWD_UP(17)
+        else LAUNCH_BWD_UP(25)
+#undef LAUNCH_BWD_UP
+        LAUNCH_CHECK("backward_kernel_up");
+        b200seg_stage(10, st);
+        return 0;
+    }
     const bool v4 = vec4_ok(logits, labels, label_dtype, hw) && aligned16(dlogits);
     const bool pipe_ok = v4 && hw % 16 == 0 && (c == 8 || c == 17 || c == 25);
     if (ce_enabled && !pipe_ok) {
@@ -2687,6 +2794,56 @@ extern "C" int b200seg_lovasz_ce_backward(const float* logits, const void* label
                                 workspace, workspace_bytes, grad_lovasz, dlogits, stream, true, ce_ignore_index, grad_ce);
 }
 
+// ---- fused bilinear upsampling (align_corners = True) + loss: the logits stay at the model's resolution -------------------------
+static int up_check(const float* lowres, int32_t n, int32_t c, int32_t h, int32_t w, int32_t H, int32_t W, UpSrc* u) {
+    if (h < 1 || w < 1 || H < 1 || W < 1) { b200seg_set_error("invalid upsampling shape %dx%d -> %dx%d", h, w, H, W); return B200SEG_E_INVALID; }
+    if (int rc = check_shape(n, c, (int64_t)H * W)) return rc;
+    if (!(c == 8 || c == 17 || c == 25) || W % 32 != 0) {
+        b200seg_set_error("fused upsampling covers C in {8, 17, 25} and output widths that are multiples of 32 (got C=%d, W=%d)", c, W);
+        return B200SEG_E_UNSUPPORTED;
+    }
+    *u = make_up_src(lowres, h, w, H, W);
+    // source columns one 32-pixel strip can touch (backward flush table)
+    if ((int)ceilf(31.0f * u->rx) + 2 > UP_MAX_COLS) {
+        b200seg_set_error("fused upsampling needs a horizontal scale factor of at least ~3.2 (got %d -> %d)", w, W);
+        return B200SEG_E_UNSUPPORTED;
+    }
+    if ((long double)n * c * h * w >= (long double)(1ull << 31)) { b200seg_set_error("low-resolution logits too large"); return B200SEG_E_INVALID; }
+    return 0;
+}
+
+extern "C" int b200seg_lovasz_up_supported(int32_t n, int32_t c, int32_t h, int32_t w, int32_t H, int32_t W) {
+    UpSrc u;
+    return up_check(nullptr, n, c, h, w, H, W, &u) == 0 ? 1 : 0;
+}
+
+extern "C" int b200seg_lovasz_up_forward(const float* lowres, int32_t h, int32_t w, const void* labels, int32_t label_dtype,
+                                         int32_t n, int32_t c, int32_t H, int32_t W, int32_t per_image, int64_t filter_label,
+                                         int32_t keep_absent, uint32_t class_mask, int32_t need_grad, void* workspace,
+                                         size_t workspace_bytes, float* loss_out, int32_t ce_enabled, int64_t ce_ignore_index,
+                                         float* ce_out, int64_t* cm, int64_t cm_drop_label, int32_t* status, void* stream) {
+    UpSrc u;
+    if (int rc = up_check(lowres, n, c, h, w, H, W, &u)) return rc;
+    if (!lowres && (long long)n * H * W != 0) { b200seg_set_error("null pointer argument"); return B200SEG_E_INVALID; }
+    return lovasz_forward_impl(nullptr, labels, label_dtype, n, c, (int64_t)H * W, per_image, filter_label, keep_absent,
+                               class_mask, need_grad, workspace, workspace_bytes, loss_out, cm, cm_drop_label, status, stream,
+                               ce_enabled != 0, ce_ignore_index, ce_out, &u);
+}
+
+extern "C" int b200seg_lovasz_up_backward(const float* lowres, int32_t h, int32_t w, const void* labels, int32_t label_dtype,
+                                          int32_t n, int32_t c, int32_t H, int32_t W, int32_t per_image, int64_t filter_label,
+                                          int32_t keep_absent, uint32_t class_mask, const void* workspace,
+                                          size_t workspace_bytes, const float* grad_lovasz, int32_t ce_enabled,
+                                          int64_t ce_ignore_index, const float* grad_ce, float* dlowres, void* stream) {
+    UpSrc u;
+    if (int rc = up_check(lowres, n, c, h, w, H, W, &u)) return rc;
+    if (!lowres && (long long)n * H * W != 0) { b200seg_set_error("null pointer argument"); return B200SEG_E_INVALID; }
+    if (ce_enabled && !grad_ce) { b200seg_set_error("grad_ce is NULL"); return B200SEG_E_INVALID; }
+    return lovasz_backward_impl(nullptr, labels, label_dtype, n, c, (int64_t)H * W, per_image, filter_label, keep_absent,
+                                class_mask, workspace, workspace_bytes, grad_lovasz, dlowres, stream, ce_enabled != 0,
+                                ce_ignore_index, grad_ce, &u);
+}
+
 // ---- test hook: byte offsets of a few workspace regions (tests inspect the per-pixel records) -----------------------
 extern "C" int b200seg_debug_layout(int32_t n, int32_t c, int64_t hw, int32_t per_image, size_t* offsets, int32_t n_offsets) {
     if (!offsets || n_offsets < 8) { b200seg_set_error("need room for 8 offsets"); return B200SEG_E_INVALID; }
@@ -2714,6 +2871,17 @@ extern "C" int b200seg_debug_exp_mismatches(const float* x, int32_t n, int32_t* 
     if (!x || !mismatches || n < 0) { b200seg_set_error("invalid argument"); return B200SEG_E_INVALID; }
     exp_check_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(x, n, mismatches);
     LAUNCH_CHECK("exp_check_kernel");
+    return 0;
+}
+
+// ---- test hook: bilinear upsampling (align_corners = True) as the fused kernels compute it ----------------------------------
+// pattern < 0: the product's arithmetic; 0..35: the candidate contraction patterns of tools/upsample_pattern.py
+extern "C" int b200seg_debug_upsample(const float* lowres, int32_t planes, int32_t h, int32_t w, int32_t H, int32_t W,
+                                      float* out, int32_t pattern, void* stream) {
+    if (!lowres || !out || planes < 1 || h < 1 || w < 1 || H < 1 || W < 1) { b200seg_set_error("invalid argument"); return B200SEG_E_INVALID; }
+    const UpSrc u = make_up_src(lowres, h, w, H, W);
+    upsample_debug_kernel<<<b200seg_sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(u, planes, out, pattern);
+    LAUNCH_CHECK("upsample_debug_kernel");
     return 0;
 }
 
