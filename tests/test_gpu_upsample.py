@@ -53,7 +53,9 @@ def _inputs(n, c, h, w, H, W, seed, dist, with_ignore):
         flips = torch.rand((n, h, w), generator=g) < 0.10
         noisy[flips] = torch.randint(0, c, (int(flips.sum()),), generator=g)
         low = 6.0 * F.one_hot(noisy.clamp(max=c - 1), c).permute(0, 3, 1, 2).float() + torch.randn((n, c, h, w), generator=g)
-    return low, y
+    # NCHW-contiguous like a convolution's output (models/OCR.py:125): the sum above comes out channels-last, and ATen
+    # interpolates channels-last tensors with another kernel whose rounding differs (up to 1e-6 on a logit)
+    return low.contiguous(), y
 
 
 CASES = [

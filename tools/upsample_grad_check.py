@@ -9,7 +9,10 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import miccai2021_cataract_semantic_segmentation_b200 as b200
 from test_gpu_upsample import _inputs, CASES
 
+only = sys.argv[1:] 
 for name, (n, c, h, w, H, W), dist, opt in CASES:
+    if only and name not in only:
+        continue
     low, y = _inputs(n, c, h, w, H, W, 99 + n * c + h, dist, opt.get("ignore", False))
     yd = y.cuda()
     kw = dict(per_image=opt.get("per_image", False), classes_to_ignore=opt.get("classes_to_ignore"),
