@@ -269,6 +269,56 @@ def measure_config(b200, args, device, name, dist, classes, per_image, batch, st
     return out
 
 
+def measure_upsampled(b200, args, device, name, stride, classes, batch, steps):
+    """SURVEY §8 F2: the training-loss step from the model's LOW-resolution logits (models/OCR.py:126: stride 8;
+    models/DeepLabv3Plus.py:65: stride 4), fused kernels against F.interpolate(align_corners=True) + the full-resolution
+    kernels; both produce loss + confusion matrix forward and the gradient w.r.t. the low-resolution logits."""
+    import torch.nn.functional as F
+    exp = experiment_of(classes)
+    h_out, w_out = (args.height + 31) // 32 * 32, args.width          # the models' input size (544 x 960: a multiple of 32)
+    h_lo, w_lo = h_out // stride, w_out // stride
+    g = torch.Generator(device=device).manual_seed(5)
+    # trained-like: blocky coarse label map, logits confident about a 10 % noisy copy of it
+    coarse = torch.randint(0, classes, (batch, h_lo, w_lo), generator=g, device=device)
+    coarse = coarse // 3 * 3 % classes if classes > 8 else coarse
+    y = F.interpolate(coarse[:, None].float(), size=(h_out, w_out), mode="nearest")[:, 0].long()
+    noisy = coarse.clone()
+    flips = torch.rand((batch, h_lo, w_lo), generator=g, device=device) < 0.10
+    noisy[flips] = torch.randint(0, classes, (int(flips.sum()),), generator=g, device=device)
+    low = (6.0 * F.one_hot(noisy, classes).permute(0, 3, 1, 2).float()
+           + torch.randn((batch, classes, h_lo, w_lo), generator=g, device=device)).contiguous().requires_grad_(True)
+    meter = b200.SegmentationMeter(exp, classes, device)
+
+    def fused():
+        meter.reset()
+        low.grad = None
+        loss = b200.lovasz_softmax_upsampled(low, y, confusion=meter.cm, confusion_drop_label=None, status=meter.status)
+        loss.backward()
+        return loss
+
+    def unfused():
+        meter.reset()
+        low.grad = None
+        full = F.interpolate(low, size=(h_out, w_out), mode="bilinear", align_corners=True)
+        loss = b200.lovasz_softmax(full, y, confusion=meter.cm, confusion_drop_label=None, status=meter.status)
+        loss.backward()
+        return loss
+
+    ms_f = _device_time(fused, steps, 3, torch.cuda.synchronize)
+    lf = float(fused().detach())
+    cm_f = meter.cm.clone()
+    ms_u = _device_time(unfused, steps, 3, torch.cuda.synchronize)
+    lu = float(unfused().detach())
+    assert lf == lu and torch.equal(cm_f, meter.cm), "fused upsampling differs from interpolate + loss"
+    px = batch * h_out * w_out
+    out = {"name": name, "dist": "trained-like", "classes": classes, "batch": batch, "low_res": [h_lo, w_lo],
+           "size": [h_out, w_out], "steps": steps, "ms_per_step": ms_f, "value": px / (ms_f * 1e-3) / 1e6, "unit": UNIT,
+           "interpolate_then_loss_ms_per_step": ms_u, "speedup_vs_interpolate_then_loss": ms_u / ms_f, "loss": lf}
+    del low, y, meter, coarse, noisy
+    torch.cuda.empty_cache()
+    return out
+
+
 def sweep_time(b200, args, device, frames_rank, world, barrier):
     """Confusion-matrix sweep (managers/BaseManager.py:640-688 of the reference: t_get_confusion_matrix per frame, summed):
     frames_rank frames on this rank in batches of --sweep-batch, int32 labels as the managers pass them, ONE all-reduce of
@@ -555,6 +605,9 @@ def main():
             if (dist_, cc, pi) == (args.dist, c, args.per_image):
                 continue
             cfgs.append(measure_config(b200, args, device, name, dist_, cc, pi, args.batch, min(args.steps, 20), hbm))
+        for name, stride in (("fused_upsample_stride8_c25 (SURVEY F2, OCRNet geometry)", 8),
+                             ("fused_upsample_stride4_c25 (SURVEY F2, DeepLabv3+ geometry)", 4)):
+            cfgs.append(measure_upsampled(b200, args, device, name, stride, 25, args.batch, min(args.steps, 10)))
         frames = 512
         sms, smiou = sweep_time(b200, args, device, frames, 1, torch.cuda.synchronize)
         spx = frames * args.height * args.width
