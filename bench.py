@@ -292,7 +292,7 @@ def measure_upsampled(b200, args, device, name, stride, classes, batch, steps):
     def fused():
         meter.reset()
         low.grad = None
-        loss = b200.lovasz_softmax_upsampled(low, y, confusion=meter.cm, confusion_drop_label=None, status=meter.status)
+        loss = b200.lovasz_softmax_upsampled(low, y, confusion=meter.cm, confusion_drop_label=meter.drop_label, status=meter.status)
         loss.backward()
         return loss
 
@@ -300,7 +300,7 @@ def measure_upsampled(b200, args, device, name, stride, classes, batch, steps):
         meter.reset()
         low.grad = None
         full = F.interpolate(low, size=(h_out, w_out), mode="bilinear", align_corners=True)
-        loss = b200.lovasz_softmax(full, y, confusion=meter.cm, confusion_drop_label=None, status=meter.status)
+        loss = b200.lovasz_softmax(full, y, confusion=meter.cm, confusion_drop_label=meter.drop_label, status=meter.status)
         loss.backward()
         return loss
 

@@ -192,6 +192,82 @@ def main():
         timing[tag] = {"step_ms": e0.elapsed_time(e1) / args.steps, "wall_ms": wall, "loss_forward_ms": lf,
                        "backward_all_ms": bw, "optimizer+metrics_ms": mt}
     out["timing"] = timing
+
+    # ---- the same step with the model's final F.interpolate (models/OCR.py:126-131) folded into the loss kernels ----
+    # The model stops at its stride-8 logits (the six calls below are OCR.py:110-125); CE + Lovasz + confusion matrix are
+    # computed from them by lovasz_softmax_upsampled, whose backward returns the gradient at stride 8.
+    if world == 1 and args.loss == "wrapper":
+        from miccai2021_cataract_semantic_segmentation_b200.fused import ce_ignore_index
+
+        def forward_low(m, x):
+            feats = m.backbone(x)
+            interm_ = m.interm_prediction_head(feats["low"])
+            hi = m.conv_high_map(feats["high"])
+            ctx = m.spatial_gather(hi, interm_)
+            return m.conv_out(m.spatial_ocr_head(hi, ctx))
+
+        ign = ce_ignore_index(exp)
+        meter = b200.SegmentationMeter(exp, c, device)
+        lbl64 = lbl.long()
+        # parity of the fused step against the reference loss on the upsampled logits (same weights, same batch)
+        for p_ in model.parameters():
+            p_.grad = None
+        low = forward_low(model, img)
+        low.retain_grad()
+        lov, ce = b200.lovasz_softmax_upsampled(low, lbl64, ce_ignore_index=ign, confusion=meter.cm,
+                                                confusion_drop_label=meter.drop_label, status=meter.status)
+        (lov + ce).backward()
+        g_fused = low.grad.clone()
+        for p_ in model.parameters():
+            p_.grad = None
+        low2 = forward_low(model, img)
+        low2.retain_grad()
+        full = torch.nn.functional.interpolate(low2, size=img.shape[-2:], mode="bilinear", align_corners=True)
+        ref_total = loss_call(ref_loss, args.loss, None, full, lbl)
+        ref_total.backward()
+        cm_ref = _RefUtils.t_get_confusion_matrix(full.detach(), lbl)
+        out["fused_upsample"] = {
+            "loss_rel_err": abs(float((lov + ce).detach()) - float(ref_total.detach())) / abs(float(ref_total.detach())),
+            "dlowres_rel_err": rel(g_fused, low2.grad),
+            "confusion_matrix_equal": bool(torch.equal(meter.cm, cm_ref.long())),
+            "low_res": list(low.shape[-2:])}
+        del low, low2, full, g_fused
+        torch.cuda.empty_cache()
+
+        def step_fused(detail):
+            opt.zero_grad(set_to_none=True)
+            t = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            meter.reset()
+            low_ = forward_low(model, img)
+            t[0].record()
+            lov_, ce_ = b200.lovasz_softmax_upsampled(low_, lbl64, ce_ignore_index=ign, confusion=meter.cm,
+                                                      confusion_drop_label=meter.drop_label, status=meter.status)
+            total = lov_ + ce_
+            t[1].record()
+            total.backward()
+            t[2].record()
+            opt.step()
+            meter.summary()
+            t[3].record()
+            if detail:
+                torch.cuda.synchronize()
+                return t[0].elapsed_time(t[1]), t[1].elapsed_time(t[2]), t[2].elapsed_time(t[3])
+            return None
+
+        for _ in range(2):
+            step_fused(False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_fused(False)
+        e1.record()
+        torch.cuda.synchronize()
+        lf, bw, mt = step_fused(True)
+        timing["b200_fused_upsample"] = {"step_ms": e0.elapsed_time(e1) / args.steps, "loss_forward_ms": lf,
+                                         "backward_all_ms": bw, "optimizer+metrics_ms": mt,
+                                         "note": "model stops at stride-8 logits; the intermediate head's unused upsampling "
+                                                 "(LossWrapper ignores interm_prediction) is not computed either"}
     out["config"] = {"model": "OCRNet resnet50 random init out_stride 8", "loss": args.loss, "experiment": exp, "batch_per_gpu": args.batch,
                      "size": [args.height, args.width], "world": world, "ddp": world > 1, "anomaly_mode": True,
                      "reference_root": os.path.basename(root.rstrip("/")), "rebound_modules": sorted(rebound)}
