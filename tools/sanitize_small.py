@@ -50,4 +50,19 @@ for (n, c, h, w) in [(2, 25, 32, 48), (1, 12, 21, 19)]:
         lo.backward()
     torch.cuda.synchronize()
     print("sliding / ohem", n, c, h, w, float(m.mean()), float(lo.detach()))
+# fused bilinear upsampling: both emission paths, per-image, fused cross entropy, stride-like and odd geometries
+for (n, c, h, w, H, W, kw) in [(2, 25, 9, 12, 72, 96, {}), (2, 17, 16, 16, 64, 64, {"per_image": True}),
+                               (1, 8, 5, 7, 33, 64, {"ce_ignore_index": None}), (1, 25, 1, 6, 8, 32, {})]:
+    low = (torch.randn((n, c, h, w), generator=g) * 3).cuda().requires_grad_(True)
+    yu = torch.randint(0, c, (n, H, W), generator=g).cuda()
+    cmu = torch.zeros((c, c), dtype=torch.int64, device="cuda")
+    stu = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for path in (1, 2):
+        _native.set_tuning(emit_path=path)
+        res = b200.lovasz_softmax_upsampled(low, yu, confusion=cmu, status=stu, **kw)
+        tot = res[0] + res[1] if isinstance(res, tuple) else res
+        tot.backward()
+        torch.cuda.synchronize()
+    print("upsampled", n, c, h, w, H, W, kw, float(tot.detach()), float(low.grad.abs().max()))
+_native.set_tuning(emit_path=0)
 print("done")
