@@ -2351,7 +2351,7 @@ static bool fill_params(LovaszParams& p, const LovaszLayout& L, char* ws, const 
                         int32_t n, int32_t c, int64_t hw, int32_t per_image, int64_t filter_label,
                         int32_t keep_absent, uint32_t class_mask) {
     p.logits = logits; p.labels = labels;
-    p.up = UpSrc{nullptr, 0, 0, 0, 0, 0.f, 0.f};
+    p.up = UpSrc{nullptr, 0, 0, 0, 0, 0.f, 0.f, 1};
     p.N = n; p.C = c; p.HW = hw; p.P = (long long)n * hw;
     p.inv_hw = hw >= 2 ? (u32)((1ull << 32) / (unsigned long long)hw) : 0xFFFFFFFFu;
     p.per_image = per_image ? 1 : 0;

@@ -30,6 +30,23 @@ __device__ __forceinline__ int up_first_row(const UpSrc& u, int k) {
     return y;
 }
 
+// Work item -> (image, strip, source-row interval, output rows [ya, yb)); false when the item is empty.
+struct UpItem { int n, sx, k, ya, yb; };
+__device__ __forceinline__ u32 up_item_count(const UpSrc& u, int N) { return (u32)(u.W / 32) * (u32)u.h * (u32)u.jmax * (u32)N; }
+__device__ __forceinline__ bool up_item(const UpSrc& u, u32 item, UpItem& it) {
+    const u32 nsx = (u32)(u.W / 32);
+    it.sx = (int)(item % nsx);
+    u32 t = item / nsx;
+    const int j = (int)(t % (u32)u.jmax);
+    t /= (u32)u.jmax;
+    it.k = (int)(t % (u32)u.h);
+    it.n = (int)(t / (u32)u.h);
+    const int y0 = up_first_row(u, it.k), y1 = up_first_row(u, it.k + 1);
+    it.ya = y0 + j * UP_ROWS_MAX;
+    it.yb = min(y1, it.ya + UP_ROWS_MAX);
+    return it.ya < it.yb;
+}
+
 // horizontal interpolation of source row `ys` of image n for the strip's 32 output columns: Hd[c][lane]
 template <int CT>
 __device__ __forceinline__ void up_fill_row(float (*Hd)[32], const float* __restrict__ img, int ys, const UpSrc& u,
@@ -61,7 +78,7 @@ __global__ void __launch_bounds__(TPB) stats_kernel_up(LovaszParams p) {
     __syncthreads();
 
     const UpSrc u = p.up;
-    const u32 nsx = (u32)(u.W / 32), items = nsx * (u32)u.h * (u32)p.N;
+    const u32 items = up_item_count(u, p.N);
     const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
     const size_t img_lo = (size_t)CT * u.h * u.w;
 
@@ -84,16 +101,15 @@ __global__ void __launch_bounds__(TPB) stats_kernel_up(LovaszParams p) {
     ExpConsts ek;
     ek.load();
     for (u32 item = gw; item < items; item += nwarps) {
-        const u32 sx = item % nsx, t = item / nsx;
-        const int k = (int)(t % (u32)u.h), n = (int)(t / (u32)u.h);
-        const int y0 = up_first_row(u, k), y1 = up_first_row(u, k + 1);
-        if (y0 >= y1) continue;                            // (warp-uniform) no output row has this upper source row
+        UpItem wi;
+        if (!up_item(u, item, wi)) continue;               // (warp-uniform: no output row of this chunk has this upper source row)
+        const int sx = wi.sx, k = wi.k, n = wi.n, y0 = wi.ya, y1 = wi.yb;
         const int g = p.per_image ? n : 0;
         if (g != cur_g) {
             if (cur_g >= 0) { flush_group(cur_g, A.nvalid); A.nvalid = 0; }
             cur_g = g;
         }
-        const int X = (int)sx * 32 + lane;
+        const int X = sx * 32 + lane;
         const UpAxis ax = up_axis(u.rx, X, u.w);
         const float* img = u.lo + (size_t)n * img_lo;
         const int k1 = k + ((k < u.h - 1) ? 1 : 0);
@@ -158,15 +174,14 @@ __global__ void __launch_bounds__(TPB) emit_kernel_up(LovaszParams p) {
     typedef float Tile[CT][32];
     Tile* tiles = reinterpret_cast<Tile*>(pipe_smem_raw) + (size_t)warp * 3;     // H0, H1, T
     const UpSrc u = p.up;
-    const u32 nsx = (u32)(u.W / 32), items = nsx * (u32)u.h * (u32)p.N;
+    const u32 items = up_item_count(u, p.N);
     const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
     const size_t img_lo = (size_t)CT * u.h * u.w;
     int cur_g = -1;
     for (u32 item = gw; item < items; item += nwarps) {
-        const u32 sx = item % nsx, t = item / nsx;
-        const int k = (int)(t % (u32)u.h), n = (int)(t / (u32)u.h);
-        const int y0 = up_first_row(u, k), y1 = up_first_row(u, k + 1);
-        if (y0 >= y1) continue;
+        UpItem wi;
+        if (!up_item(u, item, wi)) continue;               // (warp-uniform: no output row of this chunk has this upper source row)
+        const int sx = wi.sx, k = wi.k, n = wi.n, y0 = wi.ya, y1 = wi.yb;
         const int g = p.per_image ? n : 0;
         if (g != cur_g) {
             __syncwarp();
@@ -174,7 +189,7 @@ __global__ void __launch_bounds__(TPB) emit_kernel_up(LovaszParams p) {
             cur_g = g;
             __syncwarp();
         }
-        const int X = (int)sx * 32 + lane;
+        const int X = sx * 32 + lane;
         const UpAxis ax = up_axis(u.rx, X, u.w);
         const float* img = u.lo + (size_t)n * img_lo;
         const int k1 = k + ((k < u.h - 1) ? 1 : 0);
@@ -219,7 +234,7 @@ __global__ void __launch_bounds__(TPB, 3) backward_kernel_up(LovaszParams p, con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     UpBwdSmem<CT>& S = reinterpret_cast<UpBwdSmem<CT>*>(pipe_smem_raw)[warp];
     const UpSrc u = p.up;
-    const u32 nsx = (u32)(u.W / 32), items = nsx * (u32)u.h * (u32)p.N;
+    const u32 items = up_item_count(u, p.N);
     const u32 gw = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
     const size_t img_lo = (size_t)CT * u.h * u.w, pl_lo = (size_t)u.h * u.w;
     const float gsc = __ldg(go);
@@ -228,10 +243,9 @@ __global__ void __launch_bounds__(TPB, 3) backward_kernel_up(LovaszParams p, con
     int cur_g = -1;
 
     for (u32 item = gw; item < items; item += nwarps) {
-        const u32 sx = item % nsx, t = item / nsx;
-        const int k = (int)(t % (u32)u.h), n = (int)(t / (u32)u.h);
-        const int y0 = up_first_row(u, k), y1 = up_first_row(u, k + 1);
-        if (y0 >= y1) continue;
+        UpItem wi;
+        if (!up_item(u, item, wi)) continue;               // (warp-uniform: no output row of this chunk has this upper source row)
+        const int sx = wi.sx, k = wi.k, n = wi.n, y0 = wi.ya, y1 = wi.yb;
         const int g = p.per_image ? n : 0;
         if (g != cur_g) {
             __syncwarp();
@@ -239,7 +253,7 @@ __global__ void __launch_bounds__(TPB, 3) backward_kernel_up(LovaszParams p, con
             cur_g = g;
             __syncwarp();
         }
-        const int X = (int)sx * 32 + lane;
+        const int X = sx * 32 + lane;
         const UpAxis ax = up_axis(u.rx, X, u.w);
         const float* img = u.lo + (size_t)n * img_lo;
         const int k1 = k + ((k < u.h - 1) ? 1 : 0);

@@ -14,7 +14,10 @@ struct UpSrc {
     const float* lo;     // [N, C, h, w] low-resolution logits; nullptr = the kernels read full-resolution logits
     int h, w, H, W;
     float ry, rx;        // (h - 1) / (H - 1), (w - 1) / (W - 1), fp32 division of the converted integers (0 when H or W is 1)
+    int jmax;            // work items per (strip, source-row interval): an interval's rows are walked in chunks of UP_ROWS_MAX
 };
+#define UP_ROWS_MAX 32   // output rows per work item at most (bounds the sequential fp32 accumulation of the backward pass and
+                         // keeps the warps busy when the source has very few rows)
 
 struct UpAxis {
     int i0, i1;          // the two source indices (i1 = i0 at the far edge)
@@ -109,5 +112,9 @@ static inline UpSrc make_up_src(const float* lo, int h, int w, int H, int W) {
     // ATen: area_pixel_compute_scale<float>(in, out, align_corners = true) = out > 1 ? (float)(in - 1) / (out - 1) : 0
     u.ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
     u.rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    // output rows that share one upper source row: at most floor(1 / ry) + 1 (+1 for the fp32 rounding of ry * Y)
+    const long long per_interval = u.ry > 0.f ? (long long)(1.0f / u.ry) + 2 : (long long)H;
+    u.jmax = (int)((per_interval + UP_ROWS_MAX - 1) / UP_ROWS_MAX);
+    if (u.jmax < 1) u.jmax = 1;
     return u;
 }

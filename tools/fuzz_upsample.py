@@ -2,7 +2,8 @@
 """Randomised sweep of the fused bilinear upsampling + Lovasz path on a GPU box: random low-resolution / output geometries,
 class counts, modes, label dtypes, emission paths and logit styles.  Per case: the in-kernel interpolation equals ATen's bit
 for bit; loss (1e-6) and confusion matrix (exact) equal F.interpolate + the full-resolution kernels; the low-resolution gradient
-agrees to 1e-5 of its maximum; every fourth case is also checked against oracle/port.py on the upsampled logits.
+agrees with the float64 adjoint of the
+full-resolution gradient to 1e-5 of its maximum (and with ATen's fp32 result within ATen's own distance from that referee); every fourth case is also checked against oracle/port.py on the upsampled logits.
     python tools/fuzz_upsample.py [n_cases] [seed]"""
 import os, sys
 import numpy as np
@@ -18,6 +19,7 @@ n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 lib = _native.load()
 bad = 0
+worst_f = worst_a = 0.0
 for case in range(n_cases):
     c, exp = [(8, 1), (17, 2), (25, 3)][rng.randint(3)]
     n = int(rng.randint(1, 4))
@@ -67,8 +69,9 @@ for case in range(n_cases):
         lf = lowd.clone().requires_grad_(True)
         loss_f = b200.lovasz_softmax_upsampled(lf, yd, confusion=cm_f, confusion_drop_label=drop, status=st_f, **kw)
         lu = lowd.clone().requires_grad_(True)
-        loss_u = b200.lovasz_softmax(F.interpolate(lu, size=(H, W), mode="bilinear", align_corners=True), yd, confusion=cm_u,
-                                     confusion_drop_label=drop, status=st_u, **kw)
+        full = F.interpolate(lu, size=(H, W), mode="bilinear", align_corners=True)
+        full.retain_grad()
+        loss_u = b200.lovasz_softmax(full, yd, confusion=cm_u, confusion_drop_label=drop, status=st_u, **kw)
         a, b = float(loss_f.detach()), float(loss_u.detach())
         assert abs(a - b) <= 1e-6 * max(abs(b), 1e-30), f"loss {a} vs {b}"
         assert torch.equal(cm_f, cm_u) and int(st_f) == int(st_u), "confusion matrix / status differ"
@@ -76,8 +79,23 @@ for case in range(n_cases):
             loss_f.backward(); loss_u.backward()
             gmax = float(lu.grad.abs().max())
             if gmax > 0:
-                err = float((lf.grad - lu.grad).abs().max()) / gmax
-                assert err <= 1e-5, f"gradient error {err}"
+                # the referee: float64 adjoint of the interpolation applied to the (bit-identical) full-resolution gradient;
+                # ATen's own fp32 atomics drift from it by up to ~2e-5 when a low-resolution cell collects 10^4 pixels
+                l64 = lowd.double().requires_grad_(True)
+                F.interpolate(l64, size=(H, W), mode="bilinear", align_corners=True).backward(full.grad.double())
+                # scale: the largest gradient, but not less than 1 % of the largest sum of |terms| a cell collects (a 1 x 1
+                # source makes the true gradient cancel to ~0, where an error relative to it means nothing)
+                a64 = lowd.double().requires_grad_(True)
+                F.interpolate(a64, size=(H, W), mode="bilinear", align_corners=True).backward(full.grad.abs().double())
+                scale = max(gmax, 0.01 * float(a64.grad.max()))
+                e_f = float((lf.grad.double() - l64.grad).abs().max()) / scale
+                e_a = float((lu.grad.double() - l64.grad).abs().max()) / scale
+                worst_f, worst_a = max(worst_f, e_f), max(worst_a, e_a)
+                # (the referee forms its weights in float64: where h ~ H their fp32 rounding alone moves both fp32 results by
+                # ~1e-5, identically -- hence the second alternative)
+                assert e_f <= 1e-5 or e_f <= 1.1 * e_a, f"gradient error vs the float64 adjoint {e_f} (ATen's: {e_a})"
+                err = float((lf.grad - lu.grad).abs().max()) / scale
+                assert err <= 1e-5 + 1.5 * e_a, f"gradient error vs ATen {err} (ATen vs float64: {e_a})"
         if case % 4 == 0 and not kw.get("keep_absent"):
             lo = lowd.clone().requires_grad_(True)
             ref = port.lovasz_softmax(F.interpolate(lo, size=(H, W), mode="bilinear", align_corners=True), yd.long(), exp,
@@ -88,5 +106,5 @@ for case in range(n_cases):
         bad += 1
         print(tag, "FAILED:", repr(e)[:300])
 _native.set_tuning(emit_path=0, sort_path=0)
-print(f"{n_cases} cases, {bad} bad")
+print(f"{n_cases} cases, {bad} bad; worst gradient error against the float64 adjoint: fused {worst_f:.2e}, ATen fp32 {worst_a:.2e}")
 sys.exit(1 if bad else 0)
