@@ -53,6 +53,30 @@ def test_no_cpu_fallback(native):
         b200.t_get_confusion_matrix(x, y)
 
 
+def test_fused_upsampling_host_logic(native):
+    """b200seg_lovasz_up_supported is pure host logic: the reference's two geometries are covered, the rest falls
+    back; the Python entry validates shapes and refuses CPU tensors like every other op."""
+    import miccai2021_cataract_semantic_segmentation_b200 as b200
+    lib = native.load()
+    assert lib.b200seg_lovasz_up_supported(8, 25, 68, 120, 544, 960) == 1      # OCRNet, stride 8 (models/OCR.py:126)
+    assert lib.b200seg_lovasz_up_supported(8, 25, 136, 240, 544, 960) == 1     # DeepLabv3+, stride 4 (DeepLabv3Plus.py:65)
+    assert lib.b200seg_lovasz_up_supported(8, 17, 68, 120, 540, 960) == 1
+    assert lib.b200seg_lovasz_up_supported(1, 8, 1, 1, 8, 32) == 1
+    assert lib.b200seg_lovasz_up_supported(8, 25, 272, 480, 544, 960) == 0     # scale 2: a strip touches too many source columns
+    assert lib.b200seg_lovasz_up_supported(8, 25, 68, 120, 544, 950) == 0      # W % 32 != 0
+    assert lib.b200seg_lovasz_up_supported(8, 12, 68, 120, 544, 960) == 0      # no templated kernel for 12 classes
+    assert lib.b200seg_lovasz_up_supported(8, 25, 0, 120, 544, 960) == 0
+    assert lib.b200seg_lovasz_up_forward(None, 68, 120, None, 2, 8, 25, 544, 960, 0, native.NO_LABEL, 0, (1 << 25) - 1, 1, None, 0,
+                                         None, 0, native.NO_LABEL, None, None, native.NO_LABEL, None, None) != 0
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        b200.LovaszSoftmaxUpsampled({"experiment": 1})(torch.zeros(1, 8, 4, 4), torch.zeros(1, 32, 32, dtype=torch.int64))
+    with pytest.raises(ValueError):
+        b200.lovasz_softmax_upsampled(torch.zeros(1, 8, 4, 4), torch.zeros(2, 32, 32, dtype=torch.int64))
+    mod = b200.LovaszSoftmaxUpsampled({"experiment": 3, "per_image": True, "classes_to_ignore": 25})
+    ref = b200.LovaszSoftmax({"experiment": 3, "per_image": True, "classes_to_ignore": 25})
+    assert (mod.num_classes, mod.per_image, mod.classes_to_ignore) == (ref.num_classes, True, 25) and not list(mod.parameters())
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "miccai2021_cataract_semantic_segmentation_b200")
     for dirpath, _, files in os.walk(pkg):
