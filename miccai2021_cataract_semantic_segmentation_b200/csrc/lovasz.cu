@@ -380,8 +380,11 @@ struct StatsAcc {
     float ce_acc = 0.f;
 };
 template <int CT, int WT>
-__device__ __forceinline__ void stats_pixel(const LovaszParams& p, const float (*T)[WT], int lane, int lab, size_t px,
+__device__ __forceinline__ void stats_pixel(const LovaszParams& p, const float (*T)[WT], int lane, int lab_in, size_t px,
                                             u32* s_fg_w, u32* s_key_w, u32* s_cm, const ExpConsts& ek, StatsAcc& A) {
+    int lab = lab_in;
+    asm volatile("" : "+r"(lab));                          // a plain 32-bit value from here on: without this the compiler compares
+                                                           // the 64-bit label it was narrowed from, two ISETPs per class
     float z[CT];
 #pragma unroll
     for (int c = 0; c < CT; ++c) z[c] = T[c][lane];
@@ -389,14 +392,15 @@ __device__ __forceinline__ void stats_pixel(const LovaszParams& p, const float (
 #pragma unroll
     for (int c = 1; c < CT; ++c) m = fmaxf(m, z[c]);
     // softmax denominator (ascending class order, like ATen) and the three largest exps among the other classes:
-    // exps are positive, so their bit patterns order like integers; the class index rides in the low byte
+    // exps are positive, so their bit patterns order like integers; 31 - class rides in the low byte (of equal exps the
+    // lowest class wins: b1 then also yields torch's first-maximum argmax, see below)
     float s = 0.f;
     int b1 = -1, b2 = -1, b3 = -1;
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
         const float e = sm_exp_k(z[c], m, ek);
         s = __fadd_rn(s, e);
-        int v = (int)__byte_perm(__float_as_uint(e), (u32)c, 0x3214);   // low byte <- class (one PRMT)
+        int v = (int)__byte_perm(__float_as_uint(e), (u32)(31 - c), 0x3214);   // low byte <- 31 - class (one PRMT)
         v = (c == lab) ? -1 : v;
         const int t1v = min(b1, v); b1 = max(b1, v);
         const int t2v = min(b2, t1v); b2 = max(b2, t1v);
@@ -416,7 +420,7 @@ __device__ __forceinline__ void stats_pixel(const LovaszParams& p, const float (
         }
     }
     {
-        const int c1 = b1 & 31, c2 = b2 & 31;          // CT >= 4: b1..b3 are real classes
+        const int c1 = 31 - (b1 & 31), c2 = 31 - (b2 & 31);   // CT >= 4: b1..b3 are real classes
         const float p1 = sm_prob(T[c1][lane], m, s), p2 = sm_prob(T[c2][lane], m, s);
         const float p3 = __fdiv_ru(__uint_as_float((u32)b3 | 255u), s);  // >= p of every class not recorded
         p.rec16[px] = make_uint4(kfg, __float_as_uint(p1), __float_as_uint(p2), __float_as_uint(p3));
@@ -424,14 +428,20 @@ __device__ __forceinline__ void stats_pixel(const LovaszParams& p, const float (
     }
     if (p.cm && !(p.has_drop && lab == p.drop)) {
         if ((unsigned)lab < (unsigned)CT) {
-            int arg = 0;
-#pragma unroll
-            for (int c = CT - 1; c >= 0; --c) arg = (z[c] == m) ? c : arg;          // first maximum
-            if (s != s || m != m) {                   // NaN / inf among the logits: torch's argmax lets NaN win
-                float best = z[0];
+            // torch's argmax (first maximum) without a pass over the classes: the maximum's exponential is exactly 1.0, so
+            // among the other classes it is b1's class (ties go to the lowest class through the low byte) unless a SECOND
+            // other class also has exponential 1.0 -- a logit within an ulp of the maximum rounds to 1.0 as well -- or NaN /
+            // inf are around; those pixels (~1e-6 of them) take the plain loop.  The own class competes by its exact logit.
+            const int cb = 31 - (b1 & 31);
+            int arg;
+            if (((u32)b2 >> 8) == (ONE_BITS >> 8) || s != s || m != m) {
+                float best = T[0][lane];
                 arg = 0;
 #pragma unroll
-                for (int c = 1; c < CT; ++c) argmax_step(z[c], c, best, arg);
+                for (int c = 1; c < CT; ++c) argmax_step(T[c][lane], c, best, arg);   // NaN wins, like torch
+            } else {
+                const bool own_max = T[lab][lane] == m, cb_max = T[cb][lane] == m;
+                arg = (own_max && (!cb_max || lab < cb)) ? lab : cb;
             }
             atomicAdd(&s_cm[arg * CT + lab], 1u);
         } else A.oob = 1;

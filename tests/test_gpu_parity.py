@@ -498,6 +498,41 @@ def test_large_batch_parity_with_the_oracle_on_device(b200):
     assert float((grad - ref_grad).abs().max()) <= GRAD_RTOL * float(ref_grad.abs().max())
 
 
+@pytest.mark.parametrize("c,exp", [(8, 1), (17, 2), (25, 3)])
+def test_fused_argmax_on_near_ties(b200, c, exp):
+    """The fused confusion matrix takes torch.argmax (first maximum) from the top-3 search of the stats kernel; logits within
+    an ulp of the maximum have exponential exactly 1.0 too and must not be mistaken for it (torch_utils.py:221-241 after
+    managers/OCRNet_Manager.py:108: argmax, then the matrix).  Pixels: two or three classes at v, v - 1 ulp, v - 2 ulp in every
+    order, exact ties, the pixel's own class among them or not, NaN and inf pixels."""
+    n, h, w = 2, 64, 96
+    g = torch.Generator(device="cuda").manual_seed(31 + c)
+    x = torch.randn((n, c, h, w), generator=g, device="cuda") * 0.1 - 5.0
+    P = n * h * w
+    v = torch.rand(P, generator=g, device="cuda") * 0.4 + 0.01
+    down1 = torch.nextafter(v, torch.full_like(v, -1.0))
+    down2 = torch.nextafter(down1, torch.full_like(v, -1.0))
+    vals = torch.stack([v, down1, down2, v], 1)                          # candidates for the three special classes
+    perm = torch.rand(P, c, generator=g, device="cuda").argsort(1)[:, :3]  # three distinct classes per pixel
+    pick = torch.randint(0, 4, (P, 3), generator=g, device="cuda")
+    xf = x.permute(0, 2, 3, 1).reshape(P, c).clone()
+    xf.scatter_(1, perm, torch.gather(vals, 1, pick))
+    xf[:50, 3] = float("nan")                                           # NaN wins in torch.argmax
+    xf[50:100, 1] = float("inf")
+    x = xf.view(n, h, w, c).permute(0, 3, 1, 2).contiguous()
+    y = torch.randint(0, c, (n, h, w), generator=g, device="cuda")
+    yf = y.view(-1)
+    own = torch.rand(P, generator=g, device="cuda") < 0.5                # half the pixels are labelled with one of the special classes
+    yf[own] = perm[own, torch.randint(0, 3, (int(own.sum()),), generator=g, device="cuda")]
+    meter = b200.SegmentationMeter(exp, c)
+    with torch.no_grad():
+        b200.LovaszSoftmaxWithMetrics({"experiment": exp}, meter)(x, y)
+    ref = torch.bincount((x.argmax(1) * c + y).flatten(), minlength=c * c).view(c, c)
+    assert torch.equal(meter.cm, ref)
+    # the standalone confusion-matrix kernel (its own argmax loop) on the same pixels
+    cm2 = b200.t_get_confusion_matrix(x, y.int())
+    assert torch.equal(cm2.long(), ref)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the softmax the kernels form is ATen's CUDA softmax, bit for bit (DESIGN.md section 2)
 # ---------------------------------------------------------------------------------------------------------------
