@@ -2738,7 +2738,7 @@ static int lovasz_backward_impl(const float* logits, const void* labels, int32_t
         CUDA_TRY(cudaFuncSetAttribute(backward_kernel_up<CC, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       (int)smem));                                                                \
         int per_sm = (int)((224 * 1024) / (smem + 2048));                                                         \
-        if (per_sm > 3) per_sm = 3;                                                                               \
+        if (per_sm > 4) per_sm = 4;                                                                               \
         backward_kernel_up<CC, TT><<<sms * per_sm, TT, smem, st>>>(p, grad_out, grad_ce, dlogits);                \
     }
         if (c == 8) LAUNCH_BWD_UP(8)

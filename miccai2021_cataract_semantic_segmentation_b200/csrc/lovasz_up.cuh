@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(TPB) emit_kernel_up(LovaszParams p) {
 // ---- K6 -----------------------------------------------------------------------------------------------------------------------
 template <int CT>
 struct UpBwdSmem {
-    float H0[CT][32], H1[CT][32];
-    float T[CT][32], D[CT][32];                            // logits / gradient of the row; reused as the transposed staging of a flush
+    float H0[CT][32], H1[CT][32];                          // horizontally interpolated source rows; reused as the staging of a flush
+    float T[CT][32];                                       // logits of the row; exact gradients replace the logits of their classes
     float wt[UP_MAX_COLS][32];                             // horizontal weight of lane j's column for source column xs + i
     float thr[B200SEG_MAX_CLASSES];
     unsigned char jlo[UP_MAX_COLS], jhi[UP_MAX_COLS];     // lanes [jlo, jhi) touch the column
@@ -225,11 +225,11 @@ struct UpBwdSmem {
 };
 
 template <int CT, int TPB>
-__global__ void __launch_bounds__(TPB, 3) backward_kernel_up(LovaszParams p, const float* __restrict__ go,
+__global__ void __launch_bounds__(TPB, 4) backward_kernel_up(LovaszParams p, const float* __restrict__ go,
                                                               const float* __restrict__ go_ce, float* __restrict__ dlow) {
     constexpr int NW = TPB / 32;
     constexpr int PS = 33;                                 // row stride of the flush staging (bank-conflict-free columns)
-    static_assert(2 * CT * 32 >= CT * PS, "staging fits T + D");
+    static_assert(2 * CT * 32 >= CT * PS, "staging fits H0 + H1");
     extern __shared__ __align__(16) unsigned char pipe_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     UpBwdSmem<CT>& S = reinterpret_cast<UpBwdSmem<CT>*>(pipe_smem_raw)[warp];
@@ -262,7 +262,6 @@ __global__ void __launch_bounds__(TPB, 3) backward_kernel_up(LovaszParams p, con
         const float (*H0)[32] = S.H0;
         const float (*H1)[32] = (k1 != k) ? S.H1 : S.H0;
         float (*T)[32] = S.T;
-        float (*D)[32] = S.D;
         float acc0[CT], acc1[CT];
 #pragma unroll
         for (int c = 0; c < CT; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
@@ -329,11 +328,9 @@ __global__ void __launch_bounds__(TPB, 3) backward_kernel_up(LovaszParams p, con
             }
             const float inv_s = __fdiv_rn(1.0f, s);
             const float nd = (filt ? 0.f : -gsc * d * inv_s) + gcp * inv_s;
-#pragma unroll
-            for (int c = 0; c < CT; ++c) {
-                const float fast = nd * __expf(T[c][lane] - m);
-                D[c][lane] = (c == lab) ? ownv : fast;
-            }
+            // every class gets -go * p_k * dot with the fast exponential; the classes in `exact` take an exact value instead,
+            // which replaces their logit in the tile (each needs only its own logit, read before it is overwritten)
+            u32 exact = cmask_cur;
             if (cmask_cur) {
                 u32 mm = cmask_cur;
                 int i = 0;
@@ -350,20 +347,23 @@ __global__ void __launch_bounds__(TPB, 3) backward_kernel_up(LovaszParams p, con
                             for (int j = 1; j < NX; ++j) gk = (i == 2 + j) ? gx[j] : gk;
                         } else gk = gb[(size_t)c * plane];
                     }
-                    D[c][lane] = gsc * pk * (gk - d) + gcp * pk;
+                    T[c][lane] = gsc * pk * (gk - d) + gcp * pk;
                     ++i;
                 }
             }
-            if (gcp != 0.f && lab < 0) D[ce_lab][lane] = nd * __expf(T[ce_lab][lane] - m) - gcp;
+            if (lab >= 0) { T[lab][lane] = ownv; exact |= 1u << lab; }
+            // cross-entropy only: the label's class is not summed by the Lovasz term, its "- 1" is applied here
+            if (gcp != 0.f && lab < 0) { T[ce_lab][lane] = nd * __expf(T[ce_lab][lane] - m) - gcp; exact |= 1u << ce_lab; }
             if (p.dbg & 256) {                             // debugging aid: the full-resolution gradient, into the dead sort buffer B
                 float* dbg = reinterpret_cast<float*>(p.keysB) + (size_t)n * CT * plane + q;
 #pragma unroll
-                for (int c = 0; c < CT; ++c) dbg[(size_t)c * plane] = D[c][lane];
+                for (int c = 0; c < CT; ++c) dbg[(size_t)c * plane] = ((exact >> c) & 1u) ? T[c][lane] : nd * __expf(T[c][lane] - m);
             }
             // vertical part of the adjoint: this row's gradient goes to source rows k (l0) and k1 (l1)
 #pragma unroll
             for (int c = 0; c < CT; ++c) {
-                const float dv = D[c][lane];
+                const float t = T[c][lane];
+                const float dv = ((exact >> c) & 1u) ? t : nd * __expf(t - m);
                 acc0[c] = fmaf(ay.l0, dv, acc0[c]);
                 acc1[c] = fmaf(ay.l1, dv, acc1[c]);
             }
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(TPB, 3) backward_kernel_up(LovaszParams p, con
             const u32 touch = __ballot_sync(FULL_MASK, hit0 || hit1);
             if (lane == 0) { S.jlo[i] = (unsigned char)(__ffs(touch) - 1); S.jhi[i] = (unsigned char)(32 - __clz(touch)); }
         }
-        float* stg = &S.T[0][0];                                               // [CT][PS], spans T and D
+        float* stg = &S.H0[0][0];                                              // [CT][PS], spans H0 and H1 (dead once the rows are done)
         float* out_n = dlow + (size_t)n * img_lo;
         const int nout = CT * ncols;
 #pragma unroll 1
