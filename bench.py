@@ -355,6 +355,46 @@ def sweep_time(b200, args, device, frames_rank, world, barrier):
     return ms, float(summary[0])
 
 
+def sweep_time_upsampled(b200, args, device, frames, stride=8):
+    """The same sweep when the model hands over its stride-8 logits (models/OCR.py:126-131 not applied): the matrix straight
+    from them (SegmentationMeter.update_upsampled) against F.interpolate(align_corners=True) + update.  -> (ms fused, ms unfused)."""
+    import torch.nn.functional as F
+    c, exp = args.classes, experiment_of(args.classes)
+    h_out, w_out = (args.height + 31) // 32 * 32, args.width
+    bsz = min(args.sweep_batch, frames)
+    g = torch.Generator(device=device).manual_seed(11)
+    low = torch.randn((bsz, c, h_out // stride, w_out // stride), generator=g, device=device)
+    y = torch.randint(0, c + 1, (bsz, h_out, w_out), generator=g, device=device, dtype=torch.int32)
+    nb = frames // bsz
+    out = []
+    mats = []
+    for fused in (True, False):
+        meter = b200.SegmentationMeter(exp, c, device)
+
+        def sweep():
+            meter.reset()
+            for _ in range(nb):
+                if fused:
+                    meter.update_upsampled(low, y)
+                else:
+                    meter.update(F.interpolate(low, size=(h_out, w_out), mode="bilinear", align_corners=True), y)
+            return meter.summary()
+
+        sweep()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sweep()
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1))
+        mats.append(meter.cm.clone())
+    assert torch.equal(mats[0], mats[1]), "confusion matrix from low-resolution logits differs from interpolate + update"
+    del low, y
+    torch.cuda.empty_cache()
+    return out[0], out[1], nb * bsz * h_out * w_out
+
+
 def run_sweep_main(b200, bdist, args, rank, world, local, device):
     """`--sweep-frames F`: the sweep is the main workload (BASELINE configs[4]); a step = one batch of frames."""
     import torch.distributed as dist
@@ -614,6 +654,10 @@ def main():
         cfgs.append({"name": "confmat_sweep_slice (BASELINE configs[4]: 512 of 4096 frames = one GPU's share at N=8)",
                      "frames": frames, "batch": args.sweep_batch, "ms": sms, "value": spx / (sms * 1e-3) / 1e6, "unit": UNIT,
                      "bytes_per_pixel": 4 * c + 4, "roofline_frac": spx * (4 * c + 4) / (sms * 1e-3) / 1e9 / hbm, "miou": smiou})
+        ums_f, ums_u, upx = sweep_time_upsampled(b200, args, device, frames)
+        cfgs.append({"name": "confmat_sweep_slice_from_stride8_logits (SURVEY F2 on the metric path: 512 frames, 68x120 -> 544x960)",
+                     "frames": frames, "batch": args.sweep_batch, "ms": ums_f, "value": upx / (ums_f * 1e-3) / 1e6, "unit": UNIT,
+                     "interpolate_then_confmat_ms": ums_u, "speedup_vs_interpolate_then_confmat": ums_u / ums_f})
         out["configs"] = cfgs
     if world == 1 and not args.no_cpu_baseline:
         cstep, cpx = cpu_step_fn(args, args.cpu_sample_images)

@@ -276,6 +276,16 @@ int b200seg_lovasz_up_backward(const float* lowres, int32_t h, int32_t w, const 
                                size_t workspace_bytes, const float* grad_lovasz, int32_t ce_enabled,
                                int64_t ce_ignore_index, const float* grad_ce, float* dlowres, void* stream);
 
+/* Confusion matrix of (argmax_c upsample(lowres), labels) without the upsampled tensor: the metric-side twin of
+ * b200seg_lovasz_up_forward for the validation loop (managers/OCRNet_Manager.py:161, managers/BaseManager.py:640-688 after
+ * models/OCR.py:126-131).  Same cm / drop_label / status semantics as b200seg_confmat_accumulate; the argmax is the one torch
+ * takes on F.interpolate(lowres, (H, W), mode='bilinear', align_corners=True) (NCHW-contiguous), bit for bit.
+ * Any n_classes <= 32 and any scale; W % 32 == 0 is required (B200SEG_E_UNSUPPORTED otherwise; _supported returns 1 / 0). */
+int b200seg_confmat_up_supported(int32_t n_images, int32_t n_classes, int32_t h, int32_t w, int32_t H, int32_t W);
+int b200seg_confmat_up_accumulate(const float* lowres, int32_t h, int32_t w, const void* labels, int32_t label_dtype,
+                                  int32_t n_images, int32_t n_classes, int32_t H, int32_t W, int64_t drop_label,
+                                  int64_t* cm, int32_t* status, void* stream);
+
 /* Test hook: out[planes, H, W] = bilinear upsampling (align_corners = True) of lowres[planes, h, w] exactly as the fused
  * b200seg_lovasz_up_* kernels compute it (pattern < 0), i.e. bit for bit what F.interpolate gives on the same device
  * (models/OCR.py:126, models/DeepLabv3Plus.py:65); pattern 0..35 selects one of the candidate multiply-add contractions

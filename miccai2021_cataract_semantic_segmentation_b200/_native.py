@@ -39,6 +39,8 @@ SIGNATURES = {
                                               _vp, _sz, _vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp]),
     "b200seg_lovasz_up_backward": (_c.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i32, _u32,
                                                _vp, _sz, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "b200seg_confmat_up_supported": (_c.c_int, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "b200seg_confmat_up_accumulate": (_c.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp]),
     "b200seg_confmat_accumulate": (_c.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp]),
     "b200seg_metrics_from_confmat": (_c.c_int, [_vp, _i32, _u32, _c.POINTER(_u32), _i32, _vp, _vp, _vp]),
     "b200seg_sliding_miou_scratch_bytes": (_c.c_int, [_i32, _i64, _i64, _c.POINTER(_sz)]),

@@ -9,6 +9,7 @@
 // the int64 matrix once at the end.
 #include "b200seg.h"
 #include "common.cuh"
+#include "upsample.cuh"
 
 #define CM_TPB 256
 
@@ -147,6 +148,145 @@ extern "C" int b200seg_confmat_accumulate(const float* prediction, const void* l
         DISPATCH_LABEL(label_dtype, confmat_kernel_generic<LT><<<grid, CM_TPB, 0, st>>>(p));
     }
     LAUNCH_CHECK("confmat_kernel");
+    return 0;
+}
+
+// ---- confusion matrix straight from low-resolution logits (SURVEY 8 F2 applied to the metric path) --------------------------------
+// The validation loop's matrix is t_get_confusion_matrix(model(img), lbl) (managers/OCRNet_Manager.py:161,
+// managers/BaseManager.py:640-688) on logits the model has just upsampled with F.interpolate(align_corners=True)
+// (models/OCR.py:126-131).  This kernel interpolates in shared memory with ATen's arithmetic (upsample.cuh), so the argmax is
+// the one torch would take on the upsampled tensor, and the 4*C bytes per pixel of that tensor are never written or read.
+// Work decomposition as in lovasz_up.cuh: a warp owns (image, strip of 32 columns, source-row interval), interpolates the two
+// source rows horizontally once, then every output row is a vertical mix with a running first-maximum.
+struct ConfmatUpParams {
+    UpSrc up;
+    const void* labels;
+    int N, C;
+    int has_drop, drop;
+    unsigned long long* cm;
+    int* status;
+};
+#define CMU_TPB 128
+template <int CT, typename LT>                             // CT = 0: class count known at run time only
+__global__ void __launch_bounds__(CMU_TPB) confmat_up_kernel(ConfmatUpParams p) {
+    extern __shared__ __align__(16) float cmu_tiles[];
+    __shared__ u32 s_cm[B200SEG_MAX_CLASSES * B200SEG_MAX_CLASSES];
+    const int C = CT ? CT : p.C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* H0 = cmu_tiles + (size_t)warp * 2 * C * 32;
+    float* H1 = H0 + (size_t)C * 32;
+    for (int i = tid; i < C * C; i += CMU_TPB) s_cm[i] = 0;
+    __syncthreads();
+    const UpSrc u = p.up;
+    const u32 items = up_item_count(u, p.N);
+    const u32 gw = blockIdx.x * (CMU_TPB / 32) + warp, nwarps = gridDim.x * (CMU_TPB / 32);
+    const size_t pl = (size_t)u.h * u.w, HW = (size_t)u.H * u.W;
+    u32 oob = 0;
+    for (u32 item = gw; item < items; item += nwarps) {
+        UpItem wi;
+        if (!up_item(u, item, wi)) continue;
+        const int X = wi.sx * 32 + lane;
+        const UpAxis ax = up_axis(u.rx, X, u.w);
+        const float* img = u.lo + (size_t)wi.n * C * pl;
+        const int k1 = wi.k + ((wi.k < u.h - 1) ? 1 : 0);
+        if (CT) {
+            up_fill_row<CT ? CT : 1>(reinterpret_cast<float (*)[32]>(H0), img, wi.k, u, ax, lane);
+            if (k1 != wi.k) up_fill_row<CT ? CT : 1>(reinterpret_cast<float (*)[32]>(H1), img, k1, u, ax, lane);
+        } else {                                           // run-time class count: batches of four classes
+            const float* r0 = img + (size_t)wi.k * u.w;
+            const float* r1 = img + (size_t)k1 * u.w;
+            for (int c0 = 0; c0 < C; c0 += 4) {
+                float a0[4], b0[4], a1[4], b1[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const size_t o = (size_t)min(c0 + j, C - 1) * pl;
+                    a0[j] = __ldg(r0 + o + ax.i0); b0[j] = __ldg(r0 + o + ax.i1);
+                    a1[j] = __ldg(r1 + o + ax.i0); b1[j] = __ldg(r1 + o + ax.i1);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c0 + j < C) {
+                        H0[(c0 + j) * 32 + lane] = up_row(ax.l0, a0[j], ax.l1, b0[j]);
+                        H1[(c0 + j) * 32 + lane] = up_row(ax.l0, a1[j], ax.l1, b1[j]);
+                    }
+            }
+        }
+        const float* Hb = (CT && k1 == wi.k) ? H0 : H1;     // (templated path: the bottom row is the top row at the last source row)
+        size_t px = (size_t)wi.n * HW + (size_t)wi.ya * u.W + X;
+        int lab_next = load_label<LT>(p.labels, px);
+        for (int Y = wi.ya; Y < wi.yb; ++Y, px += u.W) {
+            const int lab = lab_next;
+            if (Y + 1 < wi.yb) lab_next = load_label<LT>(p.labels, px + u.W);
+            const UpAxis ay = up_axis(u.ry, Y, u.h);
+            float best = up_col(ay.l0, H0[lane], ay.l1, Hb[lane]);
+            int arg = 0;
+            if (CT) {
+#pragma unroll
+                for (int c = 1; c < CT; ++c) argmax_step(up_col(ay.l0, H0[c * 32 + lane], ay.l1, Hb[c * 32 + lane]), c, best, arg);
+            } else {
+                for (int c = 1; c < C; ++c) argmax_step(up_col(ay.l0, H0[c * 32 + lane], ay.l1, Hb[c * 32 + lane]), c, best, arg);
+            }
+            if (!(p.has_drop && lab == p.drop)) {
+                if ((unsigned)lab < (unsigned)C) atomicAdd(s_cm + arg * C + lab, 1u);
+                else oob = 1;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < C * C; i += CMU_TPB)
+        if (s_cm[i]) atomicAdd(p.cm + i, (unsigned long long)s_cm[i]);
+    if (oob) atomicOr(p.status, STATUS_LABEL_OOB);
+}
+
+extern "C" int b200seg_confmat_up_supported(int32_t n, int32_t c, int32_t h, int32_t w, int32_t H, int32_t W) {
+    if (n < 0 || c < 1 || c > B200SEG_MAX_CLASSES || h < 1 || w < 1 || H < 1 || W < 1) return 0;
+    if ((long double)n * H * W >= (long double)(1u << 30) || (long double)n * c * h * w >= (long double)(1ull << 31)) return 0;
+    return W % 32 == 0 ? 1 : 0;
+}
+
+extern "C" int b200seg_confmat_up_accumulate(const float* lowres, int32_t h, int32_t w, const void* labels, int32_t label_dtype,
+                                             int32_t n, int32_t c, int32_t H, int32_t W, int64_t drop_label, int64_t* cm,
+                                             int32_t* status, void* stream) {
+    if (n < 0 || c < 1 || c > B200SEG_MAX_CLASSES || h < 1 || w < 1 || H < 1 || W < 1 ||
+        (long double)n * H * W >= (long double)(1u << 30) || (long double)n * c * h * w >= (long double)(1ull << 31)) {
+        b200seg_set_error("invalid shape: n_images=%d n_classes=%d %dx%d -> %dx%d", n, c, h, w, H, W);
+        return B200SEG_E_INVALID;
+    }
+    if (W % 32 != 0) {
+        b200seg_set_error("confusion matrix from low-resolution logits needs an output width that is a multiple of 32 (got %d)", W);
+        return B200SEG_E_UNSUPPORTED;
+    }
+    if (!lowres || !labels || !cm || !status) { b200seg_set_error("null pointer argument"); return B200SEG_E_INVALID; }
+    if (n == 0) return 0;
+    ConfmatUpParams p;
+    p.up = make_up_src(lowres, h, w, H, W);
+    p.labels = labels; p.N = n; p.C = c;
+    p.has_drop = (drop_label != B200SEG_NO_LABEL && drop_label >= INT_MIN && drop_label <= INT_MAX) ? 1 : 0;
+    p.drop = p.has_drop ? (int)drop_label : 0;
+    p.cm = (unsigned long long*)cm; p.status = status;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = b200seg_sm_count();
+    const size_t smem = (size_t)(CMU_TPB / 32) * 2 * c * 32 * sizeof(float);
+    int per_sm = (int)((224 * 1024) / (smem + 5 * 1024));
+    if (per_sm * CMU_TPB > 2048) per_sm = 2048 / CMU_TPB;
+    const long long items = (long long)(W / 32) * h * p.up.jmax * n;
+    long long grid = (long long)sms * per_sm;
+    if (grid * (CMU_TPB / 32) > items) grid = (items + CMU_TPB / 32 - 1) / (CMU_TPB / 32);
+    if (grid < 1) grid = 1;
+#define LAUNCH_CMU(CC)                                                                                            \
+    {                                                                                                             \
+        CUDA_TRY(cudaFuncSetAttribute(confmat_up_kernel<CC, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)smem));                                                                \
+        confmat_up_kernel<CC, LT><<<(int)grid, CMU_TPB, smem, st>>>(p);                                           \
+    }
+    DISPATCH_LABEL(label_dtype, {
+        if (c == 8) LAUNCH_CMU(8)
+        else if (c == 17) LAUNCH_CMU(17)
+        else if (c == 25) LAUNCH_CMU(25)
+        else LAUNCH_CMU(0)
+    });
+#undef LAUNCH_CMU
+    LAUNCH_CHECK("confmat_up_kernel");
     return 0;
 }
 

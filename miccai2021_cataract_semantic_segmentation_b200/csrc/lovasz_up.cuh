@@ -18,49 +18,6 @@
 
 #define UP_MAX_COLS 12               // source columns a 32-pixel strip may touch (scale factors >= ~3.2 along x)
 
-__device__ __forceinline__ int up_src_row(const UpSrc& u, int Y) { return (int)__fmul_rn(u.ry, (float)Y); }
-// smallest output row in [0, H] whose upper source row is >= k (the source index is monotone in the output row)
-__device__ __forceinline__ int up_first_row(const UpSrc& u, int k) {
-    if (k <= 0) return 0;
-    if (!(u.ry > 0.f)) return u.H;
-    float est = ceilf((float)k / u.ry);
-    int y = est >= (float)u.H ? u.H : (int)est;
-    while (y > 0 && up_src_row(u, y - 1) >= k) --y;
-    while (y < u.H && up_src_row(u, y) < k) ++y;
-    return y;
-}
-
-// Work item -> (image, strip, source-row interval, output rows [ya, yb)); false when the item is empty.
-struct UpItem { int n, sx, k, ya, yb; };
-__device__ __forceinline__ u32 up_item_count(const UpSrc& u, int N) { return (u32)(u.W / 32) * (u32)u.h * (u32)u.jmax * (u32)N; }
-__device__ __forceinline__ bool up_item(const UpSrc& u, u32 item, UpItem& it) {
-    const u32 nsx = (u32)(u.W / 32);
-    it.sx = (int)(item % nsx);
-    u32 t = item / nsx;
-    const int j = (int)(t % (u32)u.jmax);
-    t /= (u32)u.jmax;
-    it.k = (int)(t % (u32)u.h);
-    it.n = (int)(t / (u32)u.h);
-    const int y0 = up_first_row(u, it.k), y1 = up_first_row(u, it.k + 1);
-    it.ya = y0 + j * UP_ROWS_MAX;
-    it.yb = min(y1, it.ya + UP_ROWS_MAX);
-    return it.ya < it.yb;
-}
-
-// horizontal interpolation of source row `ys` of image n for the strip's 32 output columns: Hd[c][lane]
-template <int CT>
-__device__ __forceinline__ void up_fill_row(float (*Hd)[32], const float* __restrict__ img, int ys, const UpSrc& u,
-                                            const UpAxis& ax, int lane) {
-    const float* r = img + (size_t)ys * u.w;
-    const size_t pl = (size_t)u.h * u.w;
-#pragma unroll
-    for (int c = 0; c < CT; ++c) {
-        const float a = __ldg(r + ax.i0), b = __ldg(r + ax.i1);
-        Hd[c][lane] = up_row(ax.l0, a, ax.l1, b);
-        r += pl;
-    }
-}
-
 // ---- K1 -----------------------------------------------------------------------------------------------------------------------
 template <int CT, int TPB, typename LT>
 __global__ void __launch_bounds__(TPB) stats_kernel_up(LovaszParams p) {

@@ -72,6 +72,64 @@ __device__ __forceinline__ float up_logit(const UpSrc& u, int C, int n, int c, l
     return up_col(ay.l0, top, ay.l1, bot);
 }
 
+// ---- work decomposition shared by the fused kernels (lovasz_up.cuh, confmat.cu) -------------------------------------------
+__device__ __forceinline__ int up_src_row(const UpSrc& u, int Y) { return (int)__fmul_rn(u.ry, (float)Y); }
+// smallest output row in [0, H] whose upper source row is >= k (the source index is monotone in the output row)
+__device__ __forceinline__ int up_first_row(const UpSrc& u, int k) {
+    if (k <= 0) return 0;
+    if (!(u.ry > 0.f)) return u.H;
+    float est = ceilf((float)k / u.ry);
+    int y = est >= (float)u.H ? u.H : (int)est;
+    while (y > 0 && up_src_row(u, y - 1) >= k) --y;
+    while (y < u.H && up_src_row(u, y) < k) ++y;
+    return y;
+}
+
+// Work item -> (image, strip, source-row interval, output rows [ya, yb)); false when the item is empty.
+struct UpItem { int n, sx, k, ya, yb; };
+__device__ __forceinline__ u32 up_item_count(const UpSrc& u, int N) { return (u32)(u.W / 32) * (u32)u.h * (u32)u.jmax * (u32)N; }
+__device__ __forceinline__ bool up_item(const UpSrc& u, u32 item, UpItem& it) {
+    const u32 nsx = (u32)(u.W / 32);
+    it.sx = (int)(item % nsx);
+    u32 t = item / nsx;
+    const int j = (int)(t % (u32)u.jmax);
+    t /= (u32)u.jmax;
+    it.k = (int)(t % (u32)u.h);
+    it.n = (int)(t / (u32)u.h);
+    const int y0 = up_first_row(u, it.k), y1 = up_first_row(u, it.k + 1);
+    it.ya = y0 + j * UP_ROWS_MAX;
+    it.yb = min(y1, it.ya + UP_ROWS_MAX);
+    return it.ya < it.yb;
+}
+
+// horizontal interpolation of source row `ys` of image n for the strip's 32 output columns: Hd[c][lane].
+// All 2*CT loads are issued before the first use.  Left to itself the compiler sinks every load next to its multiply-add (32
+// registers, ~16 loads in flight): issue is in order, so the warp stalls at the first use and the row costs several dependent
+// L2 round trips -- 48 % of the samples of the confusion-matrix kernel.  The loads are volatile (kept in program order) and
+// both weights are made to depend on the last pair, so no multiply-add can be scheduled before the last load is out.
+__device__ __forceinline__ float ldg_ordered(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+template <int CT>
+__device__ __forceinline__ void up_fill_row(float (*Hd)[32], const float* __restrict__ img, int ys, const UpSrc& u,
+                                            const UpAxis& ax, int lane) {
+    const size_t pl = (size_t)u.h * u.w;
+    const float* p0 = img + (size_t)ys * u.w + ax.i0;
+    const float* p1 = img + (size_t)ys * u.w + ax.i1;
+    float a[CT], b[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) { a[c] = ldg_ordered(p0); b[c] = ldg_ordered(p1); p0 += pl; p1 += pl; }
+    // zero, but not to the assembler: a data dependency of both weights on the last pair of loads
+    u32 z;                                                 // (popc(a) + popc(b)) >> 7 == 0; opaque to both compiler stages
+    asm volatile("{\n\t.reg .u32 t0, t1;\n\tpopc.b32 t0, %1;\n\tpopc.b32 t1, %2;\n\tadd.u32 t0, t0, t1;\n\tshr.u32 %0, t0, 7;\n\t}"
+                 : "=r"(z) : "r"(__float_as_uint(a[CT - 1])), "r"(__float_as_uint(b[CT - 1])));
+    const float l0 = __uint_as_float(__float_as_uint(ax.l0) | z), l1 = __uint_as_float(__float_as_uint(ax.l1) | z);
+#pragma unroll
+    for (int c = 0; c < CT; ++c) Hd[c][lane] = up_row(l0, a[c], l1, b[c]);
+}
+
 // debug / test kernel: materialise the upsampled logits with a chosen contraction pattern
 template <int LFMA, int INNER, int OUTER>
 __device__ __forceinline__ float up_value_t(const UpSrc& u, const float* pl, int Y, int X) {
@@ -82,7 +140,7 @@ __device__ __forceinline__ float up_value_t(const UpSrc& u, const float* pl, int
     const float bot = up_mix_t<INNER>(ax.l0, r1[ax.i0], ax.l1, r1[ax.i1]);
     return up_mix_t<OUTER>(ay.l0, top, ay.l1, bot);
 }
-__global__ void upsample_debug_kernel(UpSrc u, long long planes, float* __restrict__ out, int pattern) {
+static __global__ void upsample_debug_kernel(UpSrc u, long long planes, float* __restrict__ out, int pattern) {
     const long long HW = (long long)u.H * u.W, total = planes * HW;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long pc = i / HW, q = i - pc * HW;

@@ -10,7 +10,7 @@ import torch.nn as nn
 from . import _native
 from .class_info import CLASS_INFO
 from .lovasz import LovaszSoftmax, _PRESENT, _resolve_classes, lovasz_softmax, lovasz_softmax_ce
-from .metrics import (accumulate_confusion_matrix, confusion_drop_label, metrics_summary,
+from .metrics import (accumulate_confusion_matrix, accumulate_confusion_matrix_upsampled, confusion_drop_label, metrics_summary,
                       raise_if_label_out_of_range)
 
 
@@ -45,6 +45,11 @@ class SegmentationMeter:
 
     def update(self, prediction: torch.Tensor, target: torch.Tensor):
         accumulate_confusion_matrix(prediction, target, self.cm, self.status, self.drop_label)
+
+    def update_upsampled(self, low_res: torch.Tensor, target: torch.Tensor):
+        """``update(F.interpolate(low_res, target.shape[-2:], 'bilinear', align_corners=True), target)`` without the upsampled
+        logits: for validation loops whose model hands over its stride-8 / stride-4 logits (models/OCR.py:126-131)."""
+        accumulate_confusion_matrix_upsampled(low_res, target, self.cm, self.status, self.drop_label)
 
     def all_reduce(self, group=None, async_op: bool = False):
         """Sum the matrix over the data-parallel ranks.  ``async_op=True``: returns a handle whose ``wait()`` must be

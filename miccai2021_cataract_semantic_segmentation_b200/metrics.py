@@ -51,6 +51,37 @@ def accumulate_confusion_matrix(prediction: torch.Tensor, target: torch.Tensor, 
             status.data_ptr(), _native.stream_ptr(pred.device)), "b200seg_confmat_accumulate")
 
 
+# calls of accumulate_confusion_matrix_upsampled that went through F.interpolate (output width not a multiple of 32)
+UPSAMPLED_FALLBACK_COUNTS = {"interpolate_torch": 0}
+
+
+def accumulate_confusion_matrix_upsampled(low_res: torch.Tensor, target: torch.Tensor, cm: torch.Tensor,
+                                          status: torch.Tensor, drop_label=None) -> None:
+    """``accumulate_confusion_matrix(F.interpolate(low_res, target.shape[-2:], mode='bilinear', align_corners=True), ...)``
+    without forming the upsampled logits (models/OCR.py:126-131 followed by utils/torch_utils.py:221-241): the kernel
+    interpolates in shared memory with ATen's arithmetic, so the matrix is the same bit for bit.  Asynchronous."""
+    _native.require_cuda(low_res, target, cm, status)
+    if low_res.dim() != 4 or target.dim() != 3 or target.shape[0] != low_res.shape[0]:
+        raise ValueError("low_res must be [N, C, h, w] and target [N, H, W]")
+    n, c, h, w = low_res.shape
+    big_h, big_w = target.shape[-2:]
+    low = low_res.detach()
+    low = (low if low.dtype == torch.float32 else low.float()).contiguous()
+    tgt = _native.as_label_tensor(target.detach())
+    assert cm.dtype == torch.int64 and cm.is_contiguous() and tuple(cm.shape) == (c, c)
+    assert status.dtype == torch.int32
+    lib = _native.load()
+    if not lib.b200seg_confmat_up_supported(n, c, h, w, big_h, big_w):
+        UPSAMPLED_FALLBACK_COUNTS["interpolate_torch"] += 1
+        full = torch.nn.functional.interpolate(low, size=(big_h, big_w), mode="bilinear", align_corners=True)
+        return accumulate_confusion_matrix(full, tgt, cm, status, drop_label)
+    drop = _native.NO_LABEL if drop_label is None else int(drop_label)
+    with torch.cuda.device(low.device):
+        _native.check(lib.b200seg_confmat_up_accumulate(
+            low.data_ptr(), h, w, tgt.data_ptr(), _native.label_code(tgt), n, c, big_h, big_w, drop, cm.data_ptr(),
+            status.data_ptr(), _native.stream_ptr(low.device)), "b200seg_confmat_up_accumulate")
+
+
 def raise_if_label_out_of_range(status: torch.Tensor):
     """Synchronises.  Mirrors the RuntimeError torch's one_hot raises inside the reference."""
     s = int(status.item())

@@ -175,6 +175,52 @@ def test_full_size_training_shape(b200):
     assert torch.equal(cm_f, ref_cm)
 
 
+@pytest.mark.parametrize("shape", [(2, 25, 68, 120, 544, 960), (2, 17, 34, 60, 136, 224), (3, 8, 9, 11, 75, 96), (1, 12, 5, 7, 33, 64),
+                                   (1, 25, 1, 1, 8, 32), (2, 25, 136, 240, 272, 480), (1, 3, 40, 50, 30, 32)])
+@pytest.mark.parametrize("ldt", [torch.int64, torch.int32, torch.uint8])
+def test_confusion_matrix_from_low_resolution_logits(b200, shape, ldt):
+    """SegmentationMeter.update_upsampled == update(F.interpolate(...)) bit for bit (torch_utils.py:221-241 after OCR.py:126),
+    any class count and scale, near-ties from exactly equal low-resolution logits, the ignore label dropped, NaN pixels."""
+    n, c, h, w, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(5 + c + h)
+    low = torch.randn((n, c, h, w), generator=g, device="cuda")
+    low[:, : c // 2] = (low[:, : c // 2] * 2).round() / 2               # plateaus: exact ties after interpolation
+    if h > 2 and w > 2:
+        low[0, 1, 1, 1] = float("nan")
+    exp = {8: 1, 17: 2, 25: 3}.get(c, 1)
+    y = torch.randint(0, c + (1 if c in (17, 25) else 0), (n, H, W), generator=g, device="cuda").to(ldt)
+    m1 = b200.SegmentationMeter(exp, c)
+    m2 = b200.SegmentationMeter(exp, c)
+    m1.update_upsampled(low, y)
+    m1.update_upsampled(low, y)                                          # accumulates
+    full = _up(low, (H, W))
+    m2.update(full, y)
+    m2.update(full, y)
+    assert torch.equal(m1.cm, m2.cm) and int(m1.cm.sum()) > 0
+    pred = full.argmax(1)
+    keep = y.long() < c
+    ref = 2 * torch.bincount((pred[keep] * c + y.long()[keep]), minlength=c * c).view(c, c)
+    assert torch.equal(m1.cm, ref)
+    m1.check()
+
+
+def test_confusion_matrix_upsampled_falls_back_for_odd_widths(b200):
+    from miccai2021_cataract_semantic_segmentation_b200 import metrics
+    low = torch.randn((1, 8, 6, 7), device="cuda")
+    y = torch.randint(0, 8, (1, 24, 40), device="cuda")
+    before = metrics.UPSAMPLED_FALLBACK_COUNTS["interpolate_torch"]
+    m1, m2 = b200.SegmentationMeter(1, 8), b200.SegmentationMeter(1, 8)
+    m1.update_upsampled(low, y)
+    m2.update(_up(low, (24, 40)), y)
+    assert metrics.UPSAMPLED_FALLBACK_COUNTS["interpolate_torch"] == before + 1
+    assert torch.equal(m1.cm, m2.cm)
+    y[0, 0, 0] = 9                                                        # out-of-range label: status word, raised by check()
+    m3 = b200.SegmentationMeter(1, 8)
+    m3.update_upsampled(torch.randn((1, 8, 6, 8), device="cuda"), torch.full((1, 24, 64), 9, device="cuda"))
+    with pytest.raises(RuntimeError):
+        m3.check()
+
+
 def test_unsupported_shapes_fall_back_and_count(b200):
     from miccai2021_cataract_semantic_segmentation_b200 import upsampled
     n, c, h, w, H, W = 1, 5, 8, 8, 32, 40            # C = 5 and W % 32 != 0: outside the fused kernels
