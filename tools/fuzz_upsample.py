@@ -75,6 +75,9 @@ for case in range(n_cases):
         a, b = float(loss_f.detach()), float(loss_u.detach())
         assert abs(a - b) <= 1e-6 * max(abs(b), 1e-30), f"loss {a} vs {b}"
         assert torch.equal(cm_f, cm_u) and int(st_f) == int(st_u), "confusion matrix / status differ"
+        cm_s = torch.zeros((c, c), dtype=torch.int64, device="cuda"); st_s = torch.zeros(1, dtype=torch.int32, device="cuda")
+        b200.accumulate_confusion_matrix_upsampled(lowd, yd, cm_s, st_s, drop)      # the standalone kernel on the same pixels
+        assert torch.equal(cm_s, cm_u) and int(st_s) == int(st_u), "confusion matrix from low-resolution logits differs"
         if loss_f.requires_grad and loss_u.requires_grad:
             loss_f.backward(); loss_u.backward()
             gmax = float(lu.grad.abs().max())

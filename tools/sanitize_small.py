@@ -63,6 +63,12 @@ for (n, c, h, w, H, W, kw) in [(2, 25, 9, 12, 72, 96, {}), (2, 17, 16, 16, 64, 6
         tot = res[0] + res[1] if isinstance(res, tuple) else res
         tot.backward()
         torch.cuda.synchronize()
-    print("upsampled", n, c, h, w, H, W, kw, float(tot.detach()), float(low.grad.abs().max()))
+    mu = b200.SegmentationMeter({8: 1, 17: 2, 25: 3}[c], c)
+    mu.update_upsampled(low, yu)                        # confusion matrix straight from the low-resolution logits
+    torch.cuda.synchronize()
+    print("upsampled", n, c, h, w, H, W, kw, float(tot.detach()), float(low.grad.abs().max()), int(mu.cm.sum()))
 _native.set_tuning(emit_path=0)
+mg = b200.SegmentationMeter(1, 12)                      # run-time class count
+mg.update_upsampled(torch.randn((2, 12, 5, 7), generator=g).cuda(), torch.randint(0, 12, (2, 33, 64), generator=g).cuda().int())
+torch.cuda.synchronize()
 print("done")
