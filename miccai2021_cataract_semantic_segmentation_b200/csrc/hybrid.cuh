@@ -81,10 +81,29 @@ __global__ void __launch_bounds__(SORT_TPB) hyb_count_kernel(SortArgs a, HybArgs
     const u32 t0 = (u32)((u64)total_tiles * blockIdx.x / gridDim.x), t1 = (u32)((u64)total_tiles * (blockIdx.x + 1) / gridDim.x);
     int cur_seg = -1;
     u32 ntl = 0, L = 0;
+    // software pipeline: the keys of tile t + 1 (and the descriptor of tile t + 2) are requested before the shared-memory
+    // atomics of tile t, so a CTA's tiles do not each pay the descriptor -> keys round trips one after the other
+    auto load_keys = [&](const uint4& d, u32 (&k)[SORT_KPT]) {
+        const u32* __restrict__ kp = a.keys[0] + (size_t)d.x * a.cap + d.y;
+#pragma unroll
+        for (int j = 0; j < SORT_KPT; ++j) {
+            const u32 idx = j * SORT_TPB + tid;
+            k[j] = idx < d.z ? kp[idx] : 0u;
+        }
+    };
+    const uint4 none = make_uint4(0, 0, 0, 0);
+    uint4 d4 = t0 < t1 ? a.tile_desc[t0] : none;
+    uint4 dn = t0 + 1 < t1 ? a.tile_desc[t0 + 1] : none;
+    u32 key[SORT_KPT];
+    if (t0 < t1) load_keys(d4, key);
     for (u32 t = t0; t < t1; ++t) {
-        const uint4 d4 = a.tile_desc[t];
+        const uint4 dnn = t + 2 < t1 ? a.tile_desc[t + 2] : none;
+        u32 nkey[SORT_KPT];
+#pragma unroll
+        for (int j = 0; j < SORT_KPT; ++j) nkey[j] = 0u;
+        if (t + 1 < t1) load_keys(dn, nkey);
         const int seg = (int)d4.x;
-        const u32 off = d4.y, n = d4.z;
+        const u32 n = d4.z;
         if (seg != cur_seg) {
             if (cur_seg >= 0) hyb_count_flush(a, h, s_hist, s_warp, &s_last, cur_seg, ntl);
             const HybPlan pl = hyb_plan(a.seg_bits[seg], a.seg_count[seg]);
@@ -96,13 +115,6 @@ __global__ void __launch_bounds__(SORT_TPB) hyb_count_kernel(SortArgs a, HybArgs
             ntl = 0;
         }
         __syncthreads();                                   // bins cleared
-        const u32* __restrict__ kp = a.keys[0] + (size_t)seg * a.cap + off;
-        u32 key[SORT_KPT];
-#pragma unroll
-        for (int k = 0; k < SORT_KPT; ++k) {
-            const u32 idx = k * SORT_TPB + tid;
-            key[k] = idx < n ? kp[idx] : 0u;
-        }
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
             if (k * SORT_TPB + tid < n) {                  // (the foreground flag rides in bit 31 of the key: the values are not read)
@@ -112,6 +124,9 @@ __global__ void __launch_bounds__(SORT_TPB) hyb_count_kernel(SortArgs a, HybArgs
             }
         }
         ++ntl;
+        d4 = dn; dn = dnn;
+#pragma unroll
+        for (int j = 0; j < SORT_KPT; ++j) key[j] = nkey[j];
     }
     if (cur_seg >= 0) hyb_count_flush(a, h, s_hist, s_warp, &s_last, cur_seg, ntl);
 }

@@ -2311,7 +2311,7 @@ static int hybrid_enqueue(const LovaszParams& p, const SortArgs& a, const HybArg
         LAUNCH_CHECK("sort_prepare_kernel");
     }
     b200seg_stage(4, st);
-    const u32 cgrid = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;
+    const u32 cgrid = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;   // 3 CTAs per SM by shared memory; 1x / 2x measured slower
     hyb_count_kernel<<<cgrid, SORT_TPB, 2 * HYB_MAX_BINS * sizeof(u32), st>>>(a, h, L.max_tiles);
     LAUNCH_CHECK("hyb_count_kernel");
     b200seg_stage(5, st);
