@@ -235,9 +235,12 @@ int b200seg_sort_segments(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_o
  *                   with the Jaccard gradient (segments whose buckets overflow shared memory fall back to 1);
  *                   1: stable LSD radix sort by (key, value) in seven passes + a separate Jaccard kernel
  *   "sort_match"    (LSD path) 2 (default) MATCH.ANY peer masks in the top digit pass only; 0 ballots; 1 MATCH.ANY
+ *   "pdl"           1 (default) the kernels of the forward chain are launched with programmatic dependent launch
+ *                   (cudaLaunchAttributeProgrammaticStreamSerialization): a kernel's CTAs are scheduled while the previous
+ *                   kernel drains and wait (griddepcontrol.wait) for its completion before touching memory; 0 plain launches
  *   "dbg"           timing experiments only (skips work: results become wrong)
  * Initial values come from the environment variables B200SEG_INTERLEAVE, B200SEG_STATS_VARIANT,
- * B200SEG_EMIT_PATH, B200SEG_SORT_PATH, B200SEG_SORT_MATCH, B200SEG_DBG.
+ * B200SEG_EMIT_PATH, B200SEG_SORT_PATH, B200SEG_SORT_MATCH, B200SEG_PDL, B200SEG_DBG.
  * ------------------------------------------------------------------------------------------------ */
 int b200seg_set_tuning(const char* key, int32_t value);
 

@@ -34,7 +34,7 @@ static int env_int(const char* name, int dflt) {
 B200segTuning& b200seg_tuning() {
     static B200segTuning t = {env_int("B200SEG_INTERLEAVE", 1), env_int("B200SEG_STATS_VARIANT", 0),
                               env_int("B200SEG_EMIT_PATH", 0), env_int("B200SEG_SORT_MATCH", 2), env_int("B200SEG_SORT_PATH", 0),
-                              env_int("B200SEG_DBG", 0)};
+                              env_int("B200SEG_DBG", 0), env_int("B200SEG_PDL", 1)};
     return t;
 }
 extern "C" int b200seg_set_tuning(const char* key, int32_t value) {
@@ -46,6 +46,7 @@ extern "C" int b200seg_set_tuning(const char* key, int32_t value) {
     else if (!strcmp(key, "sort_match")) t.sort_match = value;
     else if (!strcmp(key, "sort_path")) t.sort_path = value;
     else if (!strcmp(key, "dbg")) t.dbg = value;
+    else if (!strcmp(key, "pdl")) t.pdl = value;
     else { b200seg_set_error("b200seg_set_tuning: unknown key '%s'", key); return B200SEG_E_INVALID; }
     return 0;
 }

@@ -73,6 +73,7 @@ __device__ __forceinline__ void hyb_count_flush(const SortArgs& a, const HybArgs
 }
 
 __global__ void __launch_bounds__(SORT_TPB) hyb_count_kernel(SortArgs a, HybArgs h, u32 total_bound) {
+    pdl_enter();
     extern __shared__ __align__(16) u32 s_hist[];          // [2][HYB_MAX_BINS]: elements, foreground flags
     __shared__ u32 s_warp[2 * SORT_WARPS];
     __shared__ u32 s_last;
@@ -142,6 +143,7 @@ struct PartSmem {
 };
 
 __global__ void __launch_bounds__(SORT_TPB, 3) hyb_partition_kernel(SortArgs a, HybArgs h, u32 total_bound) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PartSmem& S = *reinterpret_cast<PartSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

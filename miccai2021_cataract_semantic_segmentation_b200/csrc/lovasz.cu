@@ -455,6 +455,7 @@ __device__ __forceinline__ void stats_pixel(const LovaszParams& p, const float (
 
 template <int CT, int TPB, int STAGES, typename LT>
 __global__ void __launch_bounds__(TPB) stats_kernel_async(LovaszParams p) {
+    pdl_enter();
     using W = WarpTile<CT, 1>;
     constexpr int WT = W::WT, NW = TPB / 32;
     constexpr int LAB_BYTES = WT * (int)sizeof(LT);       // label bytes of one tile
@@ -839,6 +840,7 @@ __global__ void __launch_bounds__(256) absent_max_kernel(LovaszParams p) {
 #define DECIDE_BLOCKS 32
 #define DECIDE_TPB 256
 __global__ void __launch_bounds__(DECIDE_TPB) finalize_decide_kernel(LovaszParams p) {
+    pdl_enter();
     __shared__ float s_tmin;
     __shared__ float s_sorted[B200SEG_MAX_CLASSES];               // thresholds of the group, ascending
     __shared__ u32 s_slow, s_n;
@@ -1181,6 +1183,7 @@ __device__ __forceinline__ void emit_tile(const LovaszParams& p, const float (*T
 
 template <int CT, int TPB>
 __global__ void __launch_bounds__(TPB) emit_kernel_async(LovaszParams p) {
+    pdl_enter();
     if (p.flags[0] != EMIT_PATH_STREAM) return;           // ctrl is zeroed per call: the default path is this one
     using W = WarpTile<CT, 1>;
     constexpr int WT = W::WT, NW = TPB / 32, STAGES = 2;  // the prefetch cursor runs exactly one tile ahead
@@ -1299,6 +1302,7 @@ struct EctaSmem {
 
 template <int CT, bool UP>
 __global__ void __launch_bounds__(ECTA_TPB, ECTA_MINB) emit_kernel_cta(LovaszParams p) {
+    pdl_enter();
     if (p.flags[0] != EMIT_PATH_RECORDS) return;
     extern __shared__ __align__(16) unsigned char ecta_smem_raw[];
     EctaSmem& S = *reinterpret_cast<EctaSmem*>(ecta_smem_raw);
@@ -1762,6 +1766,7 @@ __device__ __noinline__ double loc_heavy_unit(const LovaszParams& p, LocSmem& S,
 }
 
 __global__ void __launch_bounds__(LOC_TPB, 2) hyb_local_kernel(LovaszParams p, SortArgs a, HybArgs h, u32 max_tiles) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char loc_smem_raw[];
     LocSmem& S = *reinterpret_cast<LocSmem*>(loc_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -2307,22 +2312,22 @@ static int hybrid_enqueue(const LovaszParams& p, const SortArgs& a, const HybArg
     const int sms = b200seg_sm_count();
     {
         const int pgrid = a.n_seg < sms ? a.n_seg : sms;     // CTA 0 plans the tiles, all of them clear the bucket tables
-        sort_prepare_kernel<<<pgrid, SORT_PREP_TPB, 0, st>>>(a, h, L.max_tiles);
+        CUDA_TRY(launch_chained(sort_prepare_kernel, dim3(pgrid), dim3(SORT_PREP_TPB), 0, st, a, h, L.max_tiles));
         LAUNCH_CHECK("sort_prepare_kernel");
     }
     b200seg_stage(4, st);
     const u32 cgrid = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;   // 3 CTAs per SM by shared memory; 1x / 2x measured slower
-    hyb_count_kernel<<<cgrid, SORT_TPB, 2 * HYB_MAX_BINS * sizeof(u32), st>>>(a, h, L.max_tiles);
+    CUDA_TRY(launch_chained(hyb_count_kernel, dim3(cgrid), dim3(SORT_TPB), 2 * HYB_MAX_BINS * sizeof(u32), st, a, h, L.max_tiles));
     LAUNCH_CHECK("hyb_count_kernel");
     b200seg_stage(5, st);
     const u32 pgrid2 = L.max_tiles < (u32)sms * 3 ? L.max_tiles : (u32)sms * 3;
-    hyb_partition_kernel<<<pgrid2, SORT_TPB, sizeof(PartSmem), st>>>(a, h, L.max_tiles);
+    CUDA_TRY(launch_chained(hyb_partition_kernel, dim3(pgrid2), dim3(SORT_TPB), sizeof(PartSmem), st, a, h, L.max_tiles));
     LAUNCH_CHECK("hyb_partition_kernel");
     b200seg_stage(6, st);
     if (p.dbg & 128) return 0;                             // (debugging: stop after the partition)
     const u32 units = L.max_tiles * LOC_PER_SORT_TILE;
     const u32 lgrid = units < (u32)sms * 2 ? units : (u32)sms * 2;
-    hyb_local_kernel<<<lgrid, LOC_TPB, sizeof(LocSmem), st>>>(p, a, h, L.max_tiles);
+    CUDA_TRY(launch_chained(hyb_local_kernel, dim3(lgrid), dim3(LOC_TPB), sizeof(LocSmem), st, p, a, h, L.max_tiles));
     LAUNCH_CHECK("hyb_local_kernel");
     b200seg_stage(7, st);
     {   // cooperative: the grid barriers between its phases need the whole grid resident
@@ -2585,7 +2590,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
     const EmitGeom Gr = emit_geom(n, hw, per_image, ECTA_TILE);
     p.geo_stream = EmitGeomDev{(int)Gs.n_runs, (int)Gs.tpc};
     p.geo_rec = EmitGeomDev{(int)Gr.n_runs, (int)Gr.tpc};
-    finalize_decide_kernel<<<DECIDE_BLOCKS, DECIDE_TPB, 0, st>>>(p);
+    CUDA_TRY(launch_chained(finalize_decide_kernel, dim3(DECIDE_BLOCKS), dim3(DECIDE_TPB), 0, st, p));
     LAUNCH_CHECK("finalize_decide_kernel");
     b200seg_stage(2, st);
 
@@ -2603,7 +2608,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
             emit_kernel_cta<CC, true><<<grid, ECTA_TPB, smem, st>>>(p);                                              \
         } else {                                                                                                     \
             CUDA_TRY(cudaFuncSetAttribute(emit_kernel_cta<CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            emit_kernel_cta<CC, false><<<grid, ECTA_TPB, smem, st>>>(p);                                             \
+            CUDA_TRY(launch_chained(emit_kernel_cta<CC, false>, dim3(grid), dim3(ECTA_TPB), smem, st, p));           \
         }                                                                                                            \
     }
             if (c == 8) LAUNCH_EMIT_CTA(8)
@@ -2638,7 +2643,7 @@ static int lovasz_forward_impl(const float* logits, const void* labels, int32_t 
         if (per_sm * ET > 2048) per_sm = 2048 / ET;                                                             \
         long long grid = (long long)sms * per_sm;                                                               \
         if (grid * (ET / 32) > chunks) grid = (chunks + ET / 32 - 1) / (ET / 32);                               \
-        emit_kernel_async<CC, ET><<<(int)grid, ET, smem, st>>>(p);                                              \
+        CUDA_TRY(launch_chained(emit_kernel_async<CC, ET>, dim3((unsigned)grid), dim3(ET), smem, st, p));       \
     }
             if (c == 8) LAUNCH_EMIT_ASYNC(8)
             else if (c == 17) LAUNCH_EMIT_ASYNC(17)

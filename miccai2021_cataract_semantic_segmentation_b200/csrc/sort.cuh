@@ -156,6 +156,7 @@ __device__ __forceinline__ int sort_find_segment(const u32* tile_start, int n_se
 //              of every later kernel is a single 16-byte load instead of a chain of dependent ones
 #define SORT_PREP_TPB 1024
 __global__ void __launch_bounds__(SORT_PREP_TPB) sort_prepare_kernel(SortArgs a, HybArgs h, u32 max_tiles) {
+    pdl_enter();
     __shared__ u32 s_warp[32];
     __shared__ u32 s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

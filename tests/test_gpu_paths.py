@@ -14,7 +14,7 @@ from test_gpu_parity import CASES, _blocky, _d1
 
 pytestmark = pytest.mark.gpu
 
-DEFAULTS = dict(interleave=1, stats_variant=0, emit_path=0, sort_match=2, sort_path=0, dbg=0)
+DEFAULTS = dict(interleave=1, stats_variant=0, emit_path=0, sort_match=2, sort_path=0, dbg=0, pdl=1)
 VARIANTS = [
     ("emit_records", dict(emit_path=1)),
     ("emit_stream", dict(emit_path=2)),
@@ -30,6 +30,7 @@ VARIANTS = [
     ("sort_lsd", dict(sort_path=1)),
     ("sort_lsd_ballots", dict(sort_path=1, sort_match=0)),
     ("sort_lsd_stream", dict(sort_path=1, emit_path=2)),
+    ("plain_launches", dict(pdl=0)),
 ]
 PATH_CASES = [c for c in CASES if c[0] in ("d1_c8_flat", "d1_c17_per_image", "d1_c25_flat", "d1_c25_flat_ignore",
                                            "d1_c25_all", "d2_c25_flat", "d2_c17_per_image_ignore", "d2_c25_list")]
